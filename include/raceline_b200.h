@@ -1,0 +1,233 @@
+/*
+ * raceline_b200.h -- C ABI of the B200-native batched raceline solver.
+ *
+ * This is the drop-in boundary for the two solver stages of
+ * tjsdn3065/Practice_path_planning_for_formula_student_driverless:
+ *
+ *   raceline_min_curv::compute_min_curvature_raceline   (src/main.cpp:683-764)
+ *   raceline_min_time::compute_min_time_raceline        (src/main.cpp:905-1052)
+ *
+ * The reference has no FFI/plugin layer; its boundary is those two in-TU
+ * functions, called from pipeline::compute_raceline_and_save (main.cpp:1347)
+ * and pipeline::compute_mintime_and_save (main.cpp:1397).  Every entry point
+ * below names the reference interface it replaces.  Plain pointers and sizes
+ * only; nothing throws across this boundary; there is no CPU fallback -- a
+ * call without a usable sm_100a device returns RL_ERR_NODEVICE / RL_ERR_CUDA.
+ *
+ * Arithmetic is IEEE FP64 throughout (the reference is double-only).
+ */
+#ifndef RACELINE_B200_H
+#define RACELINE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_ABI_VERSION 1
+
+/* job stages (one solve of the BASELINE metric = one MINCURV job + one MINTIME job) */
+#define RL_STAGE_MINCURV 1 /* compute_min_curvature_raceline, main.cpp:683 */
+#define RL_STAGE_MINTIME 2 /* compute_min_time_raceline,      main.cpp:905 */
+
+/* per-outer-iteration log depth kept in rl_job_stats (cfg max_outer_iters defaults to 14) */
+#define RL_MAX_OUTER_LOG 32
+
+/* status codes (0 = ok, negative = error) */
+#define RL_OK 0
+#define RL_ERR_ARG (-1)         /* null pointer, negative size, index out of range */
+#define RL_ERR_CUDA (-2)        /* a CUDA runtime call or kernel failed */
+#define RL_ERR_UNSUPPORTED (-3) /* problem shape outside what the kernels cover */
+#define RL_ERR_NOMEM (-4)       /* host or device allocation failed */
+#define RL_ERR_NODEVICE (-5)    /* no CUDA device / not an sm_100 part */
+
+/*
+ * Config fields the hot path reads (cfg::Config, main.cpp:47-119), one struct
+ * per (track x config) problem so a Config sweep is just an array of these.
+ * Defaults: rl_default_params().  NB the reference evaluates
+ * a_total_max = mu*9.81 once at construction (main.cpp:102); a sweep over mu
+ * must set a_total_max itself.
+ */
+typedef struct rl_params {
+    double veh_width_arg;    /* the solver's veh_width argument: initial corridor (main.cpp:706, 930) */
+    double veh_width_m;      /* cfg veh_width_m: corridor updates (main.cpp:753, 1037)               */
+    double safety_margin_m;  /* main.cpp:78  */
+    double lambda_smooth;    /* main.cpp:81  */
+    double step_init;        /* main.cpp:84  */
+    double step_min;         /* main.cpp:85  */
+    double armijo_c;         /* main.cpp:86  */
+    double kappa_eps;        /* main.cpp:89  */
+    double v_cap_mps;        /* main.cpp:90  */
+    double mass_kg;          /* main.cpp:93  */
+    double Cd;               /* main.cpp:94  */
+    double A_front_m2;       /* main.cpp:95  */
+    double rho_air;          /* main.cpp:96  */
+    double c_rr;             /* main.cpp:97  */
+    double P_max_W;          /* main.cpp:98  */
+    double a_total_max;      /* main.cpp:102 */
+    double a_lat_max;        /* main.cpp:103 */
+    double a_long_acc_cap;   /* main.cpp:104 */
+    double a_long_brake_cap; /* main.cpp:105 */
+    double w_time_gain;      /* main.cpp:108 */
+    double time_gamma_power; /* main.cpp:109 */
+    double inv_v_gain;       /* main.cpp:111 */
+    int32_t max_outer_iters; /* main.cpp:82  */
+    int32_t max_inner_iters; /* main.cpp:83  */
+    int32_t max_vpass_iters; /* main.cpp:112 */
+    int32_t time_weight_use_inv_v; /* main.cpp:110 */
+    int32_t use_total_ge_lat;      /* main.cpp:113 */
+    int32_t reserved;
+} rl_params;
+
+/* one unit of work: solve stage `stage` of track `track` under params[param] */
+typedef struct rl_job {
+    int32_t track;
+    int32_t param;
+    int32_t stage; /* RL_STAGE_MINCURV or RL_STAGE_MINTIME */
+    int32_t reserved;
+} rl_job;
+
+/*
+ * Per-job counters.  The reference only prints these to stderr ("[GN k] J0=",
+ * main.cpp:725; "[MT k] J0= .. t=", 998; "[PG] .. bt=", 1019-1022) and logs no
+ * backtracks at all for min-curv; here they are returned.
+ */
+typedef struct rl_job_stats {
+    int32_t status;       /* RL_OK or an error for this job                    */
+    int32_t n;            /* samples                                            */
+    int32_t outer_done;   /* outer linearisations executed                      */
+    int32_t accepted;     /* accepted PGD steps, all outers (main.cpp:735)      */
+    int32_t backtracks;   /* Armijo step halvings, all outers (main.cpp:737)    */
+    int32_t evals;        /* cost/grad evaluations (main.cpp:724, 732)          */
+    int32_t vpass_rounds; /* device diagnostic: relaxation rounds of the v(s) passes */
+    int32_t reserved;
+    int64_t ray_tests;    /* device diagnostic: exact FP64 ray/segment tests run */
+    double lap_time;      /* min-time: final predicted lap (main.cpp:1047); else 0 */
+    double J0[RL_MAX_OUTER_LOG];        /* cost at alpha=0 per outer (main.cpp:724, 997)  */
+    double Jend[RL_MAX_OUTER_LOG];      /* cost after the last accepted step per outer    */
+    double lap_outer[RL_MAX_OUTER_LOG]; /* min-time: VP.lap_time per outer (main.cpp:998) */
+    int32_t acc_outer[RL_MAX_OUTER_LOG]; /* accepted steps per outer */
+    int32_t bt_outer[RL_MAX_OUTER_LOG];  /* backtracks per outer     */
+} rl_job_stats;
+
+/*
+ * A batch of problems in packed (CSR-style) layout.  All pointers are HOST
+ * pointers for the host entry points (pinned memory makes the copies
+ * asynchronous) and are only read.
+ *
+ *   track t: centre samples  center_xy[2*samp_off[t] .. 2*samp_off[t+1])   (x,y interleaved,
+ *            the reference's vector<Vec2>, closing duplicate already dropped, main.cpp:1681-1683)
+ *            inner segments  seg[4*seg_off[2t]   .. 4*seg_off[2t+1])       (x0,y0,x1,y1 per segment,
+ *            outer segments  seg[4*seg_off[2t+1] .. 4*seg_off[2t+2])        the reference's
+ *                                                                           vector<pair<Vec2,Vec2>>,
+ *                                                                           edges::ringEdges main.cpp:251)
+ *            L = track_L[t] (CL.L), closed = track_closed[t] (cfg is_closed_track)
+ */
+typedef struct rl_batch_desc {
+    int32_t n_tracks;
+    int32_t n_params;
+    int32_t n_jobs;
+    int32_t reserved;
+    const int64_t* samp_off;      /* [n_tracks+1]   */
+    const int64_t* seg_off;       /* [2*n_tracks+1] */
+    const double* center_xy;      /* [2*samp_off[n_tracks]]   */
+    const double* seg;            /* [4*seg_off[2*n_tracks]]  */
+    const double* track_L;        /* [n_tracks] */
+    const int32_t* track_closed;  /* [n_tracks] */
+    const rl_params* params;      /* [n_params] */
+    const rl_job* jobs;           /* [n_jobs]   */
+} rl_batch_desc;
+
+/*
+ * Caller-allocated outputs (the fields of the reference's Result structs,
+ * main.cpp:677-681 and 897-903).  Per-sample arrays hold the jobs' samples back
+ * to back in job order: job j owns rows [off[j], off[j+1]) with
+ * off = rl_job_sample_offsets().  v/ax rows of MINCURV jobs are left untouched.
+ * Any per-sample pointer may be NULL to skip that download.
+ */
+typedef struct rl_batch_out {
+    double* xy;           /* raceline, x,y interleaved   [2*rows] */
+    double* heading;      /* [rows] */
+    double* curvature;    /* [rows] */
+    double* alpha_total;  /* [rows] */
+    double* alpha_last;   /* [rows] */
+    double* v;            /* [rows] (MINTIME jobs) */
+    double* ax;           /* [rows] (MINTIME jobs) */
+    rl_job_stats* stats;  /* [n_jobs] */
+} rl_batch_out;
+
+typedef struct rl_ctx rl_ctx;     /* owns the device, streams, staging */
+typedef struct rl_batch rl_batch; /* a device-resident batch */
+
+/* ---- library / context ------------------------------------------------- */
+int rl_abi_version(void);
+const char* rl_status_string(int status);
+int rl_device_count(void);
+/* cfg::Config defaults for the fields above (main.cpp:77-113) */
+int rl_default_params(rl_params* p);
+/* one context per device (and per host thread); replaces the process-global cfg::get() (main.cpp:120) */
+rl_ctx* rl_create(int device, int* status);
+void rl_destroy(rl_ctx* ctx);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream */
+int rl_set_stream(rl_ctx* ctx, void* cuda_stream);
+const char* rl_last_error(rl_ctx* ctx);
+
+/* ---- layout helpers ---------------------------------------------------- */
+/* off[j] = sum of N(track(job k)) for k<j; off has n_jobs+1 entries */
+int rl_job_sample_offsets(const rl_batch_desc* desc, int64_t* off);
+
+/* ---- batched solve: the data-parallel form of main.cpp:1347 + main.cpp:1397 */
+/* host buffers in, host buffers out; H2D, kernels and D2H are chunk-pipelined inside */
+int rl_solve_batch(rl_ctx* ctx, const rl_batch_desc* desc, const rl_batch_out* out);
+
+/* device-resident form: upload once, solve many times, download on demand */
+rl_batch* rl_batch_create(rl_ctx* ctx, const rl_batch_desc* desc, int* status);
+int rl_batch_upload(rl_batch* b, const rl_batch_desc* desc);   /* async H2D of the same shapes   */
+int rl_batch_solve(rl_batch* b);                               /* async kernel launches          */
+int rl_batch_download(rl_batch* b, const rl_batch_out* out);   /* async D2H                      */
+int rl_batch_sync(rl_batch* b);                                /* wait; returns first CUDA error */
+int rl_batch_launches_per_solve(const rl_batch* b);            /* kernels one rl_batch_solve launches */
+void rl_batch_destroy(rl_batch* b);
+
+/* ---- single-problem entry points with the reference's argument meaning -- */
+/*
+ * compute_min_curvature_raceline(center, innerE, outerE, veh_width, L, closed) -> Result
+ * (main.cpp:683-686).  veh_width/L/closed as in the reference; Config via `p`
+ * (p->veh_width_arg is overwritten by veh_width).  n == 0 returns RL_OK with
+ * nothing written, like the reference's empty Result (main.cpp:689).
+ */
+int rl_compute_min_curvature_raceline(rl_ctx* ctx, const double* center_xy, int n,
+                                      const double* inner_seg, int m_inner,
+                                      const double* outer_seg, int m_outer,
+                                      double veh_width, double L, int closed, const rl_params* p,
+                                      double* raceline_xy, double* heading, double* curvature,
+                                      double* alpha_total, double* alpha_last, rl_job_stats* stats);
+/*
+ * compute_min_time_raceline(center, innerE, outerE, veh_width, L, closed) -> Result
+ * (main.cpp:905-909); adds v, ax and lap_time (main.cpp:897-903).
+ */
+int rl_compute_min_time_raceline(rl_ctx* ctx, const double* center_xy, int n,
+                                 const double* inner_seg, int m_inner,
+                                 const double* outer_seg, int m_outer,
+                                 double veh_width, double L, int closed, const rl_params* p,
+                                 double* raceline_xy, double* heading, double* curvature,
+                                 double* alpha_total, double* alpha_last, double* v, double* ax,
+                                 double* lap_time, rl_job_stats* stats);
+
+/* ---- measurement helpers (bench / tests; not on the solve path) -------- */
+/*
+ * Deterministic synthetic closed tracks: track id
+ * first_id+k is drawn from mt19937_64(seed_base + id).  Writes n_samples centre
+ * points, m_per_ring inner and m_per_ring outer ring segments and L per track
+ * into packed arrays of exactly the rl_batch_desc layout.  Host only.
+ */
+int rl_synth_tracks(uint64_t seed_base, int64_t first_id, int n_tracks, int n_samples,
+                    int m_per_ring, int n_threads, double* center_xy, double* seg, double* track_L);
+/* measured DFMA throughput of this device in TFLOP/s (2 flop per FMA); the FP64 roofline denominator */
+int rl_measure_fp64_peak(rl_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RACELINE_B200_H */

@@ -1,0 +1,102 @@
+"""TEST INFRASTRUCTURE: binary file formats shared by oracle/ref_harness.cpp, tests and bench.py.
+
+RLG1 (one shipped map, written by `ref_harness frontend`): hot-path inputs produced by the
+reference front end (main.cpp:1613-1663) plus both solver outputs (main.cpp:677-681, 897-903).
+RLB1 (a packed batch = the rl_batch_desc layout of include/raceline_b200.h) and RLR1 (results +
+per-job solver wall-clock) are the `ref_harness solve` input and output.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MAGIC_G = 0x31474C52
+MAGIC_B = 0x31424C52
+MAGIC_R = 0x31524C52
+
+# rl_params field order (include/raceline_b200.h); ints are stored as doubles in RLB1
+PARAM_FIELDS = [
+    "veh_width_arg", "veh_width_m", "safety_margin_m", "lambda_smooth", "step_init", "step_min",
+    "armijo_c", "kappa_eps", "v_cap_mps", "mass_kg", "Cd", "A_front_m2", "rho_air", "c_rr", "P_max_W",
+    "a_total_max", "a_lat_max", "a_long_acc_cap", "a_long_brake_cap", "w_time_gain",
+    "time_gamma_power", "inv_v_gain", "max_outer_iters", "max_inner_iters", "max_vpass_iters",
+    "time_weight_use_inv_v", "use_total_ge_lat", "reserved",
+]
+
+
+def read_rlg1(path):
+    """Return a dict of numpy arrays for one `ref_harness frontend` dump."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    hdr = raw[:40].view(np.int64)
+    assert hdr[0] == MAGIC_G, "not an RLG1 file"
+    n, m_in, m_out, closed = (int(hdr[1]), int(hdr[2]), int(hdr[3]), int(hdr[4]))
+    pos = 40
+
+    def f64(count):
+        nonlocal pos
+        out = raw[pos:pos + 8 * count].view(np.float64).copy()
+        pos += 8 * count
+        return out
+
+    def i64(count):
+        nonlocal pos
+        out = raw[pos:pos + 8 * count].view(np.int64).copy()
+        pos += 8 * count
+        return out
+
+    d = {"n": n, "m_inner": m_in, "m_outer": m_out, "closed": closed}
+    d["L"] = float(f64(1)[0])
+    d["s0"] = float(f64(1)[0])
+    d["center_xy"] = f64(2 * n).reshape(n, 2)
+    d["inner_seg"] = f64(4 * m_in).reshape(m_in, 4)
+    d["outer_seg"] = f64(4 * m_out).reshape(m_out, 4)
+    for st, extra in (("mc", ()), ("mt", ("v", "ax"))):
+        d[st + "_xy"] = f64(2 * n).reshape(n, 2)
+        for k in ("heading", "curvature", "alpha_total", "alpha_last") + extra:
+            d[st + "_" + k] = f64(n)
+    d["mt_lap_time"] = float(f64(1)[0])
+    k = int(i64(1)[0])
+    d["mc_bt"] = i64(k)
+    k = int(i64(1)[0])
+    d["mt_bt"] = i64(k)
+    assert pos == raw.size, "trailing bytes in RLG1 file"
+    return d
+
+
+def write_rlb1(path, samp_off, seg_off, track_L, track_closed, center_xy, seg, params_rows, jobs):
+    """params_rows: (n_params, 28) float64 in PARAM_FIELDS order; jobs: (n_jobs, 3) int (track, param, stage)."""
+    samp_off = np.ascontiguousarray(samp_off, dtype=np.int64)
+    seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+    params_rows = np.ascontiguousarray(params_rows, dtype=np.float64).reshape(-1, len(PARAM_FIELDS))
+    jobs = np.ascontiguousarray(jobs, dtype=np.int64).reshape(-1, 3)
+    nt = samp_off.size - 1
+    with open(path, "wb") as f:
+        np.array([MAGIC_B, nt, params_rows.shape[0], jobs.shape[0]], dtype=np.int64).tofile(f)
+        samp_off.tofile(f)
+        seg_off.tofile(f)
+        np.ascontiguousarray(track_L, dtype=np.float64).tofile(f)
+        np.ascontiguousarray(track_closed, dtype=np.int64).tofile(f)
+        np.ascontiguousarray(center_xy, dtype=np.float64).tofile(f)
+        np.ascontiguousarray(seg, dtype=np.float64).tofile(f)
+        params_rows.tofile(f)
+        jobs.tofile(f)
+
+
+def read_rlr1(path):
+    """Return a list of per-job dicts from a `ref_harness solve` result file."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    hdr = raw[:16].view(np.int64)
+    assert hdr[0] == MAGIC_R, "not an RLR1 file"
+    pos = 16
+    out = []
+    for _ in range(int(hdr[1])):
+        n, stage = (int(x) for x in raw[pos:pos + 16].view(np.int64))
+        ms, lap = (float(x) for x in raw[pos + 16:pos + 32].view(np.float64))
+        pos += 32
+        body = raw[pos:pos + 8 * 8 * n].view(np.float64)
+        pos += 8 * 8 * n
+        r = {"n": n, "stage": stage, "wall_ms": ms, "lap_time": lap, "xy": body[:2 * n].reshape(n, 2).copy()}
+        for i, k in enumerate(("heading", "curvature", "alpha_total", "alpha_last", "v", "ax")):
+            r[k] = body[(2 + i) * n:(3 + i) * n].copy()
+        out.append(r)
+    assert pos == raw.size
+    return out

@@ -19,6 +19,7 @@
 #ifndef RACELINE_B200_H
 #define RACELINE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -172,6 +173,10 @@ void rl_destroy(rl_ctx* ctx);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream */
 int rl_set_stream(rl_ctx* ctx, void* cuda_stream);
 const char* rl_last_error(rl_ctx* ctx);
+
+/* page-locked host memory for asynchronous copies (cudaHostAlloc / cudaFreeHost) */
+void* rl_host_alloc(size_t bytes);
+void rl_host_free(void* p);
 
 /* ---- layout helpers ---------------------------------------------------- */
 /* off[j] = sum of N(track(job k)) for k<j; off has n_jobs+1 entries */

@@ -1,0 +1,65 @@
+"""In-tree build of csrc/libraceline_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+
+    python -m practice_path_planning_for_formula_student_driverless_b200.build [--force]
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libraceline_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+SOURCES = ["raceline_kernels.cu", "raceline_api.cu", "synth_tracks.cpp"]
+HEADERS = [os.path.join(CSRC, "raceline_device.h"), os.path.join(HERE, "..", "include", "raceline_b200.h")]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: cannot build the CUDA extension")
+    return exe
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every source for sm_100a and link the shared library. Returns its path."""
+    nvcc = _nvcc()
+    objs = []
+    for src in SOURCES:
+        sp = os.path.join(CSRC, src)
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [sp] + HEADERS):
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", sp, "-o", obj]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError(f"nvcc failed on {src}")
+            log = os.path.join(CSRC, os.path.splitext(src)[0] + ".ptxas.log")
+            with open(log, "w") as f:
+                f.write(res.stdout + res.stderr)
+            if verbose:
+                sys.stderr.write(f"built {obj}\n")
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,519 @@
+// raceline_api.cu -- the extern "C" ABI of include/raceline_b200.h over the kernels in raceline_kernels.cu.
+// Host side only: validation, packing of job lists per size class, device buffers, copies, launches.
+// There is no CPU fallback: without a usable device every entry point returns an error status.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "raceline_device.h"
+
+using rl::DevBatch;
+
+struct rl_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;   // own_stream or the caller's
+    std::string err;
+    rl_batch* scratch = nullptr;     // reused by rl_solve_batch and the single-problem entry points
+};
+
+namespace {
+
+template <class T>
+struct DevArr {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 16;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct ClassList { int cls; bool exact; int begin; int count; };
+
+}  // namespace
+
+struct rl_batch {
+    rl_ctx* ctx = nullptr;
+    int n_tracks = 0, n_params = 0, n_jobs = 0;
+    long long total_samples = 0, total_segs = 0, rows = 0;
+    // device inputs
+    DevArr<long long> d_samp_off, d_seg_off, d_job_off;
+    DevArr<double> d_center, d_seg, d_L;
+    DevArr<int> d_closed, d_joblist;
+    DevArr<rl_params> d_params;
+    DevArr<rl_job> d_jobs;
+    // device outputs
+    DevArr<double> d_xy, d_heading, d_curv, d_atot, d_alast, d_v, d_ax;
+    DevArr<rl_job_stats> d_stats;
+    // host-side plan
+    std::vector<long long> job_off;
+    std::vector<int> joblist;
+    std::vector<ClassList> lists;
+    std::vector<std::pair<int, int>> skipped;   // (job, status) for jobs no kernel covers
+    void release()
+    {
+        d_samp_off.release(); d_seg_off.release(); d_job_off.release(); d_center.release(); d_seg.release();
+        d_L.release(); d_closed.release(); d_joblist.release(); d_params.release(); d_jobs.release();
+        d_xy.release(); d_heading.release(); d_curv.release(); d_atot.release(); d_alast.release();
+        d_v.release(); d_ax.release(); d_stats.release();
+    }
+};
+
+namespace {
+
+int fail(rl_ctx* c, int status, const std::string& msg)
+{
+    if (c) c->err = msg;
+    return status;
+}
+int cuda_fail(rl_ctx* c, cudaError_t e, const char* what)
+{
+    return fail(c, RL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define RL_CUDA(ctx, call)                                          \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return cuda_fail((ctx), e__, #call); \
+    } while (0)
+
+int validate_desc(rl_ctx* c, const rl_batch_desc* d)
+{
+    if (!d) return fail(c, RL_ERR_ARG, "null batch descriptor");
+    if (d->n_tracks < 0 || d->n_params < 0 || d->n_jobs < 0) return fail(c, RL_ERR_ARG, "negative count");
+    if (d->n_jobs == 0) return RL_OK;
+    if (!d->samp_off || !d->seg_off || !d->track_L || !d->track_closed || !d->params || !d->jobs)
+        return fail(c, RL_ERR_ARG, "null array in batch descriptor");
+    if (d->n_tracks == 0 || d->n_params == 0) return fail(c, RL_ERR_ARG, "jobs without tracks or params");
+    if (d->samp_off[0] != 0 || d->seg_off[0] != 0) return fail(c, RL_ERR_ARG, "offset arrays must start at 0");
+    for (int t = 0; t < d->n_tracks; ++t) {
+        if (d->samp_off[t + 1] < d->samp_off[t]) return fail(c, RL_ERR_ARG, "samp_off not monotone");
+        if (d->seg_off[2 * t + 1] < d->seg_off[2 * t] || d->seg_off[2 * t + 2] < d->seg_off[2 * t + 1])
+            return fail(c, RL_ERR_ARG, "seg_off not monotone");
+        if (d->samp_off[t + 1] - d->samp_off[t] > (1ll << 30)) return fail(c, RL_ERR_ARG, "track too long");
+    }
+    if (d->samp_off[d->n_tracks] > 0 && !d->center_xy) return fail(c, RL_ERR_ARG, "null center_xy");
+    if (d->seg_off[2 * d->n_tracks] > 0 && !d->seg) return fail(c, RL_ERR_ARG, "null seg");
+    for (int j = 0; j < d->n_jobs; ++j) {
+        const rl_job& jb = d->jobs[j];
+        if (jb.track < 0 || jb.track >= d->n_tracks) return fail(c, RL_ERR_ARG, "job.track out of range");
+        if (jb.param < 0 || jb.param >= d->n_params) return fail(c, RL_ERR_ARG, "job.param out of range");
+        if (jb.stage != RL_STAGE_MINCURV && jb.stage != RL_STAGE_MINTIME) return fail(c, RL_ERR_ARG, "job.stage invalid");
+    }
+    return RL_OK;
+}
+
+// size the buffers, classify the jobs, upload the (small) plan arrays
+int plan_batch(rl_batch* b, const rl_batch_desc* d)
+{
+    rl_ctx* c = b->ctx;
+    b->n_tracks = d->n_tracks; b->n_params = d->n_params; b->n_jobs = d->n_jobs;
+    b->total_samples = d->n_tracks ? d->samp_off[d->n_tracks] : 0;
+    b->total_segs = d->n_tracks ? d->seg_off[2 * d->n_tracks] : 0;
+    b->job_off.assign((size_t)d->n_jobs + 1, 0);
+    for (int j = 0; j < d->n_jobs; ++j) {
+        const int t = d->jobs[j].track;
+        b->job_off[j + 1] = b->job_off[j] + (d->samp_off[t + 1] - d->samp_off[t]);
+    }
+    b->rows = b->job_off[d->n_jobs];
+
+    // job lists per (class, exact); min-time jobs first (they run longer: better tail)
+    b->lists.clear(); b->joblist.clear(); b->skipped.clear();
+    std::vector<std::vector<int>> bucket(rl::kNumClasses * 2);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < d->n_jobs; ++j) {
+            const rl_job& jb = d->jobs[j];
+            if ((pass == 0) != (jb.stage == RL_STAGE_MINTIME)) continue;
+            const int t = jb.track;
+            const long long n = d->samp_off[t + 1] - d->samp_off[t];
+            if (n == 0) { b->skipped.push_back({j, RL_OK}); continue; }   // empty Result, main.cpp:689 / 912
+            const int cls = rl::class_for_n((int)n);
+            if (cls < 0 || !d->track_closed[t]) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
+            const bool exact = (n == (long long)rl::kClasses[cls].T * rl::kClasses[cls].K);
+            bucket[cls * 2 + (exact ? 1 : 0)].push_back(j);
+        }
+    }
+    for (int k = 0; k < rl::kNumClasses * 2; ++k) {
+        if (bucket[k].empty()) continue;
+        b->lists.push_back({k / 2, (k & 1) != 0, (int)b->joblist.size(), (int)bucket[k].size()});
+        b->joblist.insert(b->joblist.end(), bucket[k].begin(), bucket[k].end());
+    }
+
+    RL_CUDA(c, b->d_samp_off.ensure((size_t)d->n_tracks + 1));
+    RL_CUDA(c, b->d_seg_off.ensure((size_t)2 * d->n_tracks + 1));
+    RL_CUDA(c, b->d_job_off.ensure((size_t)d->n_jobs + 1));
+    RL_CUDA(c, b->d_center.ensure((size_t)2 * b->total_samples + 2));
+    RL_CUDA(c, b->d_seg.ensure((size_t)4 * b->total_segs + 4));
+    RL_CUDA(c, b->d_L.ensure((size_t)d->n_tracks));
+    RL_CUDA(c, b->d_closed.ensure((size_t)d->n_tracks));
+    RL_CUDA(c, b->d_params.ensure((size_t)d->n_params));
+    RL_CUDA(c, b->d_jobs.ensure((size_t)d->n_jobs));
+    RL_CUDA(c, b->d_joblist.ensure(b->joblist.size() + 1));
+    const size_t rows = (size_t)b->rows + 2;
+    RL_CUDA(c, b->d_xy.ensure(2 * rows));
+    RL_CUDA(c, b->d_heading.ensure(rows));
+    RL_CUDA(c, b->d_curv.ensure(rows));
+    RL_CUDA(c, b->d_atot.ensure(rows));
+    RL_CUDA(c, b->d_alast.ensure(rows));
+    RL_CUDA(c, b->d_v.ensure(rows));
+    RL_CUDA(c, b->d_ax.ensure(rows));
+    RL_CUDA(c, b->d_stats.ensure((size_t)d->n_jobs));
+
+    cudaStream_t s = c->stream;
+    RL_CUDA(c, cudaMemcpyAsync(b->d_job_off.p, b->job_off.data(), sizeof(long long) * b->job_off.size(), cudaMemcpyHostToDevice, s));
+    if (!b->joblist.empty())
+        RL_CUDA(c, cudaMemcpyAsync(b->d_joblist.p, b->joblist.data(), sizeof(int) * b->joblist.size(), cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemsetAsync(b->d_stats.p, 0, sizeof(rl_job_stats) * (size_t)d->n_jobs, s));
+    for (auto& sk : b->skipped) {
+        const int t = d->jobs[sk.first].track;
+        int hdr[2] = {sk.second, (int)(d->samp_off[t + 1] - d->samp_off[t])};
+        RL_CUDA(c, cudaMemcpyAsync(&b->d_stats.p[sk.first], hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));
+        RL_CUDA(c, cudaStreamSynchronize(s));   // hdr is a stack temporary
+    }
+    // job_off/joblist live in std::vectors owned by the batch: safe for the async copies above
+    return RL_OK;
+}
+
+int upload_inputs(rl_batch* b, const rl_batch_desc* d)
+{
+    rl_ctx* c = b->ctx;
+    cudaStream_t s = c->stream;
+    if (d->n_tracks != b->n_tracks || d->n_params != b->n_params || d->n_jobs != b->n_jobs ||
+        (d->n_tracks && (d->samp_off[d->n_tracks] != b->total_samples || d->seg_off[2 * d->n_tracks] != b->total_segs)))
+        return fail(c, RL_ERR_ARG, "rl_batch_upload: shapes differ from rl_batch_create");
+    if (d->n_jobs == 0) return RL_OK;
+    RL_CUDA(c, cudaMemcpyAsync(b->d_samp_off.p, d->samp_off, sizeof(long long) * ((size_t)d->n_tracks + 1), cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_seg_off.p, d->seg_off, sizeof(long long) * ((size_t)2 * d->n_tracks + 1), cudaMemcpyHostToDevice, s));
+    if (b->total_samples)
+        RL_CUDA(c, cudaMemcpyAsync(b->d_center.p, d->center_xy, sizeof(double) * 2 * (size_t)b->total_samples, cudaMemcpyHostToDevice, s));
+    if (b->total_segs)
+        RL_CUDA(c, cudaMemcpyAsync(b->d_seg.p, d->seg, sizeof(double) * 4 * (size_t)b->total_segs, cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_L.p, d->track_L, sizeof(double) * (size_t)d->n_tracks, cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_closed.p, d->track_closed, sizeof(int) * (size_t)d->n_tracks, cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_params.p, d->params, sizeof(rl_params) * (size_t)d->n_params, cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_jobs.p, d->jobs, sizeof(rl_job) * (size_t)d->n_jobs, cudaMemcpyHostToDevice, s));
+    return RL_OK;
+}
+
+DevBatch dev_view(const rl_batch* b)
+{
+    DevBatch B;
+    B.samp_off = b->d_samp_off.p; B.seg_off = b->d_seg_off.p; B.center_xy = b->d_center.p; B.seg = b->d_seg.p;
+    B.track_L = b->d_L.p; B.track_closed = b->d_closed.p; B.params = b->d_params.p; B.jobs = b->d_jobs.p;
+    B.job_off = b->d_job_off.p; B.xy = b->d_xy.p; B.heading = b->d_heading.p; B.curvature = b->d_curv.p;
+    B.alpha_total = b->d_atot.p; B.alpha_last = b->d_alast.p; B.v = b->d_v.p; B.ax = b->d_ax.p; B.stats = b->d_stats.p;
+    return B;
+}
+
+static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+
+}  // namespace
+
+extern "C" {
+
+int rl_abi_version(void) { return RL_ABI_VERSION; }
+
+const char* rl_status_string(int s)
+{
+    switch (s) {
+        case RL_OK: return "ok";
+        case RL_ERR_ARG: return "bad argument";
+        case RL_ERR_CUDA: return "CUDA error";
+        case RL_ERR_UNSUPPORTED: return "unsupported problem shape";
+        case RL_ERR_NOMEM: return "out of memory";
+        case RL_ERR_NODEVICE: return "no usable CUDA device";
+        default: return "unknown status";
+    }
+}
+
+int rl_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rl_default_params(rl_params* p)
+{
+    if (!p) return RL_ERR_ARG;
+    std::memset(p, 0, sizeof(*p));
+    // cfg::Config defaults, main.cpp:77-113
+    p->veh_width_arg = 1.0; p->veh_width_m = 1.0; p->safety_margin_m = 0.05;
+    p->lambda_smooth = 1.6e-3; p->step_init = 0.65; p->step_min = 1e-6; p->armijo_c = 1e-5;
+    p->kappa_eps = 1e-6; p->v_cap_mps = 27.0;
+    p->mass_kg = 255.0; p->Cd = 0.30; p->A_front_m2 = 1.00; p->rho_air = 1.225; p->c_rr = 0.015; p->P_max_W = 80000.0;
+    p->a_total_max = 1.17 * 9.81; p->a_lat_max = 11.0; p->a_long_acc_cap = 8.0; p->a_long_brake_cap = 11.0;
+    p->w_time_gain = 1.0; p->time_gamma_power = 2.0; p->inv_v_gain = 0.1;
+    p->max_outer_iters = 14; p->max_inner_iters = 120; p->max_vpass_iters = 6;
+    p->time_weight_use_inv_v = 0; p->use_total_ge_lat = 1;
+    return RL_OK;
+}
+
+rl_ctx* rl_create(int device, int* status)
+{
+    int st = RL_OK;
+    rl_ctx* c = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0 || device < 0 || device >= n) { cudaGetLastError(); st = RL_ERR_NODEVICE; }
+    if (st == RL_OK) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) st = RL_ERR_NODEVICE;   // sm_100a only
+    }
+    if (st == RL_OK && cudaSetDevice(device) != cudaSuccess) st = RL_ERR_CUDA;
+    if (st == RL_OK) {
+        c = new (std::nothrow) rl_ctx();
+        if (!c) st = RL_ERR_NOMEM;
+    }
+    if (st == RL_OK) {
+        c->device = device;
+        if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) st = RL_ERR_CUDA;
+        c->stream = c->own_stream;
+        if (st == RL_OK && rl::configure_kernels() != 0) st = RL_ERR_CUDA;
+        if (st != RL_OK) { if (c->own_stream) cudaStreamDestroy(c->own_stream); delete c; c = nullptr; }
+    }
+    if (status) *status = st;
+    return c;
+}
+
+void rl_destroy(rl_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->scratch) { rl_batch_destroy(c->scratch); c->scratch = nullptr; }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int rl_set_stream(rl_ctx* c, void* cuda_stream)
+{
+    if (!c) return RL_ERR_ARG;
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return RL_OK;
+}
+
+const char* rl_last_error(rl_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int rl_job_sample_offsets(const rl_batch_desc* d, int64_t* off)
+{
+    if (!d || !off || d->n_jobs < 0) return RL_ERR_ARG;
+    off[0] = 0;
+    for (int j = 0; j < d->n_jobs; ++j) {
+        const int t = d->jobs[j].track;
+        if (t < 0 || t >= d->n_tracks) return RL_ERR_ARG;
+        off[j + 1] = off[j] + (d->samp_off[t + 1] - d->samp_off[t]);
+    }
+    return RL_OK;
+}
+
+void* rl_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void rl_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+rl_batch* rl_batch_create(rl_ctx* c, const rl_batch_desc* d, int* status)
+{
+    int st = c ? validate_desc(c, d) : RL_ERR_ARG;
+    rl_batch* b = nullptr;
+    if (st == RL_OK) {
+        cudaSetDevice(c->device);
+        b = new (std::nothrow) rl_batch();
+        if (!b) st = RL_ERR_NOMEM;
+    }
+    if (st == RL_OK) {
+        b->ctx = c;
+        st = plan_batch(b, d);
+        if (st == RL_OK) st = upload_inputs(b, d);
+        if (st == RL_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = RL_ERR_CUDA;
+        if (st != RL_OK) { b->release(); delete b; b = nullptr; }
+    }
+    if (status) *status = st;
+    return b;
+}
+
+int rl_batch_upload(rl_batch* b, const rl_batch_desc* d)
+{
+    if (!b || !d) return RL_ERR_ARG;
+    cudaSetDevice(b->ctx->device);
+    return upload_inputs(b, d);
+}
+
+int rl_batch_solve(rl_batch* b)
+{
+    if (!b) return RL_ERR_ARG;
+    rl_ctx* c = b->ctx;
+    cudaSetDevice(c->device);
+    const DevBatch B = dev_view(b);
+    for (const ClassList& l : b->lists) {
+        const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, l.cls, l.exact, c->stream);
+        if (e != 0) return cuda_fail(c, (cudaError_t)e, "solve_kernel launch");
+    }
+    return RL_OK;
+}
+
+int rl_batch_launches_per_solve(const rl_batch* b) { return b ? (int)b->lists.size() : 0; }
+
+int rl_batch_download(rl_batch* b, const rl_batch_out* o)
+{
+    if (!b || !o) return RL_ERR_ARG;
+    rl_ctx* c = b->ctx;
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    const size_t rows = (size_t)b->rows;
+    if (rows) {
+        if (o->xy) RL_CUDA(c, cudaMemcpyAsync(o->xy, b->d_xy.p, 16 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->heading) RL_CUDA(c, cudaMemcpyAsync(o->heading, b->d_heading.p, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->curvature) RL_CUDA(c, cudaMemcpyAsync(o->curvature, b->d_curv.p, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->alpha_total) RL_CUDA(c, cudaMemcpyAsync(o->alpha_total, b->d_atot.p, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->alpha_last) RL_CUDA(c, cudaMemcpyAsync(o->alpha_last, b->d_alast.p, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->v) RL_CUDA(c, cudaMemcpyAsync(o->v, b->d_v.p, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->ax) RL_CUDA(c, cudaMemcpyAsync(o->ax, b->d_ax.p, 8 * rows, cudaMemcpyDeviceToHost, s));
+    }
+    if (o->stats && b->n_jobs)
+        RL_CUDA(c, cudaMemcpyAsync(o->stats, b->d_stats.p, sizeof(rl_job_stats) * (size_t)b->n_jobs, cudaMemcpyDeviceToHost, s));
+    return RL_OK;
+}
+
+int rl_batch_sync(rl_batch* b)
+{
+    if (!b) return RL_ERR_ARG;
+    cudaSetDevice(b->ctx->device);
+    RL_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+    RL_CUDA(b->ctx, cudaGetLastError());
+    return RL_OK;
+}
+
+void rl_batch_destroy(rl_batch* b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    b->release();
+    delete b;
+}
+
+int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
+{
+    if (!c || !o) return RL_ERR_ARG;
+    int st = validate_desc(c, d);
+    if (st != RL_OK) return st;
+    if (d->n_jobs == 0) return RL_OK;
+    cudaSetDevice(c->device);
+    if (!c->scratch) {
+        c->scratch = new (std::nothrow) rl_batch();
+        if (!c->scratch) return fail(c, RL_ERR_NOMEM, "host allocation failed");
+        c->scratch->ctx = c;
+    }
+    rl_batch* b = c->scratch;
+    st = plan_batch(b, d);
+    if (st == RL_OK) st = upload_inputs(b, d);
+    if (st == RL_OK) st = rl_batch_solve(b);
+    if (st == RL_OK) st = rl_batch_download(b, o);
+    if (st == RL_OK) st = rl_batch_sync(b);
+    if (st != RL_OK) return st;
+    for (auto& sk : b->skipped)
+        if (sk.second != RL_OK) return fail(c, sk.second, "a job's shape is not covered by the kernels (open track or N too large)");
+    return RL_OK;
+}
+
+static int solve_single(rl_ctx* c, int stage, const double* center_xy, int n, const double* inner_seg, int m_inner,
+                        const double* outer_seg, int m_outer, double veh_width, double L, int closed, const rl_params* p,
+                        double* xy, double* heading, double* curvature, double* alpha_total, double* alpha_last,
+                        double* v, double* ax, double* lap_time, rl_job_stats* stats)
+{
+    if (!c || !p || n < 0 || m_inner < 0 || m_outer < 0) return RL_ERR_ARG;
+    if (n > 0 && !center_xy) return RL_ERR_ARG;
+    if ((m_inner > 0 && !inner_seg) || (m_outer > 0 && !outer_seg)) return RL_ERR_ARG;
+    rl_job_stats local;
+    std::memset(&local, 0, sizeof(local));
+    if (n == 0) {   // the reference returns an empty Result (main.cpp:689 / 912)
+        if (stats) *stats = local;
+        if (lap_time) *lap_time = 0.0;
+        return RL_OK;
+    }
+    std::vector<double> seg((size_t)4 * ((size_t)m_inner + m_outer) + 4);
+    if (m_inner) std::memcpy(seg.data(), inner_seg, sizeof(double) * 4 * (size_t)m_inner);
+    if (m_outer) std::memcpy(seg.data() + 4 * (size_t)m_inner, outer_seg, sizeof(double) * 4 * (size_t)m_outer);
+    rl_params pp = *p;
+    pp.veh_width_arg = veh_width;
+    const int64_t samp_off[2] = {0, n};
+    const int64_t seg_off[3] = {0, m_inner, (int64_t)m_inner + m_outer};
+    const int32_t cl = closed ? 1 : 0;
+    const rl_job job = {0, 0, stage, 0};
+    rl_batch_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.n_tracks = 1; d.n_params = 1; d.n_jobs = 1;
+    d.samp_off = samp_off; d.seg_off = seg_off; d.center_xy = center_xy; d.seg = seg.data();
+    d.track_L = &L; d.track_closed = &cl; d.params = &pp; d.jobs = &job;
+    rl_batch_out o;
+    std::memset(&o, 0, sizeof(o));
+    o.xy = xy; o.heading = heading; o.curvature = curvature; o.alpha_total = alpha_total; o.alpha_last = alpha_last;
+    o.v = v; o.ax = ax; o.stats = &local;
+    const int st = rl_solve_batch(c, &d, &o);
+    if (stats) *stats = local;
+    if (lap_time) *lap_time = local.lap_time;
+    return st;
+}
+
+int rl_compute_min_curvature_raceline(rl_ctx* ctx, const double* center_xy, int n, const double* inner_seg, int m_inner,
+                                      const double* outer_seg, int m_outer, double veh_width, double L, int closed,
+                                      const rl_params* p, double* raceline_xy, double* heading, double* curvature,
+                                      double* alpha_total, double* alpha_last, rl_job_stats* stats)
+{
+    return solve_single(ctx, RL_STAGE_MINCURV, center_xy, n, inner_seg, m_inner, outer_seg, m_outer, veh_width, L, closed, p,
+                        raceline_xy, heading, curvature, alpha_total, alpha_last, nullptr, nullptr, nullptr, stats);
+}
+
+int rl_compute_min_time_raceline(rl_ctx* ctx, const double* center_xy, int n, const double* inner_seg, int m_inner,
+                                 const double* outer_seg, int m_outer, double veh_width, double L, int closed,
+                                 const rl_params* p, double* raceline_xy, double* heading, double* curvature,
+                                 double* alpha_total, double* alpha_last, double* v, double* ax, double* lap_time,
+                                 rl_job_stats* stats)
+{
+    return solve_single(ctx, RL_STAGE_MINTIME, center_xy, n, inner_seg, m_inner, outer_seg, m_outer, veh_width, L, closed, p,
+                        raceline_xy, heading, curvature, alpha_total, alpha_last, v, ax, lap_time, stats);
+}
+
+int rl_measure_fp64_peak(rl_ctx* c, double* tflops)
+{
+    if (!c || !tflops) return RL_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaDeviceProp prop;
+    RL_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double* d = nullptr;
+    RL_CUDA(c, cudaMalloc((void**)&d, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        const int e = rl::launch_fp64_peak(d, blocks, threads, iters, c->stream);
+        cudaEventRecord(e1, c->stream);
+        if (e != 0 || cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return cuda_fail(c, cudaGetLastError(), "fp64 probe"); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return RL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// raceline_device.h -- internal types shared by the kernels and the host-side ABI implementation.
+#pragma once
+
+#include <cstdint>
+
+#include "../../include/raceline_b200.h"
+
+namespace rl {
+
+// Device view of one packed batch (include/raceline_b200.h: rl_batch_desc / rl_batch_out).
+struct DevBatch {
+    const long long* samp_off;   // [n_tracks+1]
+    const long long* seg_off;    // [2*n_tracks+1]
+    const double* center_xy;     // [2*total_samples]
+    const double* seg;           // [4*total_segs]
+    const double* track_L;       // [n_tracks]
+    const int* track_closed;     // [n_tracks]
+    const rl_params* params;     // [n_params]
+    const rl_job* jobs;          // [n_jobs]
+    const long long* job_off;    // [n_jobs+1] output row offsets
+    double* xy;                  // [2*rows]
+    double* heading;
+    double* curvature;
+    double* alpha_total;
+    double* alpha_last;
+    double* v;
+    double* ax;
+    rl_job_stats* stats;         // [n_jobs]
+};
+
+// Size classes: one CTA of T threads solves one (track, config, stage) job, K samples per thread.
+struct SizeClass {
+    int T;
+    int K;
+};
+constexpr int kNumClasses = 5;
+constexpr SizeClass kClasses[kNumClasses] = {{32, 8}, {64, 8}, {128, 8}, {256, 8}, {512, 8}};
+constexpr int kSegBlock = 8;  // segments per bounding box in the corridor ray-cast
+
+inline int class_for_n(int n)
+{
+    for (int c = 0; c < kNumClasses; ++c)
+        if (n <= kClasses[c].T * kClasses[c].K) return c;
+    return -1;
+}
+
+// dynamic shared memory of one CTA of class (T,K): see layout in raceline_kernels.cu
+inline size_t smem_bytes_for_class(int T, int K)
+{
+    const size_t np = (size_t)T * K;
+    return np * 16      /* path points, double2            */
+           + np * 8 * 4 /* region B: PGD coefficients+stash / ray tile+corridor staging */
+           + 2048;      /* barriers, reduction + halo exchange scratch */
+}
+
+// launches job_list[0..n_list) (indices into B.jobs) with the kernel of class `cls`
+// (exact = every job in the list has N == T*K).  Returns a cudaError_t as int.
+int launch_solve(const DevBatch& B, const int* job_list, int n_list, int cls, bool exact, void* stream);
+int configure_kernels();  // sets max dynamic shared memory on every instantiation
+int launch_fp64_peak(double* d_out, int blocks, int threads, int iters, void* stream);
+
+}  // namespace rl

@@ -1,0 +1,1009 @@
+// raceline_kernels.cu -- hand-written sm_100a kernels for the batched raceline solver.
+//
+// One CTA of T threads solves one job = one stage (min-curvature or min-time) of one
+// (track, Config) problem, start to finish, with no host round trip:
+//
+//   reference stage                                   here
+//   compute_min_curvature_raceline  main.cpp:683-764   solve_kernel, stage RL_STAGE_MINCURV
+//   compute_min_time_raceline       main.cpp:905-1052  solve_kernel, stage RL_STAGE_MINTIME
+//
+// Data layout.  Samples are BLOCKED over threads: thread t owns `cnt` (<= K) consecutive
+// samples, kept in registers through the projected-gradient loop.  Shared memory holds
+//   sP      [T*K] double2   the current path P (persistent; TMA bulk-loaded / bulk-stored)
+//   region B 4*T*K doubles  phase-dependent:
+//        PGD phase : c0 | cp | cm | stash      (stencil coefficients + last accepted alpha), slot-major [k][t]
+//        ray phase : ring-segment tile (x0,y0,vx,vy per segment) + one bounding box per kSegBlock segments
+//        v(s) phase: neighbour-exchange arrays of the relaxation sweeps
+//   scratch 2 KB            mbarrier, reduction partials and warp-edge halos (double-buffered)
+//
+// Per cost/gradient evaluation (main.cpp:654-675 / 866-895) a thread needs the trial alpha of its own
+// samples plus a 2-sample halo on each side (the gradient of the periodic 3-point stencils has a
+// 5-point footprint).  Halos travel by warp shuffle, warp-edge halos through shared memory, and the
+// (J, g.dalpha) reduction shares the SAME barrier: one __syncthreads per evaluation.  The Armijo
+// decision (main.cpp:734) is taken redundantly by every thread from bit-identical reduced values.
+//
+// Tensor cores are not used on purpose: D^T D is pentadiagonal, there is no dense contraction here.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cstdint>
+
+#include "raceline_device.h"
+
+namespace rl {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int SB = kSegBlock;
+
+// scratch layout (bytes)
+constexpr int kScrBar = 0;
+constexpr int kScrRed = 64;             // [2][16][2] doubles
+constexpr int kScrExF = kScrRed + 512;  // [2][16][2] doubles: first two samples of each warp's lane 0
+constexpr int kScrExL = kScrExF + 512;  // [2][16][2] doubles: last two samples of each warp's lane 31
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// ---- TMA 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) completed through an mbarrier -------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int T>
+__device__ __forceinline__ void block_sync()
+{
+    if (T == 32) __syncwarp(); else __syncthreads();
+}
+template <int T>
+__device__ __forceinline__ int block_or(int pred)
+{
+    if (T == 32) return __any_sync(kFull, pred);
+    return __syncthreads_or(pred);
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+// Deterministic block-wide sum of two values; the result is bit-identical in every thread.
+// Contains exactly one block barrier (a warp barrier for single-warp CTAs).
+template <int T>
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* sred, int lane, int warp)
+{
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (T > 32) {
+        if (lane == 0) { sred[2 * warp] = a; sred[2 * warp + 1] = b; }
+        __syncthreads();
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) { sa += sred[2 * w]; sb += sred[2 * w + 1]; }
+        a = sa; b = sb;
+    } else {
+        __syncwarp();
+    }
+}
+
+// how the N samples of a job are blocked over the T threads of its CTA
+struct Part {
+    int N, Tact, cnt, start, tL, tR, cntL, srcL, srcR, tid, lane, warp;
+};
+
+// ---- per-sample geometry ---------------------------------------------------------------------------
+// normals_from_points_generic (closed branch), main.cpp:581-593
+__device__ __forceinline__ void normal_closed(double2 Pm, double2 Pp, int N, double& nx, double& ny)
+{
+    double tx = (Pp.x - Pm.x) * 0.5, ty = (Pp.y - Pm.y) * 0.5;
+    if (N == 1) { tx = 1.0; ty = 0.0; }
+    if (sqrt(tx * tx + ty * ty) < 1e-15) { tx = 1.0; ty = 0.0; }
+    const double nvx = -ty, nvy = tx;
+    const double len = sqrt(nvx * nvx + nvy * nvy);
+    if (len < 1e-15) { nx = 0.0; ny = 0.0; }
+    else { nx = nvx / len; ny = nvy / len; }
+}
+// the `deriv` lambda (closed branch), main.cpp:599-603 / 625-629
+__device__ __forceinline__ void derivs_closed(double2 Pm, double2 Pc, double2 Pp, double h, int N,
+                                              double& xp, double& yp, double& xpp, double& ypp)
+{
+    if (N == 1) { xp = 1.0; yp = 0.0; xpp = 0.0; ypp = 0.0; return; }
+    const double h2 = 2 * h, hh = h * h;
+    xp = (Pp.x - Pm.x) / h2; yp = (Pp.y - Pm.y) / h2;
+    xpp = (Pp.x - 2 * Pc.x + Pm.x) / hh; ypp = (Pp.y - 2 * Pc.y + Pm.y) / hh;
+}
+// pow(max(1e-12, q), 1.5), main.cpp:617 / 647
+__device__ __forceinline__ double pow15(double q)
+{
+    const double s = fmax(1e-12, q);
+    return s * sqrt(s);
+}
+__device__ __forceinline__ double2 sp_prev(const double2* sP, int i, int N) { return sP[(i == 0) ? N - 1 : i - 1]; }
+__device__ __forceinline__ double2 sp_next(const double2* sP, int i, int N) { return sP[(i == N - 1) ? 0 : i + 1]; }
+
+// ---- v(s) profile pieces: the ax_max_at lambda, main.cpp:797-824 -----------------------------------
+struct VPar {
+    double v_cap, a_lat_max, kappa_eps, a_tot2, kd, Fr, mass, P, acc_cap, brk_cap, h;
+    int has_power;
+};
+__device__ __forceinline__ double f_acc(const VPar& q, double vi, double ki)
+{   // forward step value sqrt(max(0, v^2 + 2 a_acc h)), main.cpp:830-831
+    const double alat = vi * vi * fabs(ki);
+    const double a_res = sqrt(fmax(0.0, q.a_tot2 - alat * alat));
+    const double Fd = q.kd * vi * vi;
+    double a_power = 1e9;
+    if (q.has_power && vi > 1e-6) a_power = q.P / (q.mass * vi) - (Fd + q.Fr) / q.mass;
+    double a_acc = fmin(fmin(a_res, q.acc_cap), a_power);
+    a_acc = fmax(0.0, a_acc);
+    return sqrt(fmax(0.0, vi * vi + 2.0 * a_acc * q.h));
+}
+__device__ __forceinline__ double f_brk(const VPar& q, double vi, double ki)
+{   // backward step value sqrt(max(0, v^2 + 2 a_brk h)), main.cpp:842-843
+    const double alat = vi * vi * fabs(ki);
+    const double a_res = sqrt(fmax(0.0, q.a_tot2 - alat * alat));
+    const double Fd = q.kd * vi * vi;
+    double a_brk = fmin(a_res, q.brk_cap) + (Fd + q.Fr) / q.mass;
+    a_brk = fmax(0.0, a_brk);
+    return sqrt(fmax(0.0, vi * vi + 2.0 * a_brk * q.h));
+}
+
+// velocity_profile_forward_backward, main.cpp:782-862, on the blocked layout.
+//
+// The reference sweeps are sequential recurrences v[i+1] = min(v[i+1], f(v[i])).  Here every thread
+// runs the recurrence over its own chunk from the value its neighbour published last round, and the
+// rounds repeat until no published value changes.  Each round recomputes from the values at the START
+// of the sweep (v0), so the fixed point is the unique solution of u[i+1] = min(v0[i+1], f(u[i])) --
+// exactly the sequential sweep, for any f (f is not monotone near the friction limit, so a running
+// minimum would NOT be exact).  The two closed-loop wrap updates (main.cpp:834-839, 846-850) stay single
+// post-sweep updates.  An iteration that changes nothing ends the loop early (the map is deterministic).
+// sX: 6*T doubles of exchange space.  Returns v[] (blocked); *rounds += relaxation rounds.
+template <int T, int K>
+__device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, const double (&kap)[K], double (&v)[K],
+                                                 int max_iters, double* sX, int& rounds)
+{
+    double* sVL = sX;           // [2][T] last-slot value of each thread
+    double* sVF = sX + 2 * T;   // [2][T] first-slot value
+    double* sKF = sX + 4 * T;   // [T] kappa of first slot
+    double* sKL = sX + 5 * T;   // [T] kappa of last slot
+    const int cnt = pt.cnt, tid = pt.tid;
+    const bool act = cnt > 0;
+    const bool hasL = act && tid > 0, hasR = act && tid < pt.Tact - 1;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        v[k] = (k < cnt) ? fmin(q.v_cap, sqrt(q.a_lat_max / fmax(fabs(kap[k]), q.kappa_eps))) : 0.0;   // main.cpp:787-794
+    {
+        double kl = kap[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) if (k < cnt) kl = kap[k];
+        sKF[tid] = kap[0]; sKL[tid] = kl;
+    }
+    block_sync<T>();
+    const double kapL = sKL[pt.tL], kapR = sKF[pt.tR];
+    int b = 0;
+    for (int iter = 0; iter < max_iters; ++iter) {
+        double v0[K];
+        bool chg_iter = false;
+        double vstart[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) vstart[k] = v[k];
+        // ---------------- forward sweep (main.cpp:829-833) ----------------
+#pragma unroll
+        for (int k = 0; k < K; ++k) v0[k] = v[k];
+        {
+            double last = v[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k) if (k < cnt) last = v[k];
+            sVL[b * T + tid] = last;
+        }
+        block_sync<T>();
+        for (;;) {
+            bool changed = false;
+            double last = 0.0;
+            if (act) {
+                const double vin = sVL[b * T + pt.tL];
+                double u = hasL ? fmin(v0[0], f_acc(q, vin, kapL)) : v0[0];
+                v[0] = u;
+#pragma unroll
+                for (int k = 1; k < K; ++k)
+                    if (k < cnt) { u = fmin(v0[k], f_acc(q, u, kap[k - 1])); v[k] = u; }
+                last = u;
+                changed = (last != sVL[b * T + tid]);
+            }
+            sVL[(b ^ 1) * T + tid] = last;
+            b ^= 1;
+            ++rounds;
+            if (!block_or<T>(changed)) break;
+        }
+        // closed-loop wrap: v[0] = min(v[0], f_acc(v[N-1])), main.cpp:834-839
+        if (tid == 0) v[0] = fmin(v[0], f_acc(q, sVL[b * T + pt.tL], kapL));
+        // ---------------- backward sweep (main.cpp:841-845) ----------------
+#pragma unroll
+        for (int k = 0; k < K; ++k) v0[k] = v[k];
+        sVF[b * T + tid] = v[0];
+        block_sync<T>();
+        for (;;) {
+            bool changed = false;
+            double first = 0.0;
+            if (act) {
+                const double vin = sVF[b * T + pt.tR];
+                double u = 0.0;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    if (k == cnt - 1) { u = hasR ? fmin(v0[k], f_brk(q, vin, kapR)) : v0[k]; v[k] = u; }
+                    else if (k < cnt - 1) { u = fmin(v0[k], f_brk(q, u, kap[k + 1])); v[k] = u; }
+                }
+                first = u;
+                changed = (first != sVF[b * T + tid]);
+            }
+            sVF[(b ^ 1) * T + tid] = first;
+            b ^= 1;
+            ++rounds;
+            if (!block_or<T>(changed)) break;
+        }
+        // closed-loop wrap: v[N-1] = min(v[N-1], f_brk(v[0])), main.cpp:846-850
+        if (tid == pt.Tact - 1) {
+            const double w = f_brk(q, sVF[b * T + pt.tR], kapR);
+#pragma unroll
+            for (int k = 0; k < K; ++k) if (k == cnt - 1) v[k] = fmin(v[k], w);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (k < cnt && v[k] != vstart[k]) chg_iter = true;
+        if (!block_or<T>(chg_iter)) break;
+    }
+}
+
+// ax and lap time, main.cpp:854-860.  Returns the block-wide lap time; ax[] per owned slot.
+template <int T, int K>
+__device__ __forceinline__ double lap_and_ax(const Part& pt, const VPar& q, const double (&v)[K], double (&ax)[K],
+                                             double* sX, double* sred)
+{
+    double* sVF = sX;
+    sVF[pt.tid] = v[0];
+    block_sync<T>();
+    const double vnext_edge = sVF[pt.tR];
+    double t = 0.0, dummy = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        ax[k] = 0.0;
+        if (k < pt.cnt) {
+            double v1 = vnext_edge;
+            if (k + 1 < K) { if (k + 1 < pt.cnt) v1 = v[k + 1]; }
+            const double v0 = v[k];
+            ax[k] = (v1 * v1 - v0 * v0) / (2.0 * q.h);
+            t += q.h / fmax(1e-6, v0);
+        }
+    }
+    block_sum2<T>(t, dummy, sred, pt.lane, pt.warp);
+    return t;
+}
+
+// ---- cost/gradient of the frozen problem on one thread's window --------------------------------------
+// eval_cost_grad_frozen / _timeweighted, main.cpp:654-675 / 866-895, restated per sample with the time
+// weight gamma folded into the coefficients:
+//   zhat_i = c0_i + cp_i a[i+1] + cm_i a[i-1] - (cp_i+cm_i) a[i]        (= gamma_i * W_i (N0 + A1 D1a + A2 D2a)_i)
+//   J      = sum zhat^2 + lamJ sum d^2,    d_i = a[i+1]-a[i-1]          (lamJ = lambda/(2h)^2)
+//   g_i/2  = cp_{i-1} zhat_{i-1} + cm_{i+1} zhat_{i+1} - (cp_i+cm_i) zhat_i + lamJ (d_{i-1}-d_{i+1})
+// x: trial alpha of the K owned slots; halos hl0,hl1 (samples start-2,start-1) and hr0,hr1 (start+cnt, +1).
+// Returns gh = grad/2 and accumulates Jz = sum zhat^2, Sd = sum d^2 over the OWNED slots.
+struct Halo { double l0, l1, r0, r1; };
+
+template <int T, int K, bool EXACT>
+__device__ __forceinline__ void eval_window(const double (&x)[K], const Halo& hh, int cnt,
+                                            const double* __restrict__ sC0, const double* __restrict__ sCp,
+                                            const double* __restrict__ sCm, const double (&cL)[3], const double (&cR)[3],
+                                            double lamJ, double& Jz, double& Sd, double (&gh)[K])
+{
+    double w[K + 4];
+    w[0] = hh.l0; w[1] = hh.l1;
+#pragma unroll
+    for (int k = 0; k < K; ++k) w[2 + k] = x[k];
+    w[K + 2] = hh.r0; w[K + 3] = hh.r1;
+    if (!EXACT) {
+#pragma unroll
+        for (int k = 1; k < K; ++k)
+            if (cnt == k) { w[2 + k] = hh.r0; w[3 + k] = hh.r1; }
+    }
+    double z[K + 2], s[K + 2], d[K + 2], pp[K + 2], mm[K + 2];
+#pragma unroll
+    for (int p = 0; p < K + 2; ++p) {
+        double c0, cp, cm;
+        if (p == 0) { c0 = cL[0]; cp = cL[1]; cm = cL[2]; }
+        else if (p == K + 1) { c0 = cR[0]; cp = cR[1]; cm = cR[2]; }
+        else { c0 = sC0[(p - 1) * T]; cp = sCp[(p - 1) * T]; cm = sCm[(p - 1) * T]; }
+        const double wm = w[p], wc = w[p + 1], wp = w[p + 2];
+        s[p] = cp + cm;
+        z[p] = fma(cp, wp, fma(cm, wm, fma(-s[p], wc, c0)));
+        d[p] = wp - wm;
+        pp[p] = cp * z[p];
+        mm[p] = cm * z[p];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = k + 1;
+        double t = pp[p - 1] + mm[p + 1];
+        t = fma(-s[p], z[p], t);
+        gh[k] = fma(lamJ, d[p - 1] - d[p + 1], t);
+        if (EXACT || k < cnt) {
+            Jz = fma(z[p], z[p], Jz);
+            Sd = fma(d[p], d[p], Sd);
+        }
+    }
+}
+
+// first two / last two owned samples of a thread (what its neighbours need as halos)
+template <int K, bool EXACT>
+__device__ __forceinline__ void edge_values(const double (&x)[K], int cnt, double& F0, double& F1, double& L0, double& L1)
+{
+    F0 = x[0];
+    F1 = x[1];
+    if (EXACT) { L0 = x[K - 2]; L1 = x[K - 1]; }
+    else {
+        L0 = x[0]; L1 = x[1];
+#pragma unroll
+        for (int k = 2; k < K; ++k)
+            if (k < cnt) { L0 = x[k - 1]; L1 = x[k]; }
+        if (cnt <= 1) { F1 = x[0]; L0 = x[0]; L1 = x[0]; }  // N == 1: every neighbour is the sample itself
+    }
+}
+
+// shuffle part of the halo exchange + publication of the warp-edge values (before the barrier)
+template <int T, int K, bool EXACT>
+__device__ __forceinline__ Halo halo_send(const double (&x)[K], const Part& pt, double* sExF, double* sExL)
+{
+    double F0, F1, L0, L1;
+    edge_values<K, EXACT>(x, pt.cnt, F0, F1, L0, L1);
+    Halo h;
+    h.l0 = __shfl_sync(kFull, L0, pt.srcL);
+    h.l1 = __shfl_sync(kFull, L1, pt.srcL);
+    h.r0 = __shfl_sync(kFull, F0, pt.srcR);
+    h.r1 = __shfl_sync(kFull, F1, pt.srcR);
+    if (T > 32) {
+        if (pt.lane == 0) { sExF[2 * pt.warp] = F0; sExF[2 * pt.warp + 1] = F1; }
+        if (pt.lane == 31) { sExL[2 * pt.warp] = L0; sExL[2 * pt.warp + 1] = L1; }
+    }
+    return h;
+}
+// after the barrier: warp-edge lanes pick their halos up from shared memory
+template <int T>
+__device__ __forceinline__ void halo_recv(Halo& h, const Part& pt, const double* sExF, const double* sExL)
+{
+    if (T > 32) {
+        constexpr int NW = T / 32;
+        if (pt.lane == 0) { const int wp = (pt.warp == 0) ? NW - 1 : pt.warp - 1; h.l0 = sExL[2 * wp]; h.l1 = sExL[2 * wp + 1]; }
+        if (pt.lane == 31) { const int wn = (pt.warp == NW - 1) ? 0 : pt.warp + 1; h.r0 = sExF[2 * wn]; h.r1 = sExF[2 * wn + 1]; }
+    }
+}
+
+struct PgdOut { double J0, Jend; int acc, bt, ev; };
+
+// One outer iteration's projected-gradient loop with Armijo backtracking (main.cpp:723-742 / 996-1026).
+// In: coefficients in shared memory (sC0/sCp/sCm, already offset by tid), cL/cR halo coefficients, box lo/hi.
+// Out: the accepted alpha of the owned slots in the stash sSt[k*T] (also already offset by tid).
+//
+// Steady state costs ONE barrier per evaluation: after the gradient of trial x is known, the next trial
+// x2 = clamp(x - step*g) is formed speculatively (it is the reference's next trial whenever x is accepted,
+// and x is accepted ~98% of the time), its halos are exchanged and (J(x), g_prev.(x-a)) are reduced through
+// the same barrier.  On a reject the step halves and the trial is rebuilt from the stashed accepted alpha.
+template <int T, int K, bool EXACT>
+__device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double (&lo)[K], const double (&hi)[K],
+                                            const double (&cL)[3], const double (&cR)[3],
+                                            const double* sC0, const double* sCp, const double* sCm, double* sSt,
+                                            double* sRed, double* sExF, double* sExL, int& ph,
+                                            double lamJ, double step_init, double step_min, double armijo_c, int max_inner)
+{
+    PgdOut o; o.acc = 0; o.bt = 0; o.ev = 0;
+    double x[K], gh[K];
+    Halo hx; hx.l0 = hx.l1 = hx.r0 = hx.r1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { x[k] = 0.0; sSt[k * T] = 0.0; }
+    double step2 = 2.0 * step_init;   // gh is grad/2, so alpha - step*grad = alpha - step2*gh
+    // ---- J and gradient at alpha = 0 (main.cpp:724 / 997) ----
+    double Jz = 0.0, Sd = 0.0;
+    eval_window<T, K, EXACT>(x, hx, pt.cnt, sC0, sCp, sCm, cL, cR, lamJ, Jz, Sd, gh);
+    o.ev++;
+    double Jt = fma(lamJ, Sd, Jz);
+    // first trial
+    double decp = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double xn = fmin(hi[k], fmax(lo[k], -step2 * gh[k]));
+        decp = fma(gh[k], xn, decp);
+        x[k] = xn;
+    }
+    hx = halo_send<T, K, EXACT>(x, pt, sExF + ph * 32, sExL + ph * 32);
+    double zero = 0.0;
+    block_sum2<T>(Jt, zero, sRed + ph * 32, pt.lane, pt.warp);
+    halo_recv<T>(hx, pt, sExF + ph * 32, sExL + ph * 32);
+    ph ^= 1;
+    double J = Jt, Jprev = Jt;
+    o.J0 = Jt;
+    int it = 0, bt = 0;
+    while (it < max_inner) {
+        // ---- evaluate the trial x ----
+        Jz = 0.0; Sd = 0.0;
+        eval_window<T, K, EXACT>(x, hx, pt.cnt, sC0, sCp, sCm, cL, cR, lamJ, Jz, Sd, gh);
+        o.ev++;
+        double Jn = fma(lamJ, Sd, Jz);
+        // ---- speculative next trial ----
+        double x2[K];
+        double dec2p = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double xn = fmin(hi[k], fmax(lo[k], fma(-step2, gh[k], x[k])));
+            dec2p = fma(gh[k], xn - x[k], dec2p);
+            x2[k] = xn;
+        }
+        Halo h2 = halo_send<T, K, EXACT>(x2, pt, sExF + ph * 32, sExL + ph * 32);
+        double dec = decp;
+        block_sum2<T>(Jn, dec, sRed + ph * 32, pt.lane, pt.warp);
+        halo_recv<T>(h2, pt, sExF + ph * 32, sExL + ph * 32);
+        ph ^= 1;
+        dec *= 2.0;                                   // back to grad . (a_new - alpha), main.cpp:733
+        if (Jn <= J + armijo_c * dec) {               // Armijo accept, main.cpp:734
+#pragma unroll
+            for (int k = 0; k < K; ++k) { sSt[k * T] = x[k]; x[k] = x2[k]; }
+            hx = h2; decp = dec2p; J = Jn;
+            o.acc++; it++; bt = 0;
+            if (fabs(Jprev - J) < 1e-10) break;       // main.cpp:740
+            Jprev = J;
+        } else {
+            step2 *= 0.5; bt++; o.bt++;               // main.cpp:737
+            if (0.5 * step2 < step_min || bt >= 20) break;   // not accepted: leave the inner loop (main.cpp:739)
+            // rebuild the trial from the accepted alpha: its gradient is recomputed (rejects are rare)
+            double a[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) a[k] = sSt[k * T];
+            Halo ha = halo_send<T, K, EXACT>(a, pt, sExF + ph * 32, sExL + ph * 32);
+            block_sync<T>();
+            halo_recv<T>(ha, pt, sExF + ph * 32, sExL + ph * 32);
+            ph ^= 1;
+            double jz = 0.0, sd = 0.0;
+            eval_window<T, K, EXACT>(a, ha, pt.cnt, sC0, sCp, sCm, cL, cR, lamJ, jz, sd, gh);
+            decp = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double xn = fmin(hi[k], fmax(lo[k], fma(-step2, gh[k], a[k])));
+                decp = fma(gh[k], xn - a[k], decp);
+                x[k] = xn;
+            }
+            hx = halo_send<T, K, EXACT>(x, pt, sExF + ph * 32, sExL + ph * 32);
+            block_sync<T>();
+            halo_recv<T>(hx, pt, sExF + ph * 32, sExL + ph * 32);
+            ph ^= 1;
+        }
+    }
+    o.Jend = J;
+    return o;
+}
+
+// ---- corridor (main.cpp:694-711, 749-756): rays +-n against both rings, exact nearest hit ----------------
+// Consecutive mapping (sample i = tid + j*T) so that a warp's 32 rays are neighbours and share boxes.
+// The +n and -n rays lie on one line: den, t, u of the -n ray are exactly -den, -t, u of the +n ray
+// (IEEE negation is exact), so one intersection serves both.  A box can only contain a hit if the
+// line crosses it, which prunes the brute-force loop of rayToRingDistance (main.cpp:491-500) without
+// changing its result.  A ring a ray misses entirely falls back to the nearest point-segment distance
+// (minDistanceToSegments_global, main.cpp:501-512), pruned by box lower bounds.
+// Results are returned in the BLOCKED layout through region B.
+template <int T, int K>
+__device__ __forceinline__ void corridor_build(const Part& pt, const double2* sP, double* sB, uint64_t* mbar, uint32_t& bar_phase,
+                                               const double* __restrict__ gseg, long long segI0, long long segO0, long long segE,
+                                               double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests)
+{
+    constexpr int NP = T * K;
+    constexpr int CAP = ((4 * NP * 8) / (32 + 32 / SB)) / SB * SB;   // segments per tile (+ one box per SB segments)
+    double* sSeg = sB;
+    double* sBox = sB + 4 * CAP;
+    const int N = pt.N, tid = pt.tid;
+    const double INF = dinf();
+    double dpos[K], dneg[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { dpos[j] = INF; dneg[j] = INF; }
+
+    for (int ring = 0; ring < 2; ++ring) {
+        const long long base = ring ? segO0 : segI0;
+        const int mr = (int)(ring ? (segE - segO0) : (segO0 - segI0));
+        if (mr == 0) {   // safe_ray on an empty ring returns 0 (main.cpp:696-697)
+#pragma unroll
+            for (int j = 0; j < K; ++j) { dpos[j] = fmin(dpos[j], 0.0); dneg[j] = fmin(dneg[j], 0.0); }
+            continue;
+        }
+        double pos[K], neg[K], dmin2[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { pos[j] = INF; neg[j] = INF; dmin2[j] = INF; }
+        const int ntiles = (mr + CAP - 1) / CAP;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                bool need = false;
+#pragma unroll
+                for (int j = 0; j < K; ++j) need = need || ((tid + j * T < N) && (pos[j] == INF || neg[j] == INF));
+                if (!block_or<T>(need)) break;
+            }
+            for (int tile = 0; tile < ntiles; ++tile) {
+                const int t0 = tile * CAP, nt = min(CAP, mr - t0), nblk = (nt + SB - 1) / SB;
+                if (pass == 0 || ntiles > 1) {
+                    block_sync<T>();
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(mbar, (uint32_t)nt * 32u);
+                        bulk_g2s(sSeg, gseg + 4 * (base + t0), (uint32_t)nt * 32u, mbar);
+                    }
+                    mbar_wait(mbar, bar_phase); bar_phase ^= 1;
+                    // boxes; segments become (x0, y0, vx, vy) with vx = x1-x0 as in main.cpp:482
+                    for (int bq = tid; bq < nblk; bq += T) {
+                        double xmin = INF, xmax = -INF, ymin = INF, ymax = -INF;
+                        const int e = min(nt, bq * SB + SB);
+                        for (int s = bq * SB; s < e; ++s) {
+                            const double x0 = sSeg[4 * s], y0 = sSeg[4 * s + 1], x1 = sSeg[4 * s + 2], y1 = sSeg[4 * s + 3];
+                            xmin = fmin(xmin, fmin(x0, x1)); xmax = fmax(xmax, fmax(x0, x1));
+                            ymin = fmin(ymin, fmin(y0, y1)); ymax = fmax(ymax, fmax(y0, y1));
+                            sSeg[4 * s + 2] = x1 - x0; sSeg[4 * s + 3] = y1 - y0;
+                        }
+                        const double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
+                        sBox[4 * bq] = cx; sBox[4 * bq + 1] = cy;
+                        sBox[4 * bq + 2] = 0.5 * (xmax - xmin) + 1e-9 + 1e-12 * fabs(cx);
+                        sBox[4 * bq + 3] = 0.5 * (ymax - ymin) + 1e-9 + 1e-12 * fabs(cy);
+                    }
+                    block_sync<T>();
+                }
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int i = tid + j * T;
+                    if (i >= N) continue;
+                    const double2 Pc = sP[i];
+                    if (pass == 0) {
+                        double nx, ny;
+                        normal_closed(sp_prev(sP, i, N), sp_next(sP, i, N), N, nx, ny);
+                        double bp = pos[j], bn = neg[j];
+                        for (int bq = 0; bq < nblk; ++bq) {
+                            const double cx = sBox[4 * bq], cy = sBox[4 * bq + 1], hx = sBox[4 * bq + 2], hy = sBox[4 * bq + 3];
+                            const double sc = nx * (cy - Pc.y) - ny * (cx - Pc.x);
+                            const double ext = fabs(nx) * hy + fabs(ny) * hx + 1e-7;
+                            if (fabs(sc) <= ext) {
+                                const int e = min(nt, bq * SB + SB);
+                                for (int s = bq * SB; s < e; ++s) {
+                                    const double x0 = sSeg[4 * s], y0 = sSeg[4 * s + 1], vx = sSeg[4 * s + 2], vy = sSeg[4 * s + 3];
+                                    const double den = nx * (-vy) + ny * vx;            // main.cpp:483
+                                    const double ax = x0 - Pc.x, ay = y0 - Pc.y;        // main.cpp:485
+                                    const double un = nx * ay - ny * ax;
+                                    const double aden = fabs(den);
+                                    const double us = (den > 0.0) ? un : -un;
+                                    // division-free prefilter, strictly wider than the exact test below
+                                    if (aden >= 1e-15 && us >= -2e-12 * aden && us <= aden + 2e-12 * aden) {
+                                        const double inv = 1.0 / den;
+                                        const double t = (ax * (-vy) + ay * vx) * inv;   // main.cpp:486
+                                        const double u = un * inv;                       // main.cpp:487
+                                        ++ray_tests;
+                                        if (u >= -1e-12 && u <= 1.0 + 1e-12) {           // main.cpp:488
+                                            if (t > 0.0) bp = fmin(bp, t);               // +n ray, main.cpp:497
+                                            else if (t < 0.0) bn = fmin(bn, -t);         // -n ray (t' = -t)
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        pos[j] = bp; neg[j] = bn;
+                    } else if (pos[j] == INF || neg[j] == INF) {
+                        // nearest point-segment distance to this ring (main.cpp:501-512), box-pruned
+                        const double ub = fmin(pos[j], neg[j]);   // a hit point lies on the ring
+                        double bound2 = (ub < INF) ? ub * ub * (1.0 + 1e-9) : INF;
+                        bound2 = fmin(bound2, dmin2[j] * (1.0 + 1e-9));
+                        double best2 = dmin2[j];
+                        for (int bq = 0; bq < nblk; ++bq) {
+                            const double cx = sBox[4 * bq], cy = sBox[4 * bq + 1], hx = sBox[4 * bq + 2], hy = sBox[4 * bq + 3];
+                            const double ddx = fmax(0.0, fabs(cx - Pc.x) - hx), ddy = fmax(0.0, fabs(cy - Pc.y) - hy);
+                            if (ddx * ddx + ddy * ddy <= bound2) {
+                                const int e = min(nt, bq * SB + SB);
+                                for (int s = bq * SB; s < e; ++s) {
+                                    const double x0 = sSeg[4 * s], y0 = sSeg[4 * s + 1], vx = sSeg[4 * s + 2], vy = sSeg[4 * s + 3];
+                                    const double apx = Pc.x - x0, apy = Pc.y - y0;
+                                    const double denom = fmax(1e-30, vx * vx + vy * vy);
+                                    const double tt = fmin(1.0, fmax(0.0, (vx * apx + vy * apy) / denom));
+                                    const double qx = x0 + vx * tt, qy = y0 + vy * tt;
+                                    const double ex = Pc.x - qx, ey = Pc.y - qy;
+                                    const double d2 = ex * ex + ey * ey;
+                                    best2 = fmin(best2, d2);
+                                    bound2 = fmin(bound2, d2 * (1.0 + 1e-9));
+                                }
+                            }
+                        }
+                        dmin2[j] = best2;
+                    }
+                }
+            }
+        }
+        // safe_ray + min over the two rings (main.cpp:704-705)
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double dist = (dmin2[j] < INF) ? sqrt(dmin2[j]) : 0.0;
+            const double vp = (pos[j] < INF) ? pos[j] : dist;
+            const double vn = (neg[j] < INF) ? neg[j] : dist;
+            dpos[j] = fmin(dpos[j], fmax(0.0, vp));
+            dneg[j] = fmin(dneg[j], fmax(0.0, vn));
+        }
+    }
+    // hi/lo (main.cpp:707-710), handed to the blocked layout through region B
+    block_sync<T>();
+    double* sLoS = sB;
+    double* sHiS = sB + NP;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int i = tid + j * T;
+        if (i < N) {
+            double hv = fmax(0.0, dpos[j] - guard);
+            double lv = -fmax(0.0, dneg[j] - guard);
+            if (!isfinite(hv)) hv = 0.0;
+            if (!isfinite(lv)) lv = 0.0;
+            sHiS[i] = hv; sLoS[i] = lv;
+        }
+    }
+    block_sync<T>();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        lo[k] = 0.0; hi[k] = 0.0;
+        if (k < pt.cnt) { lo[k] = sLoS[pt.start + k]; hi[k] = sHiS[pt.start + k]; }
+    }
+    block_sync<T>();
+}
+
+// ---- the solver kernel ------------------------------------------------------------------------------------
+template <int T, int K, bool EXACT>
+__global__ void __launch_bounds__(T, (512 / T) > 16 ? 16 : (512 / T))
+solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
+{
+    constexpr int NP = T * K;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* sP = reinterpret_cast<double2*>(smem_raw);
+    double* sB = reinterpret_cast<double*>(smem_raw + (size_t)NP * 16);
+    unsigned char* scr = smem_raw + (size_t)NP * 16 + (size_t)NP * 32;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(scr + kScrBar);
+    double* sRed = reinterpret_cast<double*>(scr + kScrRed);
+    double* sExF = reinterpret_cast<double*>(scr + kScrExF);
+    double* sExL = reinterpret_cast<double*>(scr + kScrExL);
+
+    if ((int)blockIdx.x >= n_list) return;
+    const int jid = job_list[blockIdx.x];
+    const rl_job job = B.jobs[jid];
+    const rl_params& C = B.params[job.param];
+    rl_job_stats* st = B.stats + jid;
+    const int trk = job.track;
+    const long long s0 = B.samp_off[trk];
+    const int N = (int)(B.samp_off[trk + 1] - s0);
+    const long long row0 = B.job_off[jid];
+    const bool mt = (job.stage == RL_STAGE_MINTIME);
+    const double h = B.track_L[trk] / (double)N;
+
+    // ---- blocked partition of the N samples over the threads ----
+    Part pt;
+    pt.N = N; pt.tid = threadIdx.x; pt.lane = pt.tid & 31; pt.warp = pt.tid >> 5;
+    {
+        const int tid = pt.tid;
+        pt.Tact = EXACT ? T : min(T, max(1, N / 2));
+        const int Kc = EXACT ? K : (N + pt.Tact - 1) / pt.Tact;
+        const int nfull = EXACT ? T : N - pt.Tact * (Kc - 1);
+        pt.cnt = EXACT ? K : (tid < pt.Tact ? (tid < nfull ? Kc : Kc - 1) : 0);
+        pt.start = EXACT ? tid * K : (tid < nfull ? tid * Kc : nfull * Kc + (tid - nfull) * (Kc - 1));
+        pt.tL = (tid == 0) ? pt.Tact - 1 : (tid < pt.Tact ? tid - 1 : 0);
+        pt.tR = (tid >= pt.Tact - 1) ? 0 : tid + 1;
+        pt.cntL = EXACT ? K : (pt.tL < nfull ? Kc : Kc - 1);
+        if (T == 32) { pt.srcL = pt.tL; pt.srcR = pt.tR; }
+        else { pt.srcL = (pt.lane + 31) & 31; pt.srcR = (pt.lane + 1) & 31; }
+    }
+    const int tid = pt.tid, cnt = pt.cnt, start = pt.start;
+
+    uint32_t bar_phase = 0;
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        st->status = RL_OK; st->n = N; st->outer_done = 0; st->accepted = 0; st->backtracks = 0; st->evals = 0;
+        st->vpass_rounds = 0; st->reserved = 0; st->ray_tests = 0; st->lap_time = 0.0;
+        for (int o = 0; o < RL_MAX_OUTER_LOG; ++o) {
+            st->J0[o] = 0.0; st->Jend[o] = 0.0; st->lap_outer[o] = 0.0; st->acc_outer[o] = 0; st->bt_outer[o] = 0;
+        }
+        fence_proxy_async();
+    }
+    block_sync<T>();
+
+    // ---- load the centre line into sP (TMA bulk copy of N*16 bytes) ----
+    if (tid == 0) {
+        mbar_expect_tx(mbar, (uint32_t)N * 16u);
+        bulk_g2s(sP, B.center_xy + 2 * s0, (uint32_t)N * 16u, mbar);
+    }
+    mbar_wait(mbar, bar_phase); bar_phase ^= 1;
+
+    // alpha_total rows are accumulated by their owning thread (blocked layout)
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if (k < cnt) { B.alpha_total[row0 + start + k] = 0.0; B.alpha_last[row0 + start + k] = 0.0; }
+
+    VPar q;
+    q.v_cap = C.v_cap_mps; q.a_lat_max = C.a_lat_max; q.kappa_eps = C.kappa_eps;
+    {
+        const double a_total = C.use_total_ge_lat ? fmax(C.a_total_max, C.a_lat_max) : C.a_total_max;   // main.cpp:802-804
+        q.a_tot2 = a_total * a_total;
+    }
+    q.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; q.Fr = C.mass_kg * 9.81 * C.c_rr; q.mass = C.mass_kg; q.P = C.P_max_W;
+    q.acc_cap = C.a_long_acc_cap; q.brk_cap = C.a_long_brake_cap; q.h = h; q.has_power = (C.P_max_W > 0);
+
+    const long long segI0 = B.seg_off[2 * trk], segO0 = B.seg_off[2 * trk + 1], segE = B.seg_off[2 * trk + 2];
+    const double inv2h = 1.0 / (2 * h), invh2 = 1.0 / (h * h);          // DiffOps, main.cpp:547
+    const double lamJ = C.lambda_smooth * inv2h * inv2h;
+    long long ray_tests = 0;
+    int vrounds = 0, ph = 0;
+    int acc_total = 0, bt_total = 0, ev_total = 0;
+    const int max_outer = C.max_outer_iters;
+
+    double lo[K], hi[K];
+    // initial corridor from the centre line: guard uses the veh_width ARGUMENT (main.cpp:706 / 930)
+    corridor_build<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,
+                         C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+
+    double* sC0 = sB + tid;
+    double* sCp = sB + NP + tid;
+    double* sCm = sB + 2 * NP + tid;
+    double* sSt = sB + 3 * NP + tid;
+
+    for (int outer = 0; outer < max_outer; ++outer) {
+        // =================== linearisation (main.cpp:722 / 941-944) ===================
+        double A1[K], A2[K], N0[K], Wd[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            A1[k] = 0.0; A2[k] = 0.0; N0[k] = 0.0; Wd[k] = 1.0;
+            if (k < cnt) {
+                const int i = start + k;
+                const double2 Pm = sp_prev(sP, i, N), Pc = sP[i], Pp = sp_next(sP, i, N);
+                double nx, ny, xp, yp, xpp, ypp;
+                normal_closed(Pm, Pp, N, nx, ny);
+                derivs_closed(Pm, Pc, Pp, h, N, xp, yp, xpp, ypp);
+                A1[k] = nx * ypp - ny * xpp;          // main.cpp:644-646
+                A2[k] = xp * ny - yp * nx;
+                N0[k] = xp * ypp - yp * xpp;
+                Wd[k] = pow15(xp * xp + yp * yp);     // denom; W = 1/denom (main.cpp:647-648)
+            }
+        }
+        double gam[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) gam[k] = 1.0;
+        double lap_outer = 0.0;
+        if (mt) {
+            // ============ v(s) profile + time weights (main.cpp:944-977) ============
+            double kap[K], vv[K], axd[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) kap[k] = (k < cnt) ? N0[k] / Wd[k] : 0.0;    // kappa, main.cpp:618
+            block_sync<T>();   // region B is free: lo/hi are in registers, coefficients not yet built
+            vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds);
+            block_sync<T>();
+            lap_outer = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32);
+            ph ^= 1;
+            double v_avg = 0.0;
+            if (C.time_weight_use_inv_v) {            // main.cpp:951
+                double sv = 0.0, dz = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) if (k < cnt) sv += vv[k];
+                block_sum2<T>(sv, dz, sRed + ph * 32, pt.lane, pt.warp);
+                ph ^= 1;
+                v_avg = sv / (double)max(1, N);
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k < cnt) {                         // main.cpp:954-975
+                    const double vk = sqrt(C.a_lat_max / fmax(fabs(kap[k]), C.kappa_eps));
+                    double r = fmin(1.0, vv[k] / fmax(1e-6, vk));
+                    r = r * r;
+                    r = fmin(1.0, fmax(0.0, r));
+                    const double pw = C.time_gamma_power;
+                    const double rp = (pw == 2.0) ? r * r : ((pw == 1.0) ? r : pow(r, pw));
+                    const double corner_w = 1.0 + C.w_time_gain * rp;
+                    double invv_w = 1.0;
+                    if (C.time_weight_use_inv_v) {
+                        const double ratio = v_avg / fmax(1e-6, vv[k]);
+                        invv_w = 1.0 + C.inv_v_gain * (ratio - 1.0);
+                        if (invv_w < 1.0) invv_w = 1.0;
+                        if (invv_w > 3.0) invv_w = 3.0;
+                    }
+                    gam[k] = corner_w * invv_w;
+                }
+            }
+            block_sync<T>();
+        }
+        // ---- stencil coefficients into region B (slot-major) ----
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double c0 = 0.0, cp = 0.0, cm = 0.0;
+            if (k < cnt) {
+                const double gw = gam[k] / Wd[k];
+                c0 = gw * N0[k];
+                const double c1 = gw * A1[k] * inv2h, c2 = gw * A2[k] * invh2;
+                cp = c1 + c2; cm = c2 - c1;
+            }
+            sC0[k * T] = c0; sCp[k * T] = cp; sCm[k * T] = cm;
+        }
+        block_sync<T>();
+        double cL[3], cR[3];
+        {
+            const int kl = pt.cntL - 1;
+            const double* b0 = sB + pt.tL; const double* br = sB + pt.tR;
+            cL[0] = b0[kl * T]; cL[1] = b0[NP + kl * T]; cL[2] = b0[2 * NP + kl * T];
+            cR[0] = br[0]; cR[1] = br[NP]; cR[2] = br[2 * NP];
+        }
+        if (!EXACT) {
+            // the first unused slot mirrors the right neighbour's first sample (position cnt+1 of the window)
+            if (cnt < K && cnt > 0) { sC0[cnt * T] = cR[0]; sCp[cnt * T] = cR[1]; sCm[cnt * T] = cR[2]; }
+        }
+        // =================== projected gradient with Armijo (main.cpp:723-742 / 996-1026) ===================
+        const PgdOut po = pgd_outer<T, K, EXACT>(pt, lo, hi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,
+                                                 C.step_init, C.step_min, C.armijo_c, C.max_inner_iters);
+        acc_total += po.acc; bt_total += po.bt; ev_total += po.ev;
+        if (tid == 0 && outer < RL_MAX_OUTER_LOG) {
+            st->J0[outer] = po.J0; st->Jend[outer] = po.Jend; st->lap_outer[outer] = lap_outer;
+            st->acc_outer[outer] = po.acc; st->bt_outer[outer] = po.bt;
+        }
+        // =================== path update (main.cpp:743-746 / 1027-1031) ===================
+        double2 Pn[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (k < cnt) {
+                const int i = start + k;
+                const double al = sSt[k * T];
+                double nx, ny;
+                normal_closed(sp_prev(sP, i, N), sp_next(sP, i, N), N, nx, ny);
+                const double2 Pc = sP[i];
+                Pn[k].x = Pc.x + nx * al; Pn[k].y = Pc.y + ny * al;
+                B.alpha_total[row0 + i] += al;
+                if (outer == max_outer - 1) B.alpha_last[row0 + i] = al;
+            }
+        }
+        block_sync<T>();
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (k < cnt) sP[start + k] = Pn[k];
+        block_sync<T>();
+        // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
+        corridor_build<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,
+                             C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+    }
+
+    // =================== final geometry (main.cpp:761 / 1046) ===================
+    block_sync<T>();
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int i = tid + j * T;
+        if (i < N) {
+            double xp, yp, xpp, ypp;
+            derivs_closed(sp_prev(sP, i, N), sP[i], sp_next(sP, i, N), h, N, xp, yp, xpp, ypp);
+            B.heading[row0 + i] = atan2(yp, xp);
+            B.curvature[row0 + i] = (xp * ypp - yp * xpp) / pow15(xp * xp + yp * yp);
+        }
+    }
+    double lap = 0.0;
+    if (mt) {
+        // final v(s) profile (main.cpp:1047)
+        double kap[K], vv[K], axd[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            kap[k] = 0.0;
+            if (k < cnt) {
+                const int i = start + k;
+                double xp, yp, xpp, ypp;
+                derivs_closed(sp_prev(sP, i, N), sP[i], sp_next(sP, i, N), h, N, xp, yp, xpp, ypp);
+                kap[k] = (xp * ypp - yp * xpp) / pow15(xp * xp + yp * yp);
+            }
+        }
+        block_sync<T>();
+        vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds);
+        block_sync<T>();
+        lap = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32);
+        ph ^= 1;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (k < cnt) { B.v[row0 + start + k] = vv[k]; B.ax[row0 + start + k] = axd[k]; }
+    }
+    // raceline out: TMA bulk store of sP
+    fence_proxy_async();
+    block_sync<T>();
+    if (tid == 0) bulk_s2g(B.xy + 2 * row0, sP, (uint32_t)N * 16u);
+
+    // counters
+    {
+        double rt = (double)ray_tests, dz = 0.0;
+        block_sum2<T>(rt, dz, sRed + ph * 32, pt.lane, pt.warp);
+        ph ^= 1;
+        if (tid == 0) {
+            st->outer_done = max_outer; st->accepted = acc_total; st->backtracks = bt_total; st->evals = ev_total;
+            st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap;
+        }
+    }
+}
+
+// FP64 FMA throughput probe: 8 independent chains per thread, 2 flops per FMA.
+__global__ void fp64_peak_kernel(double* out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int T, int K, bool EXACT>
+cudaError_t launch_one(const DevBatch& B, const int* job_list, int n_list, cudaStream_t s)
+{
+    const size_t smem = smem_bytes_for_class(T, K);
+    solve_kernel<T, K, EXACT><<<n_list, T, smem, s>>>(B, job_list, n_list);
+    return cudaGetLastError();
+}
+template <int T, int K, bool EXACT>
+cudaError_t configure_one()
+{
+    return cudaFuncSetAttribute(solve_kernel<T, K, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_bytes_for_class(T, K));
+}
+
+}  // namespace
+
+int configure_kernels()
+{
+    cudaError_t e = cudaSuccess;
+#define RL_CFG(T, K)                                                      \
+    if (e == cudaSuccess) e = configure_one<T, K, false>();               \
+    if (e == cudaSuccess) e = configure_one<T, K, true>();
+    RL_CFG(32, 8) RL_CFG(64, 8) RL_CFG(128, 8) RL_CFG(256, 8) RL_CFG(512, 8)
+#undef RL_CFG
+    return (int)e;
+}
+
+int launch_solve(const DevBatch& B, const int* job_list, int n_list, int cls, bool exact, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_list <= 0) return 0;
+    cudaError_t e = cudaErrorInvalidValue;
+#define RL_CASE(IDX, T, K)                                                                                       \
+    case IDX: e = exact ? launch_one<T, K, true>(B, job_list, n_list, s) : launch_one<T, K, false>(B, job_list, n_list, s); break;
+    switch (cls) {
+        RL_CASE(0, 32, 8) RL_CASE(1, 64, 8) RL_CASE(2, 128, 8) RL_CASE(3, 256, 8) RL_CASE(4, 512, 8)
+        default: break;
+    }
+#undef RL_CASE
+    return (int)e;
+}
+
+int launch_fp64_peak(double* d_out, int blocks, int threads, int iters, void* stream)
+{
+    fp64_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_out, iters);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace rl

@@ -1,0 +1,407 @@
+"""Host-side mirror of the reference's solver interface, over the C ABI (include/raceline_b200.h).
+
+Reference boundary (tjsdn3065/Practice_path_planning_for_formula_student_driverless, src/main.cpp):
+
+    raceline_min_curv::compute_min_curvature_raceline(center, innerE, outerE, veh_width, L, closed) -> Result   :683
+    raceline_min_time::compute_min_time_raceline(center, innerE, outerE, veh_width, L, closed)      -> Result   :905
+    cfg::Config                                                                                                :47-119
+    edges::ringEdges / edges::polylineEdges                                                                     :251 / :256
+
+Same names, same argument meaning, same Result fields; Config is passed explicitly instead of the
+process-global cfg::get().  The batched form (`solve_batch`) is the data-parallel version of the two
+calls at main.cpp:1347 and main.cpp:1397.  Everything here runs through the CUDA library; there is no
+CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from ._abi import (RL_OK, RL_STAGE_MINCURV, RL_STAGE_MINTIME, RlBatchDesc, RlBatchOut, RlJob, RlJobStats,
+                   RlParams)
+from ._lib import lib
+
+
+class RacelineError(RuntimeError):
+    def __init__(self, status, detail=""):
+        self.status = status
+        msg = lib().rl_status_string(status).decode()
+        super().__init__(f"raceline_b200: {msg} ({status}){': ' + detail if detail else ''}")
+
+
+# ------------------------------------------------------------------------------------------------
+# cfg::Config (main.cpp:47-119): the fields the min-curv / min-time stages read
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Config:
+    is_closed_track: bool = True          # main.cpp:54
+    veh_width_m: float = 1.0              # :77
+    safety_margin_m: float = 0.05         # :78
+    lambda_smooth: float = 1.6e-3         # :81
+    max_outer_iters: int = 14             # :82
+    max_inner_iters: int = 120            # :83
+    step_init: float = 0.65               # :84
+    step_min: float = 1e-6                # :85
+    armijo_c: float = 1e-5                # :86
+    kappa_eps: float = 1e-6               # :89
+    v_cap_mps: float = 27.0               # :90
+    mass_kg: float = 255.0                # :93
+    Cd: float = 0.30                      # :94
+    A_front_m2: float = 1.00              # :95
+    rho_air: float = 1.225                # :96
+    c_rr: float = 0.015                   # :97
+    P_max_W: float = 80000.0              # :98
+    mu: float = 1.17                      # :101
+    a_total_max: Optional[float] = None   # :102  mu*9.81, evaluated once at construction like the reference
+    a_lat_max: float = 11.0               # :103
+    a_long_acc_cap: float = 8.0           # :104
+    a_long_brake_cap: float = 11.0        # :105
+    w_time_gain: float = 1.0              # :108
+    time_gamma_power: float = 2.0         # :109
+    time_weight_use_inv_v: bool = False   # :110
+    inv_v_gain: float = 0.1               # :111
+    max_vpass_iters: int = 6              # :112
+    use_total_ge_lat: bool = True         # :113
+
+    def __post_init__(self):
+        if self.a_total_max is None:
+            self.a_total_max = self.mu * 9.81
+
+    def to_params(self, veh_width: Optional[float] = None) -> RlParams:
+        p = RlParams()
+        p.veh_width_arg = self.veh_width_m if veh_width is None else float(veh_width)
+        for name in ("veh_width_m", "safety_margin_m", "lambda_smooth", "step_init", "step_min", "armijo_c", "kappa_eps",
+                     "v_cap_mps", "mass_kg", "Cd", "A_front_m2", "rho_air", "c_rr", "P_max_W", "a_total_max", "a_lat_max",
+                     "a_long_acc_cap", "a_long_brake_cap", "w_time_gain", "time_gamma_power", "inv_v_gain"):
+            setattr(p, name, float(getattr(self, name)))
+        p.max_outer_iters = int(self.max_outer_iters)
+        p.max_inner_iters = int(self.max_inner_iters)
+        p.max_vpass_iters = int(self.max_vpass_iters)
+        p.time_weight_use_inv_v = int(bool(self.time_weight_use_inv_v))
+        p.use_total_ge_lat = int(bool(self.use_total_ge_lat))
+        return p
+
+
+def ring_edges(R) -> np.ndarray:
+    """edges::ringEdges (main.cpp:251): closed ring of cones -> (M,4) segments x0,y0,x1,y1."""
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 2)
+    return np.concatenate([R, np.roll(R, -1, axis=0)], axis=1) if len(R) else np.zeros((0, 4))
+
+
+def polyline_edges(R) -> np.ndarray:
+    """edges::polylineEdges (main.cpp:256): open cone chain -> (M-1,4) segments."""
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 2)
+    return np.concatenate([R[:-1], R[1:]], axis=1) if len(R) >= 2 else np.zeros((0, 4))
+
+
+@dataclass
+class Track:
+    """The solver arguments that describe one track (main.cpp:683-686)."""
+    center_xy: np.ndarray      # (N,2) centre samples, closing duplicate dropped (main.cpp:1681-1683)
+    inner_seg: np.ndarray      # (M_in,4)  innerE
+    outer_seg: np.ndarray      # (M_out,4) outerE
+    L: float                   # CL.L
+    closed: bool = True
+
+
+@dataclass
+class Result:
+    """raceline_min_curv::Result (main.cpp:677-681) / raceline_min_time::Result (main.cpp:897-903)."""
+    raceline: np.ndarray
+    heading: np.ndarray
+    curvature: np.ndarray
+    alpha_total: np.ndarray
+    alpha_last: np.ndarray
+    v: Optional[np.ndarray] = None
+    ax: Optional[np.ndarray] = None
+    lap_time: float = 0.0
+    stats: Optional[RlJobStats] = None
+
+
+def _f64(a, cols=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a.reshape(-1, cols) if cols else a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class PinnedPool:
+    """Page-locked numpy arrays (rl_host_alloc) so that H2D/D2H copies are asynchronous."""
+
+    def __init__(self):
+        self._ptrs = []
+
+    def empty(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        nbytes = max(1, n * dtype.itemsize)
+        p = lib().rl_host_alloc(nbytes)
+        if not p:
+            raise MemoryError("rl_host_alloc failed")
+        self._ptrs.append(p)
+        buf = (C.c_char * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def copy(self, a):
+        out = self.empty(a.shape, a.dtype)
+        out[...] = a
+        return out
+
+    def close(self):
+        for p in self._ptrs:
+            lib().rl_host_free(p)
+        self._ptrs = []
+
+
+class PackedBatch:
+    """Host arrays in the rl_batch_desc layout + the matching output arrays."""
+
+    def __init__(self, tracks: Sequence[Track], params: Sequence[RlParams], jobs, pool: Optional[PinnedPool] = None):
+        alloc = (lambda shape, dt: pool.empty(shape, dt)) if pool else (lambda shape, dt: np.empty(shape, dtype=dt))
+        self.n_tracks, self.n_params = len(tracks), len(params)
+        ns = [int(_f64(t.center_xy, 2).shape[0]) for t in tracks]
+        mi = [int(_f64(t.inner_seg, 4).shape[0]) for t in tracks]
+        mo = [int(_f64(t.outer_seg, 4).shape[0]) for t in tracks]
+        self.samp_off = alloc(self.n_tracks + 1, np.int64)
+        self.samp_off[0] = 0
+        self.samp_off[1:] = np.cumsum(ns)
+        self.seg_off = alloc(2 * self.n_tracks + 1, np.int64)
+        self.seg_off[0] = 0
+        inter = np.empty(2 * self.n_tracks, dtype=np.int64)
+        inter[0::2], inter[1::2] = mi, mo
+        self.seg_off[1:] = np.cumsum(inter)
+        self.center_xy = alloc((int(self.samp_off[-1]), 2), np.float64)
+        self.seg = alloc((int(self.seg_off[-1]), 4), np.float64)
+        self.track_L = alloc(self.n_tracks, np.float64)
+        self.track_closed = alloc(self.n_tracks, np.int32)
+        for t, tr in enumerate(tracks):
+            self.center_xy[self.samp_off[t]:self.samp_off[t + 1]] = _f64(tr.center_xy, 2)
+            self.seg[self.seg_off[2 * t]:self.seg_off[2 * t + 1]] = _f64(tr.inner_seg, 4)
+            self.seg[self.seg_off[2 * t + 1]:self.seg_off[2 * t + 2]] = _f64(tr.outer_seg, 4)
+            self.track_L[t] = float(tr.L)
+            self.track_closed[t] = int(bool(tr.closed))
+        self._finish(params, jobs, alloc)
+
+    @classmethod
+    def from_arrays(cls, samp_off, seg_off, center_xy, seg, track_L, track_closed, params, jobs, pool=None):
+        """Wrap arrays that are already in the packed layout (no per-track copies)."""
+        self = cls.__new__(cls)
+        alloc = (lambda shape, dt: pool.empty(shape, dt)) if pool else (lambda shape, dt: np.empty(shape, dtype=dt))
+        self.n_tracks, self.n_params = len(track_L), len(params)
+        self.samp_off = np.ascontiguousarray(samp_off, dtype=np.int64)
+        self.seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        self.center_xy = _f64(center_xy, 2)
+        self.seg = _f64(seg, 4)
+        self.track_L = _f64(track_L)
+        self.track_closed = np.ascontiguousarray(track_closed, dtype=np.int32)
+        self._finish(params, jobs, alloc)
+        return self
+
+    def _finish(self, params, jobs, alloc):
+        jobs = np.asarray(jobs, dtype=np.int64).reshape(-1, 3)
+        self.n_jobs = jobs.shape[0]
+        self.params = (RlParams * max(1, self.n_params))(*params)
+        self.jobs_np = jobs
+        self.jobs = (RlJob * max(1, self.n_jobs))()
+        for j, (t, p, s) in enumerate(jobs):
+            self.jobs[j].track, self.jobs[j].param, self.jobs[j].stage = int(t), int(p), int(s)
+        self.desc = RlBatchDesc()
+        self.desc.n_tracks, self.desc.n_params, self.desc.n_jobs = self.n_tracks, self.n_params, self.n_jobs
+        self.desc.samp_off = _ptr(self.samp_off) or self.samp_off.ctypes.data
+        self.desc.seg_off = _ptr(self.seg_off) or self.seg_off.ctypes.data
+        self.desc.center_xy = _ptr(self.center_xy)
+        self.desc.seg = _ptr(self.seg)
+        self.desc.track_L = _ptr(self.track_L)
+        self.desc.track_closed = _ptr(self.track_closed)
+        self.desc.params = C.cast(self.params, C.c_void_p)
+        self.desc.jobs = C.cast(self.jobs, C.c_void_p)
+        ns = np.diff(self.samp_off)
+        self.job_off = np.zeros(self.n_jobs + 1, dtype=np.int64)
+        if self.n_jobs:
+            self.job_off[1:] = np.cumsum(ns[jobs[:, 0]])
+        rows = int(self.job_off[-1])
+        self.rows = rows
+        self.out_xy = alloc((rows, 2), np.float64)
+        self.out_heading = alloc(rows, np.float64)
+        self.out_curvature = alloc(rows, np.float64)
+        self.out_alpha_total = alloc(rows, np.float64)
+        self.out_alpha_last = alloc(rows, np.float64)
+        self.out_v = alloc(rows, np.float64)
+        self.out_ax = alloc(rows, np.float64)
+        self.out_stats = (RlJobStats * max(1, self.n_jobs))()
+        self.out = RlBatchOut()
+        self.out.xy, self.out.heading, self.out.curvature = _ptr(self.out_xy), _ptr(self.out_heading), _ptr(self.out_curvature)
+        self.out.alpha_total, self.out.alpha_last = _ptr(self.out_alpha_total), _ptr(self.out_alpha_last)
+        self.out.v, self.out.ax = _ptr(self.out_v), _ptr(self.out_ax)
+        self.out.stats = C.cast(self.out_stats, C.c_void_p)
+
+    @property
+    def h2d_bytes(self):
+        return int(self.samp_off.nbytes + self.seg_off.nbytes + self.center_xy.nbytes + self.seg.nbytes +
+                   self.track_L.nbytes + self.track_closed.nbytes + C.sizeof(RlParams) * self.n_params +
+                   C.sizeof(RlJob) * self.n_jobs)
+
+    @property
+    def d2h_bytes(self):
+        return int(self.rows * 8 * 8 + C.sizeof(RlJobStats) * self.n_jobs)
+
+    def result(self, j) -> Result:
+        a, b = int(self.job_off[j]), int(self.job_off[j + 1])
+        st = self.out_stats[j]
+        mt = int(self.jobs_np[j, 2]) == RL_STAGE_MINTIME
+        return Result(self.out_xy[a:b], self.out_heading[a:b], self.out_curvature[a:b], self.out_alpha_total[a:b],
+                      self.out_alpha_last[a:b], self.out_v[a:b] if mt else None, self.out_ax[a:b] if mt else None,
+                      float(st.lap_time), st)
+
+
+class Context:
+    """One context per device: replaces the reference's process-global cfg::get() state (main.cpp:120)."""
+
+    def __init__(self, device: int = 0):
+        st = C.c_int(0)
+        self._h = lib().rl_create(int(device), C.byref(st))
+        if not self._h:
+            raise RacelineError(st.value, "rl_create")
+        self.device = device
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        lib().rl_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None)
+
+    def _check(self, st, what=""):
+        if st != RL_OK:
+            raise RacelineError(st, (what + " " + lib().rl_last_error(self._h).decode()).strip())
+
+    def solve_batch(self, batch: PackedBatch) -> PackedBatch:
+        """Host buffers in, host buffers out (rl_solve_batch)."""
+        self._check(lib().rl_solve_batch(self._h, C.byref(batch.desc), C.byref(batch.out)), "rl_solve_batch")
+        return batch
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double(0)
+        self._check(lib().rl_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self._h:
+            lib().rl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBatch:
+    """A device-resident batch (rl_batch_*): upload once, solve many times."""
+
+    def __init__(self, ctx: Context, batch: PackedBatch):
+        st = C.c_int(0)
+        self.ctx, self.host = ctx, batch
+        self._h = lib().rl_batch_create(ctx._h, C.byref(batch.desc), C.byref(st))
+        if not self._h:
+            ctx._check(st.value, "rl_batch_create")
+
+    def upload(self):
+        self.ctx._check(lib().rl_batch_upload(self._h, C.byref(self.host.desc)), "rl_batch_upload")
+
+    def solve(self):
+        self.ctx._check(lib().rl_batch_solve(self._h), "rl_batch_solve")
+
+    def download(self):
+        self.ctx._check(lib().rl_batch_download(self._h, C.byref(self.host.out)), "rl_batch_download")
+
+    def sync(self):
+        self.ctx._check(lib().rl_batch_sync(self._h), "rl_batch_sync")
+
+    @property
+    def launches_per_solve(self):
+        return lib().rl_batch_launches_per_solve(self._h)
+
+    def close(self):
+        if self._h:
+            lib().rl_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_DEFAULT_CTX: List[Optional[Context]] = [None]
+
+
+def default_context() -> Context:
+    if _DEFAULT_CTX[0] is None:
+        _DEFAULT_CTX[0] = Context(0)
+    return _DEFAULT_CTX[0]
+
+
+def _single(stage, center, innerE, outerE, veh_width, L, closed, cfg, ctx):
+    cfg = cfg or Config()
+    ctx = ctx or default_context()
+    center = _f64(center, 2)
+    innerE, outerE = _f64(innerE, 4), _f64(outerE, 4)
+    n = center.shape[0]
+    p = cfg.to_params(veh_width)
+    dp = C.POINTER(C.c_double)
+    xy, hd, kp, at, al = np.zeros((n, 2)), np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    st = RlJobStats()
+
+    def P(a):
+        return a.ctypes.data_as(dp)
+
+    common = [ctx._h, P(center), n, P(innerE), innerE.shape[0], P(outerE), outerE.shape[0], float(veh_width), float(L),
+              int(bool(closed)), C.byref(p), P(xy), P(hd), P(kp), P(at), P(al)]
+    if stage == RL_STAGE_MINCURV:
+        rc = lib().rl_compute_min_curvature_raceline(*common, C.byref(st))
+        ctx._check(rc, "rl_compute_min_curvature_raceline")
+        return Result(xy, hd, kp, at, al, stats=st)
+    v, ax, lap = np.zeros(n), np.zeros(n), C.c_double(0)
+    rc = lib().rl_compute_min_time_raceline(*common, P(v), P(ax), C.byref(lap), C.byref(st))
+    ctx._check(rc, "rl_compute_min_time_raceline")
+    return Result(xy, hd, kp, at, al, v, ax, lap.value, st)
+
+
+def compute_min_curvature_raceline(center, innerE, outerE, veh_width, L, closed, cfg: Optional[Config] = None,
+                                   ctx: Optional[Context] = None) -> Result:
+    """raceline_min_curv::compute_min_curvature_raceline (main.cpp:683-764) on the GPU."""
+    return _single(RL_STAGE_MINCURV, center, innerE, outerE, veh_width, L, closed, cfg, ctx)
+
+
+def compute_min_time_raceline(center, innerE, outerE, veh_width, L, closed, cfg: Optional[Config] = None,
+                              ctx: Optional[Context] = None) -> Result:
+    """raceline_min_time::compute_min_time_raceline (main.cpp:905-1052) on the GPU."""
+    return _single(RL_STAGE_MINTIME, center, innerE, outerE, veh_width, L, closed, cfg, ctx)
+
+
+def solve_batch(tracks: Sequence[Track], configs: Sequence[Config], jobs, ctx: Optional[Context] = None,
+                veh_width: Optional[float] = None) -> List[Result]:
+    """Solve jobs = [(track index, config index, stage), ...] in one batched call."""
+    ctx = ctx or default_context()
+    pb = PackedBatch(tracks, [c.to_params(veh_width) for c in configs], jobs)
+    ctx.solve_batch(pb)
+    return [pb.result(j) for j in range(pb.n_jobs)]
+
+
+def synth_tracks(n_tracks, n_samples, m_per_ring=None, seed_base=0xB200, first_id=0, threads=0, pool=None):
+    """Deterministic synthetic closed tracks; returns packed arrays (center_xy, seg, L)."""
+    m = int(round(n_samples / 2.2)) if m_per_ring is None else int(m_per_ring)
+    alloc = (lambda shape: pool.empty(shape, np.float64)) if pool else (lambda shape: np.empty(shape, dtype=np.float64))
+    center = alloc((n_tracks * n_samples, 2))
+    seg = alloc((n_tracks * 2 * m, 4))
+    L = alloc(n_tracks)
+    dp = C.POINTER(C.c_double)
+    rc = lib().rl_synth_tracks(C.c_uint64(seed_base), C.c_int64(first_id), n_tracks, n_samples, m, threads,
+                               center.ctypes.data_as(dp), seg.ctypes.data_as(dp), L.ctypes.data_as(dp))
+    if rc != RL_OK:
+        raise RacelineError(rc, "rl_synth_tracks")
+    return center, seg, L, m

@@ -1,0 +1,70 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+MAPS = ["training_map", "competition_map1", "competition_map2", "competition_map3",
+        "competition_map_testday1", "competition_map_testday2", "competition_map_testday3"]
+
+# north_star tolerances (BASELINE.json): alpha 1e-4 m, kappa 1e-6 1/m, v 1e-4 m/s, lap 1e-5 relative
+TOL_ALPHA = 1e-4
+TOL_KAPPA = 1e-6
+TOL_V = 1e-4
+TOL_LAP_REL = 1e-5
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    d = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    return {k: (v.item() if v.ndim == 0 else v) for k, v in d.items()}
+
+
+@pytest.fixture(scope="session")
+def goldens():
+    return {m: load_golden(m) for m in MAPS}
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    import practice_path_planning_for_formula_student_driverless_b200 as rl
+    c = rl.Context(0)
+    yield c
+    c.close()
+
+
+def angle_diff(a, b):
+    d = np.asarray(a) - np.asarray(b)
+    return np.abs((d + np.pi) % (2 * np.pi) - np.pi)
+
+
+def assert_result_close(res, ref, pre, mt, tag=""):
+    """res: rl.Result; ref: dict with keys pre+'_xy' etc (reference outputs)."""
+    def mx(a, b):
+        return float(np.max(np.abs(np.asarray(a) - np.asarray(b)))) if len(a) else 0.0
+    errs = {
+        "xy": mx(res.raceline, ref[pre + "xy"]),
+        "alpha_total": mx(res.alpha_total, ref[pre + "alpha_total"]),
+        "alpha_last": mx(res.alpha_last, ref[pre + "alpha_last"]),
+        "curvature": mx(res.curvature, ref[pre + "curvature"]),
+        "heading": float(np.max(angle_diff(res.heading, ref[pre + "heading"]))) if len(res.heading) else 0.0,
+    }
+    assert errs["xy"] <= TOL_ALPHA, (tag, errs)
+    assert errs["alpha_total"] <= TOL_ALPHA, (tag, errs)
+    assert errs["alpha_last"] <= TOL_ALPHA, (tag, errs)
+    assert errs["curvature"] <= TOL_KAPPA, (tag, errs)
+    assert errs["heading"] <= 1e-6, (tag, errs)
+    if mt:
+        errs["v"] = mx(res.v, ref[pre + "v"])
+        errs["ax"] = mx(res.ax, ref[pre + "ax"])
+        assert errs["v"] <= TOL_V, (tag, errs)
+        assert errs["ax"] <= 1e-3, (tag, errs)
+    return errs

@@ -1,0 +1,134 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol, host-side logic, sharding over gloo."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import practice_path_planning_for_formula_student_driverless_b200 as rl
+from conftest import ROOT
+from practice_path_planning_for_formula_student_driverless_b200 import _lib, sharding
+from practice_path_planning_for_formula_student_driverless_b200._abi import RlJobStats, RlParams
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "raceline_b200.h")).read()
+    declared = set(re.findall(r"^[a-z_ \*0-9]*?\b(rl_[a-z0-9_]+)\(", hdr, flags=re.M))
+    assert declared == set(_lib.ABI_SYMBOLS), declared ^ set(_lib.ABI_SYMBOLS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.rl_abi_version() == rl.RL_ABI_VERSION
+    assert L.rl_status_string(rl.RL_ERR_UNSUPPORTED) == b"unsupported problem shape"
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(RlParams) == 22 * 8 + 6 * 4
+    assert C.sizeof(RlJobStats) == 8 * 4 + 8 + 8 + 3 * 8 * rl.RL_MAX_OUTER_LOG + 2 * 4 * rl.RL_MAX_OUTER_LOG
+    assert RlJobStats.lap_time.offset == 40 and RlJobStats.J0.offset == 48
+
+
+def test_default_params_match_reference_config():
+    p = RlParams()
+    assert _lib.lib().rl_default_params(C.byref(p)) == 0
+    q = rl.Config().to_params()
+    from oracle import oracle
+    o = oracle.default_params()
+    for name, _ in RlParams._fields_:
+        assert getattr(p, name) == getattr(q, name) == getattr(o, name), name
+    assert abs(p.a_total_max - 1.17 * 9.81) < 1e-15 and p.max_outer_iters == 14 and p.max_inner_iters == 120
+
+
+def test_no_device_fails_loudly_without_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rl.RacelineError) as e:
+        rl.Context(0)
+    assert e.value.status == rl.RL_ERR_NODEVICE
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "practice_path_planning_for_formula_student_driverless_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no CPU fallback", ""), f
+
+
+def test_edges_and_packing():
+    ring = np.array([[0.0, 0], [1, 0], [1, 1]])
+    e = rl.ring_edges(ring)
+    assert e.shape == (3, 4) and np.array_equal(e[2], [1, 1, 0, 0])
+    assert rl.polyline_edges(ring).shape == (2, 4)
+    t0 = rl.Track(np.zeros((5, 2)), e, e[:2], 5.0)
+    t1 = rl.Track(np.ones((3, 2)), e[:1], e, 3.0)
+    pb = rl.PackedBatch([t0, t1], [rl.Config().to_params()], [(1, 0, 1), (0, 0, 2), (1, 0, 2)])
+    assert list(pb.samp_off) == [0, 5, 8] and list(pb.seg_off) == [0, 3, 5, 6, 9]
+    assert list(pb.job_off) == [0, 3, 8, 11] and pb.rows == 11
+    off = (C.c_int64 * 4)()
+    assert _lib.lib().rl_job_sample_offsets(C.byref(pb.desc), off) == 0 and list(off) == [0, 3, 8, 11]
+
+
+def test_synth_tracks_deterministic_and_well_formed():
+    a = rl.synth_tracks(3, 512, seed_base=99)
+    b = rl.synth_tracks(3, 512, seed_base=99, threads=1)
+    c = rl.synth_tracks(1, 512, seed_base=99, first_id=2)
+    for x, y in zip(a[:3], b[:3]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[0].reshape(3, 512, 2)[2], c[0].reshape(512, 2))
+    center, seg, L, m = a
+    assert m == round(512 / 2.2)
+    P = center.reshape(3, 512, 2)[0]
+    d = np.linalg.norm(np.roll(P, -1, axis=0) - P, axis=1)
+    assert abs(L[0] - 512 * 1.8) < 1e-2 and d.max() < 1.81 and d.min() > 1.7
+    s = seg.reshape(3, 2, m, 4)[0]
+    assert np.allclose(s[0, :-1, 2:], s[0, 1:, :2]) and np.allclose(s[0, -1, 2:], s[0, 0, :2])   # closed ring edges
+    w = np.linalg.norm(s[0, :, :2] - s[1, :, :2], axis=1)
+    assert np.allclose(w, 3.5, atol=1e-9)
+
+
+def test_shard_bounds_cover_and_invert():
+    for n in (0, 1, 7, 4096, 65536):
+        for g in (1, 2, 3, 4, 8):
+            cuts = [sharding.shard_bounds(n, g, r) for r in range(g)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[r][1] == cuts[r + 1][0] for r in range(g - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
+            for p in (0, n // 3, n - 1):
+                if 0 <= p < n:
+                    a, b = sharding.shard_bounds(n, g, sharding.owner_of(p, n, g))
+                    assert a <= p < b
+
+
+def _gloo_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = sharding.shard_bounds(n, world, rank)
+    laps = 20.0 + ((np.arange(lo, hi) * 7919) % 101) * 0.01      # "lap time" of each owned problem
+    allv = sharding.gather_lap_times(laps, n)
+    best = sharding.best_of_sweep(laps, n)
+    q.put((rank, allv, best))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_final_gather_over_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    n, world, port = 37, 2, 29731
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = 20.0 + ((np.arange(n) * 7919) % 101) * 0.01
+    for _, allv, best in got:
+        assert np.array_equal(allv, expect)
+        assert best[0] == int(np.argmin(expect)) and best[1] == expect.min()

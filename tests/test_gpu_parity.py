@@ -1,0 +1,237 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the reference goldens and the oracle.
+
+Tolerances are BASELINE.json's: alpha 1e-4 m, kappa 1e-6 1/m, v 1e-4 m/s, lap time 1e-5 relative, and
+identical accepted-step / Armijo-backtrack counts on the shipped maps.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import practice_path_planning_for_formula_student_driverless_b200 as rl
+from conftest import MAPS, TOL_ALPHA, TOL_LAP_REL, assert_result_close, load_golden
+from oracle import oracle
+from oracle.batchfile import PARAM_FIELDS
+
+pytestmark = pytest.mark.gpu
+
+MC, MT = rl.RL_STAGE_MINCURV, rl.RL_STAGE_MINTIME
+
+
+def track_of(g):
+    return rl.Track(g["center_xy"], g["inner_seg"], g["outer_seg"], g["L"], bool(g["closed"]))
+
+
+def oracle_ref(stage, tr, params):
+    r = oracle.solve(stage, tr.center_xy, tr.inner_seg, tr.outer_seg, tr.L, tr.closed, params)
+    d = {"o_" + k: r[k] for k in ("xy", "heading", "curvature", "alpha_total", "alpha_last", "v", "ax")}
+    d["lap"] = r["lap_time"]
+    d["stats"] = r["stats"]
+    return d
+
+
+def test_shipped_maps_batched_parity(ctx, goldens):
+    """BASELINE config 2: all shipped maps batched on one GPU, every output column against the reference."""
+    names = MAPS + ["competition_map2_n1000"]
+    gs = [goldens.get(n) or load_golden(n) for n in names]
+    tracks = [track_of(g) for g in gs]
+    jobs = [(t, 0, st) for t in range(len(tracks)) for st in (MC, MT)]
+    res = rl.solve_batch(tracks, [rl.Config()], jobs, ctx=ctx)
+    worst = {}
+    for (t, _, st), r in zip(jobs, res):
+        g, pre = gs[t], ("mc_" if st == MC else "mt_")
+        errs = assert_result_close(r, g, pre, st == MT, tag=(names[t], pre))
+        for k, v in errs.items():
+            worst[k] = max(worst.get(k, 0.0), v)
+        bt = g[pre + "bt"]
+        assert r.stats.status == 0 and r.stats.n == g["n"] and r.stats.outer_done == 14
+        assert r.stats.accepted == bt.size, (names[t], pre, r.stats.accepted)
+        assert r.stats.backtracks == int(bt.sum()), (names[t], pre, r.stats.backtracks, int(bt.sum()))
+        per_outer = [int(r.stats.bt_outer[o]) for o in range(14)]
+        assert per_outer == [int(bt[120 * o:120 * (o + 1)].sum()) for o in range(14)], (names[t], pre)
+        assert r.stats.evals == 14 + bt.size + int(bt.sum())
+        if st == MT:
+            assert abs(r.lap_time - g["mt_lap_time"]) <= TOL_LAP_REL * g["mt_lap_time"]
+    print("worst abs errors vs reference:", worst)
+
+
+def test_single_problem_entry_points(ctx, goldens):
+    """rl_compute_min_curvature_raceline / rl_compute_min_time_raceline: the reference's own signatures."""
+    g = goldens["training_map"]
+    cfg = rl.Config()
+    r = rl.compute_min_curvature_raceline(g["center_xy"], g["inner_seg"], g["outer_seg"], cfg.veh_width_m, g["L"], True,
+                                          cfg, ctx)
+    assert_result_close(r, g, "mc_", False)
+    r = rl.compute_min_time_raceline(g["center_xy"], g["inner_seg"], g["outer_seg"], cfg.veh_width_m, g["L"], True, cfg, ctx)
+    assert_result_close(r, g, "mt_", True)
+    assert abs(r.lap_time - g["mt_lap_time"]) <= TOL_LAP_REL * g["mt_lap_time"]
+    # empty input -> empty Result, no error (main.cpp:689 / 912)
+    e = rl.compute_min_time_raceline(np.zeros((0, 2)), g["inner_seg"], g["outer_seg"], 1.0, 1.0, True, cfg, ctx)
+    assert e.raceline.shape == (0, 2) and e.lap_time == 0.0
+
+
+def test_config_sweep_parity(ctx, goldens):
+    """BASELINE config 3 spot check: off-default Configs (lambda, mu->a_total_max, P_max, w_time_gain, inv-v weights)."""
+    base = goldens["competition_map2"]
+    sw = load_golden("sweep_competition_map2")
+    params = []
+    for row in sw["params_rows"]:
+        p = rl.RlParams()
+        for name, val in zip(PARAM_FIELDS, row):
+            cur = getattr(p, name)
+            setattr(p, name, int(val) if isinstance(cur, int) else float(val))
+        params.append(p)
+    pb = rl.PackedBatch([track_of(base)], params, sw["jobs"])
+    ctx.solve_batch(pb)
+    for j, (_, pi, st) in enumerate(sw["jobs"]):
+        r = pb.result(j)
+        ref = {"xy": sw[f"j{j}_xy"], "heading": sw[f"j{j}_heading"], "curvature": sw[f"j{j}_curvature"],
+               "alpha_total": sw[f"j{j}_alpha_total"], "alpha_last": sw[f"j{j}_alpha_last"], "v": sw[f"j{j}_v"],
+               "ax": sw[f"j{j}_ax"]}
+        assert_result_close(r, ref, "", st == MT, tag=("sweep", j))
+        assert r.stats.accepted == sw[f"j{j}_accepted"] and r.stats.backtracks == sw[f"j{j}_backtracks"], j
+        if st == MT:
+            assert abs(r.lap_time - sw[f"j{j}_lap_time"]) <= TOL_LAP_REL * sw[f"j{j}_lap_time"]
+
+
+@pytest.mark.parametrize("n", [16, 37, 64, 100, 130, 255, 256, 257, 300, 512, 700, 1024, 1500, 2048])
+def test_synthetic_tracks_vs_oracle(ctx, n):
+    """ragged N across every size class (and the exact-fit kernels at N = T*K) against the pinned oracle."""
+    center, seg, L, m = rl.synth_tracks(2, n, seed_base=0xB200 + 7 * n)
+    center, seg = center.reshape(2, n, 2), seg.reshape(2, 2, m, 4)
+    tracks = [rl.Track(center[i], seg[i, 0], seg[i, 1], L[i]) for i in range(2)]
+    cfg = rl.Config()
+    res = rl.solve_batch(tracks, [cfg], [(0, 0, MC), (0, 0, MT), (1, 0, MT)], ctx=ctx)
+    for (t, st), r in zip([(0, MC), (0, MT), (1, MT)], res):
+        o = oracle_ref(st, tracks[t], cfg.to_params())
+        assert_result_close(r, o, "o_", st == MT, tag=(n, t, st))
+        assert r.stats.accepted == o["stats"].accepted and r.stats.backtracks == o["stats"].backtracks, (n, t, st)
+        if st == MT:
+            assert abs(r.lap_time - o["lap"]) <= TOL_LAP_REL * o["lap"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9])
+def test_tiny_tracks_vs_oracle(ctx, n):
+    th = 2 * np.pi * np.arange(n) / max(n, 1)
+    R = 12.0
+    center = np.stack([R * np.cos(th), R * np.sin(th)], axis=1)
+    ring_in = rl.ring_edges(np.stack([(R - 1.7) * np.cos(np.linspace(0, 2 * np.pi, 24, endpoint=False)),
+                                      (R - 1.7) * np.sin(np.linspace(0, 2 * np.pi, 24, endpoint=False))], axis=1))
+    ring_out = rl.ring_edges(np.stack([(R + 1.8) * np.cos(np.linspace(0, 2 * np.pi, 30, endpoint=False)),
+                                       (R + 1.8) * np.sin(np.linspace(0, 2 * np.pi, 30, endpoint=False))], axis=1))
+    tr = rl.Track(center, ring_in, ring_out, 2 * np.pi * R)
+    cfg = rl.Config()
+    for st in (MC, MT):
+        r = rl.solve_batch([tr], [cfg], [(0, 0, st)], ctx=ctx)[0]
+        o = oracle_ref(st, tr, cfg.to_params())
+        assert_result_close(r, o, "o_", st == MT, tag=("tiny", n, st))
+        assert r.stats.accepted == o["stats"].accepted and r.stats.backtracks == o["stats"].backtracks, (n, st)
+
+
+def test_edge_cases(ctx, goldens):
+    g = goldens["competition_map1"]
+    tr = track_of(g)
+    # a ring the rays can miss entirely / an empty ring / zero iterations
+    no_outer = rl.Track(tr.center_xy, tr.inner_seg, np.zeros((0, 4)), tr.L)
+    far = rl.Track(tr.center_xy, tr.inner_seg, tr.outer_seg[:3], tr.L)
+    cfg0 = rl.Config(max_outer_iters=0)
+    cfg1 = rl.Config(max_inner_iters=0, max_outer_iters=3)
+    cfg2 = rl.Config(max_vpass_iters=0)
+    cfg3 = rl.Config(step_init=40.0)          # forces many Armijo backtracks
+    cfg4 = rl.Config(step_init=40.0, step_min=10.0, max_outer_iters=2)   # step falls below step_min -> inner loop stops
+    tracks = [tr, no_outer, far]
+    cfgs = [rl.Config(), cfg0, cfg1, cfg2, cfg3, cfg4]
+    jobs = [(1, 0, MC), (1, 0, MT), (2, 0, MC), (2, 0, MT), (0, 1, MT), (0, 2, MC), (0, 2, MT), (0, 3, MT), (0, 4, MC),
+            (0, 4, MT), (0, 5, MC)]
+    res = rl.solve_batch(tracks, cfgs, jobs, ctx=ctx)
+    for (t, c, st), r in zip(jobs, res):
+        o = oracle_ref(st, tracks[t], cfgs[c].to_params())
+        assert_result_close(r, o, "o_", st == MT, tag=("edge", t, c, st))
+        assert r.stats.accepted == o["stats"].accepted and r.stats.backtracks == o["stats"].backtracks, (t, c, st)
+        assert r.stats.evals == o["stats"].evals, (t, c, st)
+        if st == MT:
+            assert abs(r.lap_time - o["lap"]) <= TOL_LAP_REL * max(o["lap"], 1e-9)
+
+
+def test_errors_and_unsupported(ctx, goldens):
+    from practice_path_planning_for_formula_student_driverless_b200._lib import lib
+    tr = track_of(goldens["training_map"])
+    with pytest.raises(rl.RacelineError) as e:
+        rl.solve_batch([tr], [rl.Config()], [(3, 0, MC)], ctx=ctx)
+    assert e.value.status == rl.RL_ERR_ARG
+    with pytest.raises(rl.RacelineError) as e:
+        rl.solve_batch([tr], [rl.Config()], [(0, 0, 7)], ctx=ctx)
+    assert e.value.status == rl.RL_ERR_ARG
+    open_tr = rl.Track(tr.center_xy, tr.inner_seg, tr.outer_seg, tr.L, closed=False)
+    with pytest.raises(rl.RacelineError) as e:
+        rl.solve_batch([open_tr], [rl.Config()], [(0, 0, MC)], ctx=ctx)
+    assert e.value.status == rl.RL_ERR_UNSUPPORTED
+    assert lib().rl_solve_batch(ctx._h, None, None) == rl.RL_ERR_ARG
+    # the context is still usable after errors
+    r = rl.solve_batch([tr], [rl.Config()], [(0, 0, MC)], ctx=ctx)[0]
+    assert r.stats.accepted == 1680
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 4 shape (N = 2048, M = 931/ring): size-independent properties on a few hundred tracks."""
+    nt, n = 296, 2048
+    center, seg, L, m = rl.synth_tracks(nt, n)
+    samp_off = np.arange(nt + 1, dtype=np.int64) * n
+    seg_off = np.arange(2 * nt + 1, dtype=np.int64) * m
+    cfg = rl.Config()
+    jobs = [(t, 0, st) for t in range(nt) for st in (MC, MT)]
+    pb = rl.PackedBatch.from_arrays(samp_off, seg_off, center, seg, L, np.ones(nt, np.int32), [cfg.to_params()], jobs)
+    dev = rl.DeviceBatch(ctx, pb)
+    dev.solve(); dev.download(); dev.sync()
+    first = [pb.result(j) for j in range(pb.n_jobs)]
+    a_tot = pb.out_alpha_total.copy(); xy = pb.out_xy.copy(); v = pb.out_v.copy()
+    half_w = 1.75 - (cfg.veh_width_m * 0.5 + cfg.safety_margin_m)
+    for j, r in enumerate(first):
+        st = r.stats
+        assert st.status == 0 and st.outer_done == 14 and st.accepted <= 14 * 120
+        for o in range(14):
+            assert st.Jend[o] <= st.J0[o] * (1 + 1e-12)                  # Armijo: the cost never increases
+        assert np.all(np.isfinite(r.raceline)) and np.all(np.isfinite(r.curvature))
+        # the raceline stays inside the corridor: |offset from the centre line| < half width minus guard (+ slack)
+        c0 = center.reshape(nt, n, 2)[jobs[j][0]]
+        assert np.max(np.linalg.norm(r.raceline - c0, axis=1)) < half_w + 0.25
+        if jobs[j][2] == MT:
+            assert np.all(r.v > 0) and np.all(r.v <= cfg.v_cap_mps + 1e-12)
+            assert abs(r.lap_time - np.sum((L[jobs[j][0]] / n) / r.v)) <= 1e-9 * r.lap_time
+            vk = np.sqrt(cfg.a_lat_max / np.maximum(np.abs(r.curvature), cfg.kappa_eps))
+            assert np.all(r.v <= vk * (1 + 1e-12))
+    # determinism: a second solve of the resident batch reproduces every bit
+    dev.solve(); dev.download(); dev.sync()
+    assert np.array_equal(a_tot, pb.out_alpha_total) and np.array_equal(xy, pb.out_xy) and np.array_equal(v, pb.out_v)
+    # spot-check three tracks against the oracle at full size
+    for t in (0, 137, 295):
+        tr = rl.Track(center.reshape(nt, n, 2)[t], seg.reshape(nt, 2, m, 4)[t, 0], seg.reshape(nt, 2, m, 4)[t, 1], L[t])
+        for k, stg in enumerate((MC, MT)):
+            o = oracle_ref(stg, tr, cfg.to_params())
+            r = first[2 * t + k]
+            assert_result_close(r, o, "o_", stg == MT, tag=("full", t, stg))
+            assert r.stats.accepted == o["stats"].accepted and r.stats.backtracks == o["stats"].backtracks
+    dev.close()
+
+
+def test_rigid_motion_and_mirror_invariance(ctx, goldens):
+    """alpha is a geometric quantity: rotating/translating the inputs leaves it unchanged, mirroring negates it."""
+    g = goldens["competition_map3"]
+    th, sh = 0.7, np.array([13.0, -4.0])
+    Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+
+    def xf(P, M, s):
+        return P.reshape(-1, 2) @ M.T + s
+
+    def seg_xf(S, M, s):
+        return np.concatenate([xf(S[:, :2], M, s), xf(S[:, 2:], M, s)], axis=1)
+
+    mir = np.array([[1.0, 0.0], [0.0, -1.0]])
+    t0 = track_of(g)
+    t1 = rl.Track(xf(g["center_xy"], Rm, sh), seg_xf(g["inner_seg"], Rm, sh), seg_xf(g["outer_seg"], Rm, sh), g["L"])
+    t2 = rl.Track(xf(g["center_xy"], mir, 0), seg_xf(g["inner_seg"], mir, 0), seg_xf(g["outer_seg"], mir, 0), g["L"])
+    res = rl.solve_batch([t0, t1, t2], [rl.Config()], [(0, 0, MT), (1, 0, MT), (2, 0, MT)], ctx=ctx)
+    assert np.max(np.abs(res[0].alpha_total - res[1].alpha_total)) < TOL_ALPHA
+    assert np.max(np.abs(res[0].alpha_total + res[2].alpha_total)) < TOL_ALPHA
+    assert abs(res[0].lap_time - res[1].lap_time) < TOL_LAP_REL * res[0].lap_time
+    assert abs(res[0].lap_time - res[2].lap_time) < TOL_LAP_REL * res[0].lap_time

@@ -15,8 +15,10 @@ LIB = os.path.join(CSRC, "libraceline_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-SOURCES = ["raceline_kernels.cu", "raceline_api.cu", "synth_tracks.cpp"]
-HEADERS = [os.path.join(CSRC, "raceline_device.h"), os.path.join(HERE, "..", "include", "raceline_b200.h")]
+SOURCES = ["raceline_inst_256.cu", "raceline_inst_512.cu", "raceline_inst_128.cu", "raceline_inst_64.cu", "raceline_inst_32.cu",
+           "raceline_dispatch.cu", "raceline_api.cu", "synth_tracks.cpp"]
+HEADERS = [os.path.join(CSRC, "raceline_device.h"), os.path.join(CSRC, "raceline_kernels.cuh"),
+           os.path.join(HERE, "..", "include", "raceline_b200.h")]
 
 
 def _nvcc():
@@ -36,22 +38,27 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     """Compile every source for sm_100a and link the shared library. Returns its path."""
     nvcc = _nvcc()
-    objs = []
-    for src in SOURCES:
+    objs = [os.path.join(CSRC, os.path.splitext(src)[0] + ".o") for src in SOURCES]
+
+    def compile_one(src, obj):
         sp = os.path.join(CSRC, src)
-        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
-        objs.append(obj)
-        if force or _stale(obj, [sp] + HEADERS):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", sp, "-o", obj]
-            res = subprocess.run(cmd, capture_output=True, text=True)
-            if res.returncode != 0:
-                sys.stderr.write(res.stdout + res.stderr)
-                raise RuntimeError(f"nvcc failed on {src}")
-            log = os.path.join(CSRC, os.path.splitext(src)[0] + ".ptxas.log")
-            with open(log, "w") as f:
-                f.write(res.stdout + res.stderr)
-            if verbose:
-                sys.stderr.write(f"built {obj}\n")
+        if not (force or _stale(obj, [sp] + HEADERS)):
+            return
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", sp, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError(f"nvcc failed on {src}")
+        with open(os.path.join(CSRC, os.path.splitext(src)[0] + ".ptxas.log"), "w") as f:
+            f.write(res.stdout + res.stderr)
+        if verbose:
+            sys.stderr.write(f"built {obj}\n")
+
+    # the per-thread-count kernel instantiations are independent translation units: compile them in parallel
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(SOURCES), os.cpu_count() or 1))) as ex:
+        for fut in [ex.submit(compile_one, s, o) for s, o in zip(SOURCES, objs)]:
+            fut.result()
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -50,7 +50,8 @@ inline size_t smem_bytes_for_class(int T, int K)
     const size_t np = (size_t)T * K;
     return np * 16      /* path points, double2            */
            + np * 8 * 4 /* region B: PGD coefficients+stash / ray tile+corridor staging */
-           + 2048;      /* barriers, reduction + halo exchange scratch */
+           + 2048       /* barriers, reduction + halo exchange scratch */
+           + np * 4;    /* per-sample corridor hint words */
 }
 
 // launches job_list[0..n_list) (indices into B.jobs) with the kernel of class `cls`

@@ -1,4 +1,4 @@
-// raceline_kernels.cu -- hand-written sm_100a kernels for the batched raceline solver.
+// raceline_kernels.cuh -- hand-written sm_100a kernels for the batched raceline solver.
 //
 // One CTA of T threads solves one job = one stage (min-curvature or min-time) of one
 // (track, Config) problem, start to finish, with no host round trip:
@@ -28,6 +28,7 @@
 
 #include <cstdint>
 
+#pragma once
 #include "raceline_device.h"
 
 namespace rl {
@@ -41,6 +42,8 @@ constexpr int kScrBar = 0;
 constexpr int kScrRed = 64;             // [2][16][2] doubles
 constexpr int kScrExF = kScrRed + 512;  // [2][16][2] doubles: first two samples of each warp's lane 0
 constexpr int kScrExL = kScrExF + 512;  // [2][16][2] doubles: last two samples of each warp's lane 31
+constexpr int kScrMisc = kScrExL + 512; // a few ints
+constexpr int kScrBytes = 2048;         // followed by the per-sample corridor hint words [T*K]
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
@@ -508,7 +511,8 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double (&lo)[K
     return o;
 }
 
-// ---- corridor (main.cpp:694-711, 749-756): rays +-n against both rings, exact nearest hit ----------------
+// ---- corridor, general path (rings of any size, streamed through shared memory in tiles) ------------------
+// (main.cpp:694-711, 749-756): rays +-n against both rings, exact nearest hit
 // Consecutive mapping (sample i = tid + j*T) so that a warp's 32 rays are neighbours and share boxes.
 // The +n and -n rays lie on one line: den, t, u of the -n ray are exactly -den, -t, u of the +n ray
 // (IEEE negation is exact), so one intersection serves both.  A box can only contain a hit if the
@@ -517,7 +521,7 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double (&lo)[K
 // (minDistanceToSegments_global, main.cpp:501-512), pruned by box lower bounds.
 // Results are returned in the BLOCKED layout through region B.
 template <int T, int K>
-__device__ __forceinline__ void corridor_build(const Part& pt, const double2* sP, double* sB, uint64_t* mbar, uint32_t& bar_phase,
+__device__ __forceinline__ void corridor_build_tiled(const Part& pt, const double2* sP, double* sB, uint64_t* mbar, uint32_t& bar_phase,
                                                const double* __restrict__ gseg, long long segI0, long long segO0, long long segE,
                                                double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests)
 {
@@ -677,6 +681,348 @@ __device__ __forceinline__ void corridor_build(const Part& pt, const double2* sP
     block_sync<T>();
 }
 
+// ---- corridor, fast path (both rings fit one tile each) ---------------------------------------------------
+// Same results as corridor_build_tiled / the reference loops, far fewer tests:
+//  * rays, not lines: a box is visited only if it meets the +n or -n RAY inside [0, best hit so far]; the
+//    bound is shared by both rings because only min(inner, outer) enters the corridor (main.cpp:704-705);
+//  * a two-level box hierarchy (SB segments per box, SB boxes per super box) tested in FP32 with
+//    outward-rounded boxes and a margin that covers every rounding error; FP32 only ever SKIPS work, every
+//    accepted hit comes from the FP64 formulas of main.cpp:478-490;
+//  * near-first order: the scan starts at the box where this sample's nearest hit was last time (hints live
+//    in shared memory across the outer iterations), so far-side crossings are pruned by the bound instead
+//    of being descended divergently;
+//  * "does this ray hit the ring AT ALL" (needed because a ring without any hit falls back to the
+//    point-ring distance, main.cpp:696) is settled without a search when the ring is a closed chain and the
+//    sample lies inside it (parity), a bit computed once per job: the path never crosses a ring between
+//    corridor builds because |alpha| <= hit distance - guard (main.cpp:707-708, guard >= 0).
+struct RayTile {
+    const double* segD;   // [nt][4] x0,y0,vx,vy
+    const float4* segF;   // [nt]    x0,y0,x1,y1 relative to the job origin
+    const float4* boxF;   // [nblk]  cx,cy,hx,hy (inflated)
+    const float4* supF;   // [nsup]
+    int nt, nblk, nsup;
+};
+
+__device__ __forceinline__ bool ray_box(const float4 bx, float px, float py, float nx, float ny, float anx, float any,
+                                        float m, float bp, float bn, bool wp, bool wn)
+{
+    const float dx = bx.x - px, dy = bx.y - py;
+    const float sc = nx * dy - ny * dx;
+    if (fabsf(sc) > anx * bx.w + any * bx.z + m) return false;     // the line misses the box
+    const float tc = nx * dx + ny * dy;
+    const float r = anx * bx.z + any * bx.w + m;
+    const bool pos_ok = wp && (tc + r >= 0.f) && (tc - r <= bp);
+    const bool neg_ok = wn && (tc - r <= 0.f) && (-tc - r <= bn);
+    return pos_ok || neg_ok;
+}
+
+// scan one ring for one sample.  bp/bn: running nearest +n / -n hit over both rings (pruning bound);
+// pos_r/neg_r: nearest hit found on THIS ring (INF if none inside the bound).  Returns the box of the nearest hit.
+__device__ __forceinline__ int ray_scan(const RayTile& tl, double2 P, double nx, double ny, float px, float py, float fnx, float fny,
+                                        float m, int hint, bool wp, bool wn, bool first_hit_only,
+                                        double& bp, double& bn, double& pos_r, double& neg_r, long long& tests)
+{
+    const double INF = dinf();
+    const float anx = fabsf(fnx), any = fabsf(fny);
+    float bpf = (bp < INF) ? __double2float_ru(bp) : __int_as_float(0x7f800000);
+    float bnf = (bn < INF) ? __double2float_ru(bn) : __int_as_float(0x7f800000);
+    int best_box = -1;
+    double best_abs = INF;
+    int sb0 = hint / SB;
+    if (sb0 >= tl.nsup) sb0 = 0;
+    for (int q = 0; q < tl.nsup; ++q) {
+        int sb = sb0 + q;
+        if (sb >= tl.nsup) sb -= tl.nsup;
+        if (!ray_box(tl.supF[sb], px, py, fnx, fny, anx, any, m, bpf, bnf, wp, wn)) continue;
+        const int b1 = min(tl.nblk, sb * SB + SB);
+        for (int b = sb * SB; b < b1; ++b) {
+            if (!ray_box(tl.boxF[b], px, py, fnx, fny, anx, any, m, bpf, bnf, wp, wn)) continue;
+            const int s1 = min(tl.nt, b * SB + SB);
+            for (int s = b * SB; s < s1; ++s) {
+                const float4 f = tl.segF[s];
+                const float sa = fnx * (f.y - py) - fny * (f.x - px), sbb = fnx * (f.w - py) - fny * (f.z - px);
+                if (fminf(sa, sbb) > m || fmaxf(sa, sbb) < -m) continue;       // both ends strictly on one side
+                const double x0 = tl.segD[4 * s], y0 = tl.segD[4 * s + 1], vx = tl.segD[4 * s + 2], vy = tl.segD[4 * s + 3];
+                const double den = nx * (-vy) + ny * vx;                         // main.cpp:483
+                ++tests;
+                if (fabs(den) < 1e-15) continue;                                 // main.cpp:484
+                const double ax = x0 - P.x, ay = y0 - P.y;                      // main.cpp:485
+                const double inv = 1.0 / den;
+                const double t = (ax * (-vy) + ay * vx) * inv;                  // main.cpp:486
+                const double u = (nx * ay - ny * ax) * inv;                     // main.cpp:487
+                if (u >= -1e-12 && u <= 1.0 + 1e-12) {                          // main.cpp:488
+                    if (t > 0.0) {                                              // +n ray, main.cpp:497
+                        if (wp) {
+                            pos_r = fmin(pos_r, t);
+                            if (t < bp) { bp = t; bpf = __double2float_ru(t); }
+                            if (t < best_abs) { best_abs = t; best_box = b; }
+                            if (first_hit_only) return best_box;
+                        }
+                    } else if (t < 0.0) {                                       // -n ray: t' = -t
+                        if (wn) {
+                            neg_r = fmin(neg_r, -t);
+                            if (-t < bn) { bn = -t; bnf = __double2float_ru(-t); }
+                            if (-t < best_abs) { best_abs = -t; best_box = b; }
+                            if (first_hit_only) return best_box;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return best_box;
+}
+
+// nearest point-segment distance to the ring (minDistanceToSegments_global, main.cpp:501-512); ub: any known
+// upper bound (a hit point lies on the ring) or INF.
+__device__ __forceinline__ double dist_scan(const RayTile& tl, double2 P, float px, float py, float m, int hint, double ub)
+{
+    const double INF = dinf();
+    double best2 = INF;
+    float boundf = (ub < INF) ? __double2float_ru(ub) * (1.f + 1e-5f) + m : __int_as_float(0x7f800000);
+    int sb0 = hint / SB;
+    if (sb0 >= tl.nsup) sb0 = 0;
+    for (int q = 0; q < tl.nsup; ++q) {
+        int sb = sb0 + q;
+        if (sb >= tl.nsup) sb -= tl.nsup;
+        {
+            const float4 bx = tl.supF[sb];
+            const float ddx = fmaxf(0.f, fabsf(bx.x - px) - bx.z - m), ddy = fmaxf(0.f, fabsf(bx.y - py) - bx.w - m);
+            if (ddx * ddx + ddy * ddy > boundf * boundf) continue;
+        }
+        const int b1 = min(tl.nblk, sb * SB + SB);
+        for (int b = sb * SB; b < b1; ++b) {
+            const float4 bx = tl.boxF[b];
+            const float ddx = fmaxf(0.f, fabsf(bx.x - px) - bx.z - m), ddy = fmaxf(0.f, fabsf(bx.y - py) - bx.w - m);
+            if (ddx * ddx + ddy * ddy > boundf * boundf) continue;
+            const int s1 = min(tl.nt, b * SB + SB);
+            for (int s = b * SB; s < s1; ++s) {
+                {   // FP32 lower bound of the point-segment distance
+                    const float4 f = tl.segF[s];
+                    const float vx = f.z - f.x, vy = f.w - f.y, apx = px - f.x, apy = py - f.y;
+                    const float tt = fminf(1.f, fmaxf(0.f, __fdividef(vx * apx + vy * apy, fmaxf(1e-30f, vx * vx + vy * vy))));
+                    const float ex = apx - vx * tt, ey = apy - vy * tt;
+                    const float d = sqrtf(ex * ex + ey * ey) - 4.f * m;
+                    if (d > boundf) continue;
+                }
+                const double x0 = tl.segD[4 * s], y0 = tl.segD[4 * s + 1], vx = tl.segD[4 * s + 2], vy = tl.segD[4 * s + 3];
+                const double apx = P.x - x0, apy = P.y - y0;
+                const double denom = fmax(1e-30, vx * vx + vy * vy);
+                const double tt = fmin(1.0, fmax(0.0, (vx * apx + vy * apy) / denom));
+                const double qx = x0 + vx * tt, qy = y0 + vy * tt;
+                const double ex = P.x - qx, ey = P.y - qy;
+                const double d2 = ex * ex + ey * ey;
+                if (d2 < best2) {
+                    best2 = d2;
+                    const float df = __double2float_ru(sqrt(d2)) * (1.f + 1e-5f) + m;
+                    boundf = fminf(boundf, df);
+                }
+            }
+        }
+    }
+    return (best2 < INF) ? sqrt(best2) : INF;
+}
+
+// parity of the crossings of the +x ray from P with a CLOSED chain (vertices shared bit for bit): P inside?
+__device__ __forceinline__ bool inside_ring(const RayTile& tl, double2 P, float px, float py, float m)
+{
+    int cnt = 0;
+    for (int sb = 0; sb < tl.nsup; ++sb) {
+        const float4 sx = tl.supF[sb];
+        if (fabsf(sx.y - py) > sx.w + m || px > sx.x + sx.z + m) continue;
+        const int b1 = min(tl.nblk, sb * SB + SB);
+        for (int b = sb * SB; b < b1; ++b) {
+            const float4 bx = tl.boxF[b];
+            if (fabsf(bx.y - py) > bx.w + m || px > bx.x + bx.z + m) continue;
+            const int s1 = min(tl.nt, b * SB + SB);
+            for (int s = b * SB; s < s1; ++s) {
+                const int sn = (s + 1 == tl.nt) ? 0 : s + 1;
+                const double ax = tl.segD[4 * s], ay = tl.segD[4 * s + 1], bxx = tl.segD[4 * sn], byy = tl.segD[4 * sn + 1];
+                if ((ay > P.y) != (byy > P.y)) {
+                    const double xc = ax + (P.y - ay) * (bxx - ax) / (byy - ay);
+                    if (xc > P.x) ++cnt;
+                }
+            }
+        }
+    }
+    return (cnt & 1) != 0;
+}
+
+// load one ring into region B and build its FP32 filter structures.  Returns the FP32 margin; *closed tells
+// whether the segments form a closed chain (end of j == start of j+1, bit for bit).
+template <int T, int K>
+__device__ __forceinline__ float ring_tile_build(const Part& pt, double* sB, uint64_t* mbar, uint32_t& bar_phase, int* sMisc,
+                                                 const double* __restrict__ gseg, int mr, double ox, double oy,
+                                                 RayTile& tl, bool& closed)
+{
+    constexpr int NP = T * K;
+    constexpr int CAP = ((32 * NP * 4) / 201) / (SB * SB) * (SB * SB);   // 50.25 bytes per segment
+    const int tid = pt.tid;
+    double* segD = sB;
+    float4* segF = reinterpret_cast<float4*>(sB + 4 * CAP);
+    float4* boxF = segF + CAP;
+    float4* supF = boxF + CAP / SB;
+    tl.segD = segD; tl.segF = segF; tl.boxF = boxF; tl.supF = supF;
+    tl.nt = mr; tl.nblk = (mr + SB - 1) / SB; tl.nsup = (tl.nblk + SB - 1) / SB;
+    block_sync<T>();
+    if (tid == 0) {
+        sMisc[0] = 0;
+        fence_proxy_async();
+        mbar_expect_tx(mbar, (uint32_t)mr * 32u);
+        bulk_g2s(segD, gseg, (uint32_t)mr * 32u, mbar);
+    }
+    mbar_wait(mbar, bar_phase); bar_phase ^= 1;
+    block_sync<T>();
+    float emax = 0.f;
+    int ok = 1;
+    for (int s = tid; s < mr; s += T) {
+        const double x0 = segD[4 * s], y0 = segD[4 * s + 1], x1 = segD[4 * s + 2], y1 = segD[4 * s + 3];
+        const int sn = (s + 1 == mr) ? 0 : s + 1;
+        ok &= (x1 == segD[4 * sn] && y1 == segD[4 * sn + 1]);
+        float4 f;
+        f.x = (float)(x0 - ox); f.y = (float)(y0 - oy); f.z = (float)(x1 - ox); f.w = (float)(y1 - oy);
+        segF[s] = f;
+        emax = fmaxf(emax, fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fmaxf(fabsf(f.z), fabsf(f.w))));
+    }
+    atomicMax(&sMisc[0], __float_as_int(emax));
+    closed = (T == 32) ? (__all_sync(kFull, ok) != 0) : (__syncthreads_and(ok) != 0);
+    block_sync<T>();
+    // second pass: (x1,y1) -> (vx,vy) once every thread has compared the shared vertices
+    for (int s = tid; s < mr; s += T) {
+        segD[4 * s + 2] -= segD[4 * s]; segD[4 * s + 3] -= segD[4 * s + 1];   // vx = x1-x0, vy = y1-y0 (main.cpp:482)
+    }
+    const float m = 2e-6f * __int_as_float(sMisc[0]) + 1e-6f;
+    for (int b = tid; b < tl.nblk; b += T) {
+        float xmin = 3e38f, xmax = -3e38f, ymin = 3e38f, ymax = -3e38f;
+        const int e = min(mr, b * SB + SB);
+        for (int s = b * SB; s < e; ++s) {
+            const float4 f = segF[s];
+            xmin = fminf(xmin, fminf(f.x, f.z)); xmax = fmaxf(xmax, fmaxf(f.x, f.z));
+            ymin = fminf(ymin, fminf(f.y, f.w)); ymax = fmaxf(ymax, fmaxf(f.y, f.w));
+        }
+        float4 bx;
+        bx.x = 0.5f * (xmin + xmax); bx.y = 0.5f * (ymin + ymax);
+        bx.z = 0.5f * (xmax - xmin) * (1.f + 1e-6f) + m; bx.w = 0.5f * (ymax - ymin) * (1.f + 1e-6f) + m;
+        boxF[b] = bx;
+    }
+    block_sync<T>();
+    for (int sb = tid; sb < tl.nsup; sb += T) {
+        float xmin = 3e38f, xmax = -3e38f, ymin = 3e38f, ymax = -3e38f;
+        const int e = min(tl.nblk, sb * SB + SB);
+        for (int b = sb * SB; b < e; ++b) {
+            const float4 bx = boxF[b];
+            xmin = fminf(xmin, bx.x - bx.z); xmax = fmaxf(xmax, bx.x + bx.z);
+            ymin = fminf(ymin, bx.y - bx.w); ymax = fmaxf(ymax, bx.y + bx.w);
+        }
+        float4 sx;
+        sx.x = 0.5f * (xmin + xmax); sx.y = 0.5f * (ymin + ymax);
+        sx.z = 0.5f * (xmax - xmin) * (1.f + 1e-6f) + m; sx.w = 0.5f * (ymax - ymin) * (1.f + 1e-6f) + m;
+        supF[sb] = sx;
+    }
+    block_sync<T>();
+    return m;
+}
+
+// sHint word per sample: bits 0-13 hint box ring 0, 14-27 hint box ring 1, 28/29 sample inside ring 0/1
+template <int T, int K>
+__device__ __forceinline__ void corridor_build_fast(const Part& pt, const double2* sP, double* sB, uint64_t* mbar, uint32_t& bar_phase,
+                                                    int* sMisc, unsigned* sHint, bool first, bool parity_ok,
+                                                    const double* __restrict__ gseg, long long segI0, long long segO0, long long segE,
+                                                    double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests)
+{
+    constexpr int NP = T * K;
+    const int N = pt.N, tid = pt.tid;
+    const double INF = dinf();
+    const double2 org = sP[0];
+    double bp[K], bn[K], dfp[K], dfn[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { bp[j] = INF; bn[j] = INF; dfp[j] = INF; dfn[j] = INF; }
+    // parity_ok: the parity shortcut needs the path never to cross a ring between builds (every guard >= 0)
+
+    for (int ring = 0; ring < 2; ++ring) {
+        const long long base = ring ? segO0 : segI0;
+        const int mr = (int)(ring ? (segE - segO0) : (segO0 - segI0));
+        if (mr == 0) {   // safe_ray on an empty ring returns 0 (main.cpp:696-698)
+#pragma unroll
+            for (int j = 0; j < K; ++j) { dfp[j] = 0.0; dfn[j] = 0.0; }
+            continue;
+        }
+        RayTile tl;
+        bool closed;
+        const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, closed);
+        const int hshift = ring ? 14 : 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int i = tid + j * T;
+            if (i >= N) continue;
+            const double2 Pc = sP[i];
+            double nx, ny;
+            normal_closed(sp_prev(sP, i, N), sp_next(sP, i, N), N, nx, ny);
+            const float px = (float)(Pc.x - org.x), py = (float)(Pc.y - org.y), fnx = (float)nx, fny = (float)ny;
+            const float m = m0 + 2e-6f * fmaxf(fabsf(px), fabsf(py));
+            unsigned hw = sHint[i];
+            int hint = (int)((hw >> hshift) & 0x3fffu);
+            if (first) {
+                // nearest box centre: a good place to start, and the parity bit of this sample
+                float bd = 3e38f; hint = 0;
+                for (int b = 0; b < tl.nblk; ++b) {
+                    const float4 bx = tl.boxF[b];
+                    const float d = (bx.x - px) * (bx.x - px) + (bx.y - py) * (bx.y - py);
+                    if (d < bd) { bd = d; hint = b; }
+                }
+                const bool in = closed && inside_ring(tl, Pc, px, py, m);
+                hw = (hw & ~(1u << (28 + ring))) | ((in ? 1u : 0u) << (28 + ring));
+            }
+            const bool inside = parity_ok && closed && ((hw >> (28 + ring)) & 1u);
+            double pos_r = INF, neg_r = INF;
+            const bool bounded_p = (bp[j] < INF), bounded_n = (bn[j] < INF);
+            int hb = ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, hint, true, true, false, bp[j], bn[j], pos_r, neg_r, ray_tests);
+            // does a hit exist at all?  found / known by parity / searched without a bound / must search again
+            bool ex_p = (pos_r < INF), ex_n = (neg_r < INF);
+            if (!ex_p && bounded_p) { if (inside) ex_p = true; }
+            if (!ex_n && bounded_n) { if (inside) ex_n = true; }
+            // (a bound that became finite DURING this scan came from this ring: then pos_r < INF)
+            const bool redo_p = !ex_p && bounded_p, redo_n = !ex_n && bounded_n;
+            if (redo_p || redo_n) {
+                double ubp = INF, ubn = INF, pr = INF, nr = INF;
+                if (redo_p) { ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, hint, true, false, true, ubp, ubn, pr, nr, ray_tests); ex_p = (pr < INF); }
+                if (redo_n) { ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, hint, false, true, true, ubp, ubn, pr, nr, ray_tests); ex_n = (nr < INF); }
+            }
+            if (!ex_p || !ex_n) {
+                const double d = dist_scan(tl, Pc, px, py, m, (hb >= 0) ? hb : hint, fmin(pos_r, neg_r));
+                if (!ex_p) dfp[j] = fmin(dfp[j], d);
+                if (!ex_n) dfn[j] = fmin(dfn[j], d);
+            }
+            if (hb >= 0) hint = hb;
+            hw = (hw & ~(0x3fffu << hshift)) | ((unsigned)hint << hshift);
+            sHint[i] = hw;
+        }
+    }
+    // hi/lo (main.cpp:704-710), handed to the blocked layout through region B
+    block_sync<T>();
+    double* sLoS = sB;
+    double* sHiS = sB + NP;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int i = tid + j * T;
+        if (i < N) {
+            const double dpos = fmin(bp[j], dfp[j]), dneg = fmin(bn[j], dfn[j]);
+            double hv = fmax(0.0, fmax(0.0, dpos) - guard);
+            double lv = -fmax(0.0, fmax(0.0, dneg) - guard);
+            if (!isfinite(hv)) hv = 0.0;
+            if (!isfinite(lv)) lv = 0.0;
+            sHiS[i] = hv; sLoS[i] = lv;
+        }
+    }
+    block_sync<T>();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        lo[k] = 0.0; hi[k] = 0.0;
+        if (k < pt.cnt) { lo[k] = sLoS[pt.start + k]; hi[k] = sHiS[pt.start + k]; }
+    }
+    block_sync<T>();
+}
+
 // ---- the solver kernel ------------------------------------------------------------------------------------
 template <int T, int K, bool EXACT>
 __global__ void __launch_bounds__(T, (512 / T) > 16 ? 16 : (512 / T))
@@ -691,6 +1037,8 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     double* sRed = reinterpret_cast<double*>(scr + kScrRed);
     double* sExF = reinterpret_cast<double*>(scr + kScrExF);
     double* sExL = reinterpret_cast<double*>(scr + kScrExL);
+    int* sMisc = reinterpret_cast<int*>(scr + kScrMisc);
+    unsigned* sHint = reinterpret_cast<unsigned*>(scr + kScrBytes);
 
     if ((int)blockIdx.x >= n_list) return;
     const int jid = job_list[blockIdx.x];
@@ -766,8 +1114,16 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
 
     double lo[K], hi[K];
     // initial corridor from the centre line: guard uses the veh_width ARGUMENT (main.cpp:706 / 930)
-    corridor_build<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,
-                         C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+    constexpr int CAPF = ((32 * NP * 4) / 201) / (SB * SB) * (SB * SB);
+    const bool fast_rays = (segO0 - segI0 <= CAPF) && (segE - segO0 <= CAPF) && (CAPF / SB < 16384);
+    const bool parity_ok = (C.veh_width_arg * 0.5 + C.safety_margin_m >= 0.0) && (C.veh_width_m * 0.5 + C.safety_margin_m >= 0.0);
+    for (int i = tid; i < NP; i += T) sHint[i] = 0u;
+    if (fast_rays)
+        corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, true, parity_ok, B.seg, segI0, segO0, segE,
+                                  C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+    else
+        corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,
+                                   C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
 
     double* sC0 = sB + tid;
     double* sCp = sB + NP + tid;
@@ -889,8 +1245,12 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
         for (int k = 0; k < K; ++k) if (k < cnt) sP[start + k] = Pn[k];
         block_sync<T>();
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
-        corridor_build<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,
-                             C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+        if (fast_rays)
+            corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, false, parity_ok, B.seg, segI0, segO0, segE,
+                                      C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+        else
+            corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,
+                                       C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
     }
 
     // =================== final geometry (main.cpp:761 / 1046) ===================
@@ -945,65 +1305,27 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     }
 }
 
-// FP64 FMA throughput probe: 8 independent chains per thread, 2 flops per FMA.
-__global__ void fp64_peak_kernel(double* out, int iters)
-{
-    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const double m = 0.999999, c = 1e-7;
-    for (int i = 0; i < iters; ++i) {
-        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
-    }
-    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-template <int T, int K, bool EXACT>
-cudaError_t launch_one(const DevBatch& B, const int* job_list, int n_list, cudaStream_t s)
-{
-    const size_t smem = smem_bytes_for_class(T, K);
-    solve_kernel<T, K, EXACT><<<n_list, T, smem, s>>>(B, job_list, n_list);
-    return cudaGetLastError();
-}
-template <int T, int K, bool EXACT>
-cudaError_t configure_one()
-{
-    return cudaFuncSetAttribute(solve_kernel<T, K, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem_bytes_for_class(T, K));
-}
 
 }  // namespace
-
-int configure_kernels()
-{
-    cudaError_t e = cudaSuccess;
-#define RL_CFG(T, K)                                                      \
-    if (e == cudaSuccess) e = configure_one<T, K, false>();               \
-    if (e == cudaSuccess) e = configure_one<T, K, true>();
-    RL_CFG(32, 8) RL_CFG(64, 8) RL_CFG(128, 8) RL_CFG(256, 8) RL_CFG(512, 8)
-#undef RL_CFG
-    return (int)e;
-}
-
-int launch_solve(const DevBatch& B, const int* job_list, int n_list, int cls, bool exact, void* stream)
-{
-    cudaStream_t s = (cudaStream_t)stream;
-    if (n_list <= 0) return 0;
-    cudaError_t e = cudaErrorInvalidValue;
-#define RL_CASE(IDX, T, K)                                                                                       \
-    case IDX: e = exact ? launch_one<T, K, true>(B, job_list, n_list, s) : launch_one<T, K, false>(B, job_list, n_list, s); break;
-    switch (cls) {
-        RL_CASE(0, 32, 8) RL_CASE(1, 64, 8) RL_CASE(2, 128, 8) RL_CASE(3, 256, 8) RL_CASE(4, 512, 8)
-        default: break;
-    }
-#undef RL_CASE
-    return (int)e;
-}
-
-int launch_fp64_peak(double* d_out, int blocks, int threads, int iters, void* stream)
-{
-    fp64_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_out, iters);
-    return (int)cudaGetLastError();
-}
-
 }  // namespace rl
+
+// one translation unit per thread count T instantiates its two kernels (ragged and exact-fit) through this macro
+#define RL_INSTANTIATE(T, K)                                                                                          \
+    namespace rl {                                                                                                    \
+    int launch_solve_##T(const DevBatch& B, const int* job_list, int n_list, bool exact, void* stream)               \
+    {                                                                                                                 \
+        const size_t smem = smem_bytes_for_class(T, K);                                                               \
+        cudaStream_t s = (cudaStream_t)stream;                                                                        \
+        if (exact) solve_kernel<T, K, true><<<n_list, T, smem, s>>>(B, job_list, n_list);                             \
+        else solve_kernel<T, K, false><<<n_list, T, smem, s>>>(B, job_list, n_list);                                  \
+        return (int)cudaGetLastError();                                                                               \
+    }                                                                                                                 \
+    int configure_solve_##T()                                                                                         \
+    {                                                                                                                 \
+        const int smem = (int)smem_bytes_for_class(T, K);                                                             \
+        cudaError_t e = cudaFuncSetAttribute(solve_kernel<T, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e == cudaSuccess)                                                                                         \
+            e = cudaFuncSetAttribute(solve_kernel<T, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   \
+        return (int)e;                                                                                                \
+    }                                                                                                                 \
+    }

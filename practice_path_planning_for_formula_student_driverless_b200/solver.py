@@ -223,7 +223,8 @@ class PackedBatch:
         ns = np.diff(self.samp_off)
         self.job_off = np.zeros(self.n_jobs + 1, dtype=np.int64)
         if self.n_jobs:
-            self.job_off[1:] = np.cumsum(ns[jobs[:, 0]])
+            ok = (jobs[:, 0] >= 0) & (jobs[:, 0] < self.n_tracks)      # bad indices are reported by the C ABI
+            self.job_off[1:] = np.cumsum(np.where(ok, ns[np.clip(jobs[:, 0], 0, max(0, self.n_tracks - 1))], 0))
         rows = int(self.job_off[-1])
         self.rows = rows
         self.out_xy = alloc((rows, 2), np.float64)

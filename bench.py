@@ -258,7 +258,8 @@ def bench_ours(args):
         pass
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_traffic.json"))).get("dram_bytes_per_launch")
+        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, scaled to this launch's track count
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_traffic.json")))["dram_bytes_per_track"] * tpg
     except Exception:
         pass
 

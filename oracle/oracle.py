@@ -34,6 +34,8 @@ def build_ref():
     """Build oracle/_ref/* from /root/reference if it is mounted; prebuilt files are used otherwise."""
     if os.path.exists("/root/reference/src/main.cpp"):
         subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
+        # the drop-in demo binary links against the CUDA library, which must have been built first
+        subprocess.run(["make", "-C", _HERE, "dropin"], check=False, capture_output=True)
     return os.path.join(_HERE, "_ref")
 
 

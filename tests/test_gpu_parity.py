@@ -243,3 +243,37 @@ def test_rigid_motion_and_mirror_invariance(ctx, goldens):
     assert np.max(np.abs(res[0].alpha_total + res[2].alpha_total)) < TOL_ALPHA
     assert abs(res[0].lap_time - res[1].lap_time) < TOL_LAP_REL * res[0].lap_time
     assert abs(res[0].lap_time - res[2].lap_time) < TOL_LAP_REL * res[0].lap_time
+
+
+def test_dropin_binary_matches_reference_binary(tmp_path, goldens):
+    """The reference's own main() with ONLY its two solver calls redirected to the CUDA library
+    (oracle/_ref/fsd_path_b200, see oracle/Makefile `dropin`) against the unmodified reference binary:
+    same cone files in, same CSV columns out (s,x,y,heading_rad,curvature,alpha_last,v_mps,ax_mps2; main.cpp:1364, 1420)."""
+    import os
+    import subprocess
+    ref, ours = oracle.ref_binary("fsd_path"), oracle.ref_binary("fsd_path_b200")
+    if not (ref and ours):
+        pytest.skip("oracle/_ref binaries not built (they are built where /root/reference is mounted)")
+    g = goldens["competition_map3"]
+    np.savetxt(tmp_path / "inner.csv", g["inner_seg"][:, :2], delimiter=",", fmt="%.17g")
+    np.savetxt(tmp_path / "outer.csv", g["outer_seg"][:, :2], delimiter=",", fmt="%.17g")
+    outs = {}
+    for tag, exe in (("ref", ref), ("b200", ours)):
+        d = tmp_path / tag
+        d.mkdir()
+        r = subprocess.run([exe, str(tmp_path / "inner.csv"), str(tmp_path / "outer.csv"), str(d / "centerline.csv")],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lap = [l for l in r.stderr.splitlines() if "[mintime] Estimated laptime" in l]
+        outs[tag] = (d, lap)
+    assert outs["ref"][1] == outs["b200"][1] and outs["ref"][1], outs
+    for name, tols in (("centerline_raceline_with_geom.csv", [1e-6, 1e-4, 1e-4, 1e-6, 1e-6, 1e-4, 1e-4]),
+                       ("centerline_mintime_with_geom.csv", [1e-6, 1e-4, 1e-4, 1e-6, 1e-6, 1e-4, 1e-4, 1e-3])):
+        a = np.loadtxt(outs["ref"][0] / name, delimiter=",", skiprows=1)
+        b = np.loadtxt(outs["b200"][0] / name, delimiter=",", skiprows=1)
+        assert a.shape == b.shape and a.shape[0] > 100
+        for c, tol in enumerate(tols):
+            assert np.max(np.abs(a[:, c] - b[:, c])) <= tol + 2e-9, (name, c, np.max(np.abs(a[:, c] - b[:, c])))
+    # the stages the drop-in does not touch are byte-identical
+    for name in ("centerline.csv", "centerline_with_geom.csv", "centerline_inner_from_mids.csv"):
+        assert open(outs["ref"][0] / name).read() == open(outs["b200"][0] / name).read()

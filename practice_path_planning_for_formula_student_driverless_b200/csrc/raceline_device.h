@@ -36,6 +36,7 @@ struct SizeClass {
 constexpr int kNumClasses = 5;
 constexpr SizeClass kClasses[kNumClasses] = {{32, 8}, {64, 8}, {128, 8}, {256, 8}, {512, 8}};
 constexpr int kSegBlock = 8;  // segments per bounding box in the corridor ray-cast
+constexpr int kSupBlock = 8;  // boxes per super box (fast corridor path)
 
 inline int class_for_n(int n)
 {

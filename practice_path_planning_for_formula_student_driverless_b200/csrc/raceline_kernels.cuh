@@ -35,7 +35,8 @@ namespace rl {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int SB = kSegBlock;
+constexpr int SB = kSegBlock;   // segments per box
+constexpr int SU = kSupBlock;   // boxes per super box (fast corridor path)
 
 // scratch layout (bytes)
 constexpr int kScrBar = 0;
@@ -78,6 +79,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// issue a shared->global bulk store and return once its shared-memory source may be overwritten
+__device__ __forceinline__ void bulk_s2g_issue(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
@@ -411,103 +420,148 @@ __device__ __forceinline__ void halo_recv(Halo& h, const Part& pt, const double*
 
 struct PgdOut { double J0, Jend; int acc, bt, ev; };
 
+// std::min(hi, std::max(lo, a)) of main.cpp:731 as two compare-selects (fmin/fmax cost twice as much in SASS)
+__device__ __forceinline__ double clamp_box(double a, double lo, double hi)
+{
+    a = (lo < a) ? a : lo;
+    return (a < hi) ? a : hi;
+}
+
+// State shared by the two halves of the ping-pong loop below.
+template <int K>
+struct PgdCtx {
+    const double* sC0; const double* sCp; const double* sCm; double* sSt;
+    double* sRed; double* sExF; double* sExL;
+    double lamJ, armijo_c, step2, J, decp;
+    int ph;
+};
+
+// Evaluate the trial xa (halos ha), form the next trial xb = clamp(xa - step*g) speculatively, exchange its
+// halos and reduce (J(xa), g_prev.(xa - a)) through ONE barrier, then take the Armijo decision (main.cpp:734).
+// Returns true when xa is accepted: the stash then holds xa and xb/hb is the next trial.
+template <int T, int K, bool EXACT>
+__device__ __forceinline__ bool pgd_half(const Part& pt, const double (&xa)[K], const Halo& ha, double (&xb)[K], Halo& hb,
+                                         const double* sLo, const double* sHi, const double (&cL)[3],
+                                         const double (&cR)[3], PgdCtx<K>& c)
+{
+    double gh[K];
+    double Jz = 0.0, Sd = 0.0;
+    eval_window<T, K, EXACT>(xa, ha, pt.cnt, c.sC0, c.sCp, c.sCm, cL, cR, c.lamJ, Jz, Sd, gh);
+    double Jn = fma(c.lamJ, Sd, Jz);
+    double dec2p = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double xn = clamp_box(fma(-c.step2, gh[k], xa[k]), sLo[k * T], sHi[k * T]);
+        dec2p = fma(gh[k], xn - xa[k], dec2p);
+        xb[k] = xn;
+    }
+    hb = halo_send<T, K, EXACT>(xb, pt, c.sExF + c.ph * 32, c.sExL + c.ph * 32);
+    double dec = c.decp;
+    block_sum2<T>(Jn, dec, c.sRed + c.ph * 32, pt.lane, pt.warp);
+    halo_recv<T>(hb, pt, c.sExF + c.ph * 32, c.sExL + c.ph * 32);
+    c.ph ^= 1;
+    dec *= 2.0;                                    // gh is grad/2: back to grad . (a_new - alpha), main.cpp:733
+    if (Jn <= c.J + c.armijo_c * dec) {            // Armijo accept, main.cpp:734
+#pragma unroll
+        for (int k = 0; k < K; ++k) c.sSt[k * T] = xa[k];
+        c.decp = dec2p; c.J = Jn;
+        return true;
+    }
+    return false;
+}
+
 // One outer iteration's projected-gradient loop with Armijo backtracking (main.cpp:723-742 / 996-1026).
-// In: coefficients in shared memory (sC0/sCp/sCm, already offset by tid), cL/cR halo coefficients, box lo/hi.
+// In: coefficients and box bounds in shared memory (sC0/sCp/sCm/sLo/sHi, already offset by tid), cL/cR halo
+// coefficients.
 // Out: the accepted alpha of the owned slots in the stash sSt[k*T] (also already offset by tid).
 //
 // Steady state costs ONE barrier per evaluation: after the gradient of trial x is known, the next trial
-// x2 = clamp(x - step*g) is formed speculatively (it is the reference's next trial whenever x is accepted,
+// y = clamp(x - step*g) is formed speculatively (it is the reference's next trial whenever x is accepted,
 // and x is accepted ~98% of the time), its halos are exchanged and (J(x), g_prev.(x-a)) are reduced through
-// the same barrier.  On a reject the step halves and the trial is rebuilt from the stashed accepted alpha.
+// the same barrier.  The trial alternates between two register arrays (x, y) so that an accept moves no data.
+// On a reject the step halves and the trial is rebuilt from the stashed accepted alpha.
 template <int T, int K, bool EXACT>
-__device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double (&lo)[K], const double (&hi)[K],
+__device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, const double* sHi,
                                             const double (&cL)[3], const double (&cR)[3],
                                             const double* sC0, const double* sCp, const double* sCm, double* sSt,
                                             double* sRed, double* sExF, double* sExL, int& ph,
                                             double lamJ, double step_init, double step_min, double armijo_c, int max_inner)
 {
     PgdOut o; o.acc = 0; o.bt = 0; o.ev = 0;
-    double x[K], gh[K];
-    Halo hx; hx.l0 = hx.l1 = hx.r0 = hx.r1 = 0.0;
+    PgdCtx<K> c;
+    c.sC0 = sC0; c.sCp = sCp; c.sCm = sCm; c.sSt = sSt; c.sRed = sRed; c.sExF = sExF; c.sExL = sExL;
+    c.lamJ = lamJ; c.armijo_c = armijo_c; c.ph = ph;
+    c.step2 = 2.0 * step_init;   // gh is grad/2, so alpha - step*grad = alpha - step2*gh
+    double x[K], y[K];
+    Halo hx, hy;
+    hx.l0 = hx.l1 = hx.r0 = hx.r1 = 0.0;
+    hy = hx;
 #pragma unroll
-    for (int k = 0; k < K; ++k) { x[k] = 0.0; sSt[k * T] = 0.0; }
-    double step2 = 2.0 * step_init;   // gh is grad/2, so alpha - step*grad = alpha - step2*gh
-    // ---- J and gradient at alpha = 0 (main.cpp:724 / 997) ----
-    double Jz = 0.0, Sd = 0.0;
-    eval_window<T, K, EXACT>(x, hx, pt.cnt, sC0, sCp, sCm, cL, cR, lamJ, Jz, Sd, gh);
-    o.ev++;
-    double Jt = fma(lamJ, Sd, Jz);
-    // first trial
-    double decp = 0.0;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const double xn = fmin(hi[k], fmax(lo[k], -step2 * gh[k]));
-        decp = fma(gh[k], xn, decp);
-        x[k] = xn;
-    }
-    hx = halo_send<T, K, EXACT>(x, pt, sExF + ph * 32, sExL + ph * 32);
-    double zero = 0.0;
-    block_sum2<T>(Jt, zero, sRed + ph * 32, pt.lane, pt.warp);
-    halo_recv<T>(hx, pt, sExF + ph * 32, sExL + ph * 32);
-    ph ^= 1;
-    double J = Jt, Jprev = Jt;
-    o.J0 = Jt;
-    int it = 0, bt = 0;
-    while (it < max_inner) {
-        // ---- evaluate the trial x ----
-        Jz = 0.0; Sd = 0.0;
+    for (int k = 0; k < K; ++k) { x[k] = 0.0; y[k] = 0.0; sSt[k * T] = 0.0; }
+    {
+        // ---- J and gradient at alpha = 0 (main.cpp:724 / 997), first trial into x ----
+        double gh[K];
+        double Jz = 0.0, Sd = 0.0;
         eval_window<T, K, EXACT>(x, hx, pt.cnt, sC0, sCp, sCm, cL, cR, lamJ, Jz, Sd, gh);
         o.ev++;
-        double Jn = fma(lamJ, Sd, Jz);
-        // ---- speculative next trial ----
-        double x2[K];
-        double dec2p = 0.0;
+        double Jt = fma(lamJ, Sd, Jz);
+        double decp = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const double xn = fmin(hi[k], fmax(lo[k], fma(-step2, gh[k], x[k])));
-            dec2p = fma(gh[k], xn - x[k], dec2p);
-            x2[k] = xn;
+            const double xn = clamp_box(-c.step2 * gh[k], sLo[k * T], sHi[k * T]);
+            decp = fma(gh[k], xn, decp);
+            x[k] = xn;
         }
-        Halo h2 = halo_send<T, K, EXACT>(x2, pt, sExF + ph * 32, sExL + ph * 32);
-        double dec = decp;
-        block_sum2<T>(Jn, dec, sRed + ph * 32, pt.lane, pt.warp);
-        halo_recv<T>(h2, pt, sExF + ph * 32, sExL + ph * 32);
-        ph ^= 1;
-        dec *= 2.0;                                   // back to grad . (a_new - alpha), main.cpp:733
-        if (Jn <= J + armijo_c * dec) {               // Armijo accept, main.cpp:734
-#pragma unroll
-            for (int k = 0; k < K; ++k) { sSt[k * T] = x[k]; x[k] = x2[k]; }
-            hx = h2; decp = dec2p; J = Jn;
+        hx = halo_send<T, K, EXACT>(x, pt, sExF + c.ph * 32, sExL + c.ph * 32);
+        double zero = 0.0;
+        block_sum2<T>(Jt, zero, sRed + c.ph * 32, pt.lane, pt.warp);
+        halo_recv<T>(hx, pt, sExF + c.ph * 32, sExL + c.ph * 32);
+        c.ph ^= 1;
+        c.J = Jt; c.decp = decp;
+        o.J0 = Jt;
+    }
+    double Jprev = c.J;
+    int it = 0, bt = 0;
+    bool in_x = true;    // which array holds the current trial
+    while (it < max_inner) {
+        const bool acc = in_x ? pgd_half<T, K, EXACT>(pt, x, hx, y, hy, sLo, sHi, cL, cR, c)
+                              : pgd_half<T, K, EXACT>(pt, y, hy, x, hx, sLo, sHi, cL, cR, c);
+        o.ev++;
+        if (acc) {
+            in_x = !in_x;
             o.acc++; it++; bt = 0;
-            if (fabs(Jprev - J) < 1e-10) break;       // main.cpp:740
-            Jprev = J;
+            if (fabs(Jprev - c.J) < 1e-10) break;       // main.cpp:740
+            Jprev = c.J;
         } else {
-            step2 *= 0.5; bt++; o.bt++;               // main.cpp:737
-            if (0.5 * step2 < step_min || bt >= 20) break;   // not accepted: leave the inner loop (main.cpp:739)
-            // rebuild the trial from the accepted alpha: its gradient is recomputed (rejects are rare)
-            double a[K];
+            c.step2 *= 0.5; bt++; o.bt++;               // main.cpp:737
+            if (0.5 * c.step2 < step_min || bt >= 20) break;   // not accepted: leave the inner loop (main.cpp:739)
+            // rebuild the trial (into x) from the accepted alpha; its gradient is recomputed (rejects are rare)
+            double a[K], gh[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) a[k] = sSt[k * T];
-            Halo ha = halo_send<T, K, EXACT>(a, pt, sExF + ph * 32, sExL + ph * 32);
+            Halo ha = halo_send<T, K, EXACT>(a, pt, sExF + c.ph * 32, sExL + c.ph * 32);
             block_sync<T>();
-            halo_recv<T>(ha, pt, sExF + ph * 32, sExL + ph * 32);
-            ph ^= 1;
+            halo_recv<T>(ha, pt, sExF + c.ph * 32, sExL + c.ph * 32);
+            c.ph ^= 1;
             double jz = 0.0, sd = 0.0;
             eval_window<T, K, EXACT>(a, ha, pt.cnt, sC0, sCp, sCm, cL, cR, lamJ, jz, sd, gh);
-            decp = 0.0;
+            double decp = 0.0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double xn = fmin(hi[k], fmax(lo[k], fma(-step2, gh[k], a[k])));
+                const double xn = clamp_box(fma(-c.step2, gh[k], a[k]), sLo[k * T], sHi[k * T]);
                 decp = fma(gh[k], xn - a[k], decp);
                 x[k] = xn;
             }
-            hx = halo_send<T, K, EXACT>(x, pt, sExF + ph * 32, sExL + ph * 32);
+            c.decp = decp;
+            hx = halo_send<T, K, EXACT>(x, pt, sExF + c.ph * 32, sExL + c.ph * 32);
             block_sync<T>();
-            halo_recv<T>(hx, pt, sExF + ph * 32, sExL + ph * 32);
-            ph ^= 1;
+            halo_recv<T>(hx, pt, sExF + c.ph * 32, sExL + c.ph * 32);
+            c.ph ^= 1;
+            in_x = true;
         }
     }
-    o.Jend = J;
+    ph = c.ph;
+    o.Jend = c.J;
     return o;
 }
 
@@ -681,6 +735,12 @@ __device__ __forceinline__ void corridor_build_tiled(const Part& pt, const doubl
     block_sync<T>();
 }
 
+// segments of one ring that fit region B together with their FP32 copy, boxes and super boxes
+__host__ __device__ constexpr int fast_tile_cap(int np)
+{
+    return (int)(((long long)32 * np * SB * SU) / (48 * SB * SU + 16 * SU + 16)) / (SB * SU) * (SB * SU);
+}
+
 // ---- corridor, fast path (both rings fit one tile each) ---------------------------------------------------
 // Same results as corridor_build_tiled / the reference loops, far fewer tests:
 //  * rays, not lines: a box is visited only if it meets the +n or -n RAY inside [0, best hit so far]; the
@@ -728,14 +788,14 @@ __device__ __forceinline__ int ray_scan(const RayTile& tl, double2 P, double nx,
     float bnf = (bn < INF) ? __double2float_ru(bn) : __int_as_float(0x7f800000);
     int best_box = -1;
     double best_abs = INF;
-    int sb0 = hint / SB;
+    int sb0 = hint / SU;
     if (sb0 >= tl.nsup) sb0 = 0;
     for (int q = 0; q < tl.nsup; ++q) {
         int sb = sb0 + q;
         if (sb >= tl.nsup) sb -= tl.nsup;
         if (!ray_box(tl.supF[sb], px, py, fnx, fny, anx, any, m, bpf, bnf, wp, wn)) continue;
-        const int b1 = min(tl.nblk, sb * SB + SB);
-        for (int b = sb * SB; b < b1; ++b) {
+        const int b1 = min(tl.nblk, sb * SU + SU);
+        for (int b = sb * SU; b < b1; ++b) {
             if (!ray_box(tl.boxF[b], px, py, fnx, fny, anx, any, m, bpf, bnf, wp, wn)) continue;
             const int s1 = min(tl.nt, b * SB + SB);
             for (int s = b * SB; s < s1; ++s) {
@@ -780,7 +840,7 @@ __device__ __forceinline__ double dist_scan(const RayTile& tl, double2 P, float 
     const double INF = dinf();
     double best2 = INF;
     float boundf = (ub < INF) ? __double2float_ru(ub) * (1.f + 1e-5f) + m : __int_as_float(0x7f800000);
-    int sb0 = hint / SB;
+    int sb0 = hint / SU;
     if (sb0 >= tl.nsup) sb0 = 0;
     for (int q = 0; q < tl.nsup; ++q) {
         int sb = sb0 + q;
@@ -790,8 +850,8 @@ __device__ __forceinline__ double dist_scan(const RayTile& tl, double2 P, float 
             const float ddx = fmaxf(0.f, fabsf(bx.x - px) - bx.z - m), ddy = fmaxf(0.f, fabsf(bx.y - py) - bx.w - m);
             if (ddx * ddx + ddy * ddy > boundf * boundf) continue;
         }
-        const int b1 = min(tl.nblk, sb * SB + SB);
-        for (int b = sb * SB; b < b1; ++b) {
+        const int b1 = min(tl.nblk, sb * SU + SU);
+        for (int b = sb * SU; b < b1; ++b) {
             const float4 bx = tl.boxF[b];
             const float ddx = fmaxf(0.f, fabsf(bx.x - px) - bx.z - m), ddy = fmaxf(0.f, fabsf(bx.y - py) - bx.w - m);
             if (ddx * ddx + ddy * ddy > boundf * boundf) continue;
@@ -802,8 +862,8 @@ __device__ __forceinline__ double dist_scan(const RayTile& tl, double2 P, float 
                     const float vx = f.z - f.x, vy = f.w - f.y, apx = px - f.x, apy = py - f.y;
                     const float tt = fminf(1.f, fmaxf(0.f, __fdividef(vx * apx + vy * apy, fmaxf(1e-30f, vx * vx + vy * vy))));
                     const float ex = apx - vx * tt, ey = apy - vy * tt;
-                    const float d = sqrtf(ex * ex + ey * ey) - 4.f * m;
-                    if (d > boundf) continue;
+                    const float bq = boundf + 4.f * m;
+                    if (ex * ex + ey * ey > bq * bq) continue;
                 }
                 const double x0 = tl.segD[4 * s], y0 = tl.segD[4 * s + 1], vx = tl.segD[4 * s + 2], vy = tl.segD[4 * s + 3];
                 const double apx = P.x - x0, apy = P.y - y0;
@@ -814,7 +874,7 @@ __device__ __forceinline__ double dist_scan(const RayTile& tl, double2 P, float 
                 const double d2 = ex * ex + ey * ey;
                 if (d2 < best2) {
                     best2 = d2;
-                    const float df = __double2float_ru(sqrt(d2)) * (1.f + 1e-5f) + m;
+                    const float df = sqrtf(__double2float_ru(d2)) * (1.f + 1e-5f) + m;
                     boundf = fminf(boundf, df);
                 }
             }
@@ -830,8 +890,8 @@ __device__ __forceinline__ bool inside_ring(const RayTile& tl, double2 P, float 
     for (int sb = 0; sb < tl.nsup; ++sb) {
         const float4 sx = tl.supF[sb];
         if (fabsf(sx.y - py) > sx.w + m || px > sx.x + sx.z + m) continue;
-        const int b1 = min(tl.nblk, sb * SB + SB);
-        for (int b = sb * SB; b < b1; ++b) {
+        const int b1 = min(tl.nblk, sb * SU + SU);
+        for (int b = sb * SU; b < b1; ++b) {
             const float4 bx = tl.boxF[b];
             if (fabsf(bx.y - py) > bx.w + m || px > bx.x + bx.z + m) continue;
             const int s1 = min(tl.nt, b * SB + SB);
@@ -856,14 +916,14 @@ __device__ __forceinline__ float ring_tile_build(const Part& pt, double* sB, uin
                                                  RayTile& tl, bool& closed)
 {
     constexpr int NP = T * K;
-    constexpr int CAP = ((32 * NP * 4) / 201) / (SB * SB) * (SB * SB);   // 50.25 bytes per segment
+    constexpr int CAP = fast_tile_cap(NP);
     const int tid = pt.tid;
     double* segD = sB;
     float4* segF = reinterpret_cast<float4*>(sB + 4 * CAP);
     float4* boxF = segF + CAP;
     float4* supF = boxF + CAP / SB;
     tl.segD = segD; tl.segF = segF; tl.boxF = boxF; tl.supF = supF;
-    tl.nt = mr; tl.nblk = (mr + SB - 1) / SB; tl.nsup = (tl.nblk + SB - 1) / SB;
+    tl.nt = mr; tl.nblk = (mr + SB - 1) / SB; tl.nsup = (tl.nblk + SU - 1) / SU;
     block_sync<T>();
     if (tid == 0) {
         sMisc[0] = 0;
@@ -908,8 +968,8 @@ __device__ __forceinline__ float ring_tile_build(const Part& pt, double* sB, uin
     block_sync<T>();
     for (int sb = tid; sb < tl.nsup; sb += T) {
         float xmin = 3e38f, xmax = -3e38f, ymin = 3e38f, ymax = -3e38f;
-        const int e = min(tl.nblk, sb * SB + SB);
-        for (int b = sb * SB; b < e; ++b) {
+        const int e = min(tl.nblk, sb * SU + SU);
+        for (int b = sb * SU; b < e; ++b) {
             const float4 bx = boxF[b];
             xmin = fminf(xmin, bx.x - bx.z); xmax = fmaxf(xmax, bx.x + bx.z);
             ymin = fminf(ymin, bx.y - bx.w); ymax = fmaxf(ymax, bx.y + bx.w);
@@ -1114,7 +1174,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
 
     double lo[K], hi[K];
     // initial corridor from the centre line: guard uses the veh_width ARGUMENT (main.cpp:706 / 930)
-    constexpr int CAPF = ((32 * NP * 4) / 201) / (SB * SB) * (SB * SB);
+    constexpr int CAPF = fast_tile_cap(NP);
     const bool fast_rays = (segO0 - segI0 <= CAPF) && (segE - segO0 <= CAPF) && (CAPF / SB < 16384);
     const bool parity_ok = (C.veh_width_arg * 0.5 + C.safety_margin_m >= 0.0) && (C.veh_width_m * 0.5 + C.safety_margin_m >= 0.0);
     for (int i = tid; i < NP; i += T) sHint[i] = 0u;
@@ -1148,6 +1208,16 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
                 Wd[k] = pow15(xp * xp + yp * yp);     // denom; W = 1/denom (main.cpp:647-648)
             }
         }
+        // ---- park the path in global memory (the job's xy rows) while the PGD runs: its shared-memory
+        //      region holds the box bounds lo|hi (slot-major) until the path update needs P again ----
+        fence_proxy_async();
+        block_sync<T>();
+        if (tid == 0) bulk_s2g_issue(B.xy + 2 * row0, sP, (uint32_t)N * 16u);   // returns once the smem read is done
+        block_sync<T>();
+        double* sLo = reinterpret_cast<double*>(sP) + tid;
+        double* sHi = sLo + NP;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { sLo[k * T] = lo[k]; sHi[k * T] = hi[k]; }
         double gam[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) gam[k] = 1.0;
@@ -1218,13 +1288,22 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
             if (cnt < K && cnt > 0) { sC0[cnt * T] = cR[0]; sCp[cnt * T] = cR[1]; sCm[cnt * T] = cR[2]; }
         }
         // =================== projected gradient with Armijo (main.cpp:723-742 / 996-1026) ===================
-        const PgdOut po = pgd_outer<T, K, EXACT>(pt, lo, hi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,
+        const PgdOut po = pgd_outer<T, K, EXACT>(pt, sLo, sHi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,
                                                  C.step_init, C.step_min, C.armijo_c, C.max_inner_iters);
         acc_total += po.acc; bt_total += po.bt; ev_total += po.ev;
         if (tid == 0 && outer < RL_MAX_OUTER_LOG) {
             st->J0[outer] = po.J0; st->Jend[outer] = po.Jend; st->lap_outer[outer] = lap_outer;
             st->acc_outer[outer] = po.acc; st->bt_outer[outer] = po.bt;
         }
+        // ---- bring the path back ----
+        block_sync<T>();
+        if (tid == 0) {
+            bulk_wait_all();                       // the parked copy is complete and visible
+            fence_proxy_async();
+            mbar_expect_tx(mbar, (uint32_t)N * 16u);
+            bulk_g2s(sP, B.xy + 2 * row0, (uint32_t)N * 16u, mbar);
+        }
+        mbar_wait(mbar, bar_phase); bar_phase ^= 1;
         // =================== path update (main.cpp:743-746 / 1027-1031) ===================
         double2 Pn[K];
 #pragma unroll

@@ -52,7 +52,7 @@ inline size_t smem_bytes_for_class(int T, int K)
     return np * 16      /* path points, double2            */
            + np * 8 * 4 /* region B: PGD coefficients+stash / ray tile+corridor staging */
            + 2048       /* barriers, reduction + halo exchange scratch */
-           + np * 4;    /* per-sample corridor hint words */
+           + np * 6;    /* per-sample corridor state: anchor segments + parity bits (4 B), clearances (2 B) */
 }
 
 // launches job_list[0..n_list) (indices into B.jobs) with the kernel of class `cls`

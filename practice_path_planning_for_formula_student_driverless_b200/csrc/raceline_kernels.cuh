@@ -777,8 +777,9 @@ __device__ __forceinline__ bool ray_box(const float4 bx, float px, float py, flo
 }
 
 // scan one ring for one sample.  bp/bn: running nearest +n / -n hit over both rings (pruning bound);
-// pos_r/neg_r: nearest hit found on THIS ring (INF if none inside the bound).  Returns the box of the nearest hit.
-__device__ __forceinline__ int ray_scan(const RayTile& tl, double2 P, double nx, double ny, float px, float py, float fnx, float fny,
+// pos_r/neg_r: nearest hit found on THIS ring (INF if none inside the bound).  hint: box to start at.
+// Returns the segment of the nearest hit (-1 if none).
+__device__ __noinline__ int ray_scan(const RayTile& tl, double2 P, double nx, double ny, float px, float py, float fnx, float fny,
                                         float m, int hint, bool wp, bool wn, bool first_hit_only,
                                         double& bp, double& bn, double& pos_r, double& neg_r, long long& tests)
 {
@@ -786,7 +787,7 @@ __device__ __forceinline__ int ray_scan(const RayTile& tl, double2 P, double nx,
     const float anx = fabsf(fnx), any = fabsf(fny);
     float bpf = (bp < INF) ? __double2float_ru(bp) : __int_as_float(0x7f800000);
     float bnf = (bn < INF) ? __double2float_ru(bn) : __int_as_float(0x7f800000);
-    int best_box = -1;
+    int best_box = -1;   // segment index of the nearest hit found
     double best_abs = INF;
     int sb0 = hint / SU;
     if (sb0 >= tl.nsup) sb0 = 0;
@@ -815,14 +816,14 @@ __device__ __forceinline__ int ray_scan(const RayTile& tl, double2 P, double nx,
                         if (wp) {
                             pos_r = fmin(pos_r, t);
                             if (t < bp) { bp = t; bpf = __double2float_ru(t); }
-                            if (t < best_abs) { best_abs = t; best_box = b; }
+                            if (t < best_abs) { best_abs = t; best_box = s; }
                             if (first_hit_only) return best_box;
                         }
                     } else if (t < 0.0) {                                       // -n ray: t' = -t
                         if (wn) {
                             neg_r = fmin(neg_r, -t);
                             if (-t < bn) { bn = -t; bnf = __double2float_ru(-t); }
-                            if (-t < best_abs) { best_abs = -t; best_box = b; }
+                            if (-t < best_abs) { best_abs = -t; best_box = s; }
                             if (first_hit_only) return best_box;
                         }
                     }
@@ -835,7 +836,7 @@ __device__ __forceinline__ int ray_scan(const RayTile& tl, double2 P, double nx,
 
 // nearest point-segment distance to the ring (minDistanceToSegments_global, main.cpp:501-512); ub: any known
 // upper bound (a hit point lies on the ring) or INF.
-__device__ __forceinline__ double dist_scan(const RayTile& tl, double2 P, float px, float py, float m, int hint, double ub)
+__device__ __noinline__ double dist_scan(const RayTile& tl, double2 P, float px, float py, float m, int hint, double ub)
 {
     const double INF = dinf();
     double best2 = INF;
@@ -884,7 +885,7 @@ __device__ __forceinline__ double dist_scan(const RayTile& tl, double2 P, float 
 }
 
 // parity of the crossings of the +x ray from P with a CLOSED chain (vertices shared bit for bit): P inside?
-__device__ __forceinline__ bool inside_ring(const RayTile& tl, double2 P, float px, float py, float m)
+__device__ __noinline__ bool inside_ring(const RayTile& tl, double2 P, float px, float py, float m)
 {
     int cnt = 0;
     for (int sb = 0; sb < tl.nsup; ++sb) {
@@ -983,79 +984,293 @@ __device__ __forceinline__ float ring_tile_build(const Part& pt, double* sB, uin
     return m;
 }
 
-// sHint word per sample: bits 0-13 hint box ring 0, 14-27 hint box ring 1, 28/29 sample inside ring 0/1
+// ---- per-sample corridor state (persists across the outer iterations, in shared memory) ------------------
+// sHint[i]: bits 0-12 / 13-25 anchor segment j0 of ring 0 / 1 (the segment of the sample's nearest hit when the
+//           state was taken), bits 26/27 sample inside ring 0/1 (parity, once per job), bits 28/29 state valid.
+// sClr[i] : two bytes, clearance of ring 0 / 1 in units of 1/4 m, rounded down and measured at the CENTRE-LINE
+//           position C0 of the sample: every segment of the ring OUTSIDE the index window [j0-W, j0+W] is at
+//           least that far from C0.  For a later path position P with |P - C0| = disp, every outside segment is
+//           at least Rc = clearance - disp away, so
+//             * a window hit with t <= Rc is the nearest hit of the whole ring,
+//             * no window hit means the ring has no hit with t < Rc,
+//             * a window point-segment distance <= Rc is the point-ring distance,
+//           and nothing but the 2W+1 window segments has to be touched.  When a certificate fails the general
+//           box-hierarchy search runs for that sample and refreshes its state.
+constexpr int kWin = 3;
+
+__device__ __forceinline__ int wrap_seg(int s, int M) { return (s < 0) ? s + M : ((s >= M) ? s - M : s); }
+
+// exact ray/segment test of main.cpp:478-490 for both rays of the line; updates the nearest +n / -n hits
+__device__ __forceinline__ void seg_hit(const double* sd, double2 P, double nx, double ny, double& pos, double& neg, int s,
+                                        int& seg_p, int& seg_n, long long& tests)
+{
+    const double x0 = sd[0], y0 = sd[1], vx = sd[2], vy = sd[3];
+    const double den = nx * (-vy) + ny * vx;                         // main.cpp:483
+    ++tests;
+    if (fabs(den) < 1e-15) return;                                   // main.cpp:484
+    const double ax = x0 - P.x, ay = y0 - P.y;                      // main.cpp:485
+    const double inv = 1.0 / den;
+    const double t = (ax * (-vy) + ay * vx) * inv;                  // main.cpp:486
+    const double u = (nx * ay - ny * ax) * inv;                     // main.cpp:487
+    if (u >= -1e-12 && u <= 1.0 + 1e-12) {                          // main.cpp:488
+        if (t > 0.0) { if (t < pos) { pos = t; seg_p = s; } }       // +n ray, main.cpp:497
+        else if (t < 0.0) { if (-t < neg) { neg = -t; seg_n = s; } } // -n ray: t' = -t
+    }
+}
+
+// nearest +n / -n hits among the window segments [j0-W, j0+W] of the ring
+__device__ __forceinline__ void window_rays(const RayTile& tl, double2 P, double nx, double ny, float px, float py, float fnx,
+                                            float fny, float m, int j0, double& pos, double& neg, int& seg_p, int& seg_n,
+                                            long long& tests)
+{
+    const int M = tl.nt;
+    const int cntw = min(M, 2 * kWin + 1);
+    int s = (M > 2 * kWin + 1) ? wrap_seg(j0 - kWin, M) : 0;
+    for (int q = 0; q < cntw; ++q) {
+        const float4 f = tl.segF[s];
+        const float sa = fnx * (f.y - py) - fny * (f.x - px), sbb = fnx * (f.w - py) - fny * (f.z - px);
+        if (!(fminf(sa, sbb) > m || fmaxf(sa, sbb) < -m)) seg_hit(tl.segD + 4 * s, P, nx, ny, pos, neg, s, seg_p, seg_n, tests);
+        s = (s + 1 == M) ? 0 : s + 1;
+    }
+}
+
+// exact distance from P to segment s (minDistanceToSegments_global body, main.cpp:504-509), squared
+__device__ __forceinline__ double seg_dist2(const double* sd, double2 P)
+{
+    const double x0 = sd[0], y0 = sd[1], vx = sd[2], vy = sd[3];
+    const double apx = P.x - x0, apy = P.y - y0;
+    const double denom = fmax(1e-30, vx * vx + vy * vy);
+    const double tt = fmin(1.0, fmax(0.0, (vx * apx + vy * apy) / denom));
+    const double ex = P.x - (x0 + vx * tt), ey = P.y - (y0 + vy * tt);
+    return ex * ex + ey * ey;
+}
+// FP32 lower bound material: squared distance from p to the FP32 copy of a segment
+__device__ __forceinline__ float seg_dist2_f(const float4 f, float px, float py)
+{
+    const float vx = f.z - f.x, vy = f.w - f.y, apx = px - f.x, apy = py - f.y;
+    const float tt = fminf(1.f, fmaxf(0.f, __fdividef(vx * apx + vy * apy, fmaxf(1e-30f, vx * vx + vy * vy))));
+    const float ex = apx - vx * tt, ey = apy - vy * tt;
+    return ex * ex + ey * ey;
+}
+
+// nearest point-segment distance among the window segments
+__device__ __forceinline__ double window_dist(const RayTile& tl, double2 P, float px, float py, float m, int j0, double ub)
+{
+    const double INF = dinf();
+    const int M = tl.nt;
+    const int cntw = min(M, 2 * kWin + 1);
+    int s = (M > 2 * kWin + 1) ? wrap_seg(j0 - kWin, M) : 0;
+    double best2 = INF;
+    float boundf = (ub < INF) ? __double2float_ru(ub) * (1.f + 1e-5f) + m : 3e18f;
+    for (int q = 0; q < cntw; ++q) {
+        const float bq = boundf + 4.f * m;
+        if (seg_dist2_f(tl.segF[s], px, py) <= bq * bq) {
+            const double d2 = seg_dist2(tl.segD + 4 * s, P);
+            if (d2 < best2) { best2 = d2; boundf = fminf(boundf, sqrtf(__double2float_ru(d2)) * (1.f + 1e-5f) + m); }
+        }
+        s = (s + 1 == M) ? 0 : s + 1;
+    }
+    return (best2 < INF) ? sqrt(best2) : INF;
+}
+
+// conservative (rounded down) distance from p to every segment of the ring outside the window of j0
+__device__ __noinline__ float clearance_scan(const RayTile& tl, float px, float py, float m, int j0)
+{
+    const int M = tl.nt;
+    if (M <= 2 * kWin + 1) return 3e18f;
+    float best = 3e18f;   // distance, not squared
+    int sb0 = (j0 / SB) / SU;
+    if (sb0 >= tl.nsup) sb0 = 0;
+    for (int q = 0; q < tl.nsup; ++q) {
+        int sb = sb0 + q;
+        if (sb >= tl.nsup) sb -= tl.nsup;
+        {
+            const float4 bx = tl.supF[sb];
+            const float ddx = fmaxf(0.f, fabsf(bx.x - px) - bx.z), ddy = fmaxf(0.f, fabsf(bx.y - py) - bx.w);
+            if (ddx * ddx + ddy * ddy >= best * best) continue;
+        }
+        const int b1 = min(tl.nblk, sb * SU + SU);
+        for (int b = sb * SU; b < b1; ++b) {
+            const float4 bx = tl.boxF[b];
+            const float ddx = fmaxf(0.f, fabsf(bx.x - px) - bx.z), ddy = fmaxf(0.f, fabsf(bx.y - py) - bx.w);
+            if (ddx * ddx + ddy * ddy >= best * best) continue;
+            const int s1 = min(M, b * SB + SB);
+            for (int s = b * SB; s < s1; ++s) {
+                int dj = s - j0; if (dj < 0) dj += M;
+                if (dj <= kWin || dj >= M - kWin) continue;              // window segment
+                const float d = sqrtf(seg_dist2_f(tl.segF[s], px, py)) - 4.f * m;
+                best = fminf(best, fmaxf(d, 0.f));
+            }
+        }
+    }
+    return best;
+}
+
 template <int T, int K>
 __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double2* sP, double* sB, uint64_t* mbar, uint32_t& bar_phase,
-                                                    int* sMisc, unsigned* sHint, bool first, bool parity_ok,
-                                                    const double* __restrict__ gseg, long long segI0, long long segO0, long long segE,
+                                                    int* sMisc, unsigned* sHint, unsigned short* sClr, bool first, bool parity_ok,
+                                                    const double* __restrict__ gseg, const double* __restrict__ gcenter,
+                                                    long long segI0, long long segO0, long long segE,
                                                     double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests)
 {
     constexpr int NP = T * K;
     const int N = pt.N, tid = pt.tid;
     const double INF = dinf();
+    const float FINF = __int_as_float(0x7f800000);
     const double2 org = sP[0];
     double bp[K], bn[K], dfp[K], dfn[K];
+    float lbp[K], lbn[K];          // "a hit exists on some ring, value unknown but >= lb" (parity certificate)
+    unsigned flagged = 0u;         // bit j: sample j must be redone by the general search
 #pragma unroll
-    for (int j = 0; j < K; ++j) { bp[j] = INF; bn[j] = INF; dfp[j] = INF; dfn[j] = INF; }
-    // parity_ok: the parity shortcut needs the path never to cross a ring between builds (every guard >= 0)
+    for (int j = 0; j < K; ++j) { bp[j] = INF; bn[j] = INF; dfp[j] = INF; dfn[j] = INF; lbp[j] = FINF; lbn[j] = FINF; }
+    // ring order: the ring the samples lie INSIDE of goes first (its far hits are settled by parity, and the
+    // bounds it produces let the other ring skip most existence questions)
+    const unsigned h0 = sHint[0];
+    const int first_ring = (!first && ((h0 >> 27) & 1u) && !((h0 >> 26) & 1u)) ? 1 : 0;
 
-    for (int ring = 0; ring < 2; ++ring) {
-        const long long base = ring ? segO0 : segI0;
-        const int mr = (int)(ring ? (segE - segO0) : (segO0 - segI0));
-        if (mr == 0) {   // safe_ray on an empty ring returns 0 (main.cpp:696-698)
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            if (!block_or<T>(flagged != 0u)) break;
 #pragma unroll
-            for (int j = 0; j < K; ++j) { dfp[j] = 0.0; dfn[j] = 0.0; }
-            continue;
+            for (int j = 0; j < K; ++j)
+                if ((flagged >> j) & 1u) { bp[j] = INF; bn[j] = INF; dfp[j] = INF; dfn[j] = INF; lbp[j] = FINF; lbn[j] = FINF; }
         }
-        RayTile tl;
-        bool closed;
-        const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, closed);
-        const int hshift = ring ? 14 : 0;
+        for (int rr = 0; rr < 2; ++rr) {
+            const int ring = rr ^ first_ring;
+            const long long base = ring ? segO0 : segI0;
+            const int mr = (int)(ring ? (segE - segO0) : (segO0 - segI0));
+            if (mr == 0) {   // safe_ray on an empty ring returns 0 (main.cpp:696-698)
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const int i = tid + j * T;
-            if (i >= N) continue;
-            const double2 Pc = sP[i];
-            double nx, ny;
-            normal_closed(sp_prev(sP, i, N), sp_next(sP, i, N), N, nx, ny);
-            const float px = (float)(Pc.x - org.x), py = (float)(Pc.y - org.y), fnx = (float)nx, fny = (float)ny;
-            const float m = m0 + 2e-6f * fmaxf(fabsf(px), fabsf(py));
-            unsigned hw = sHint[i];
-            int hint = (int)((hw >> hshift) & 0x3fffu);
-            if (first) {
-                // nearest box centre: a good place to start, and the parity bit of this sample
-                float bd = 3e38f; hint = 0;
-                for (int b = 0; b < tl.nblk; ++b) {
-                    const float4 bx = tl.boxF[b];
-                    const float d = (bx.x - px) * (bx.x - px) + (bx.y - py) * (bx.y - py);
-                    if (d < bd) { bd = d; hint = b; }
+                for (int j = 0; j < K; ++j) { dfp[j] = 0.0; dfn[j] = 0.0; }
+                continue;
+            }
+            RayTile tl;
+            bool closed;
+            const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, closed);
+            const int hshift = 13 * ring;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int i = tid + j * T;
+                if (i >= N) continue;
+                if (pass == 1 && !((flagged >> j) & 1u)) continue;
+                const double2 Pc = sP[i];
+                double nx, ny;
+                normal_closed(sp_prev(sP, i, N), sp_next(sP, i, N), N, nx, ny);
+                const float px = (float)(Pc.x - org.x), py = (float)(Pc.y - org.y), fnx = (float)nx, fny = (float)ny;
+                const float m = m0 + 2e-6f * fmaxf(fabsf(px), fabsf(py));
+                unsigned hw = sHint[i];
+                unsigned short cw = sClr[i];
+                int j0 = (int)((hw >> hshift) & 0x1fffu);
+                if (j0 >= mr) j0 = 0;
+                const bool inside = parity_ok && closed && ((hw >> (26 + ring)) & 1u);
+                // displacement from the centre-line position the clearance refers to
+                const double cx0 = gcenter[2 * i], cy0 = gcenter[2 * i + 1];
+                const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
+                float Rc = 0.f;
+                if (pass == 0 && !first && ((hw >> (28 + ring)) & 1u)) {
+                    const unsigned cq = (cw >> (8 * ring)) & 0xffu;
+                    Rc = (cq == 255u ? 3e18f : 0.25f * (float)cq) - disp - 4.f * m;
                 }
-                const bool in = closed && inside_ring(tl, Pc, px, py, m);
-                hw = (hw & ~(1u << (28 + ring))) | ((in ? 1u : 0u) << (28 + ring));
+                double pos_r = INF, neg_r = INF;
+                int seg_p = -1, seg_n = -1;
+                bool ex_p, ex_n;          // does the +n / -n ray hit this ring at all
+                bool have_d = false;
+                double dist_r = INF;       // point-ring distance, computed on demand
+                bool general = !(Rc > 0.f);
+                if (!general) {
+                    // ---------------- certified window search ----------------
+                    window_rays(tl, Pc, nx, ny, px, py, fnx, fny, m, j0, pos_r, neg_r, seg_p, seg_n, ray_tests);
+                    const double Rcd = (double)Rc;
+                    // directions that need the general search: a hit that is not certified nearest, or no hit,
+                    // no parity and a common bound that does not make far hits irrelevant
+                    const bool open_p = (pos_r > Rcd) && ((pos_r < INF) || (!inside && !(bp[j] <= Rcd)));
+                    const bool open_n = (neg_r > Rcd) && ((neg_r < INF) || (!inside && !(bn[j] <= Rcd)));
+                    if (pos_r <= Rcd) bp[j] = fmin(bp[j], pos_r);
+                    if (neg_r <= Rcd) bn[j] = fmin(bn[j], neg_r);
+                    ex_p = (pos_r < INF); ex_n = (neg_r < INF);
+                    if (open_p || open_n) {
+                        const bool bounded_p = (bp[j] < INF) || (pos_r < INF), bounded_n = (bn[j] < INF) || (neg_r < INF);
+                        double bq = fmin(bp[j], pos_r), bm = fmin(bn[j], neg_r), pr2 = pos_r, nr2 = neg_r;
+                        ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, j0 / SB, open_p, open_n, false, bq, bm, pr2, nr2, ray_tests);
+                        if (open_p) { pos_r = pr2; bp[j] = fmin(bp[j], bq); ex_p = (pos_r < INF) || (bounded_p && inside); }
+                        if (open_n) { neg_r = nr2; bn[j] = fmin(bn[j], bm); ex_n = (neg_r < INF) || (bounded_n && inside); }
+                        const bool redo_p = open_p && !ex_p && bounded_p, redo_n = open_n && !ex_n && bounded_n;
+                        if (redo_p || redo_n) {   // pruned by a bound and no parity: look for any hit at all
+                            double ubp = INF, ubn = INF, pr = INF, nr = INF;
+                            if (redo_p) { ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, j0 / SB, true, false, true, ubp, ubn, pr, nr, ray_tests); ex_p = (pr < INF); }
+                            if (redo_n) { ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, j0 / SB, false, true, true, ubp, ubn, pr, nr, ray_tests); ex_n = (nr < INF); }
+                        }
+                    }
+                    // directions without a window hit that were not searched: the ring has no hit with t < Rc
+#pragma unroll
+                    for (int dir = 0; dir < 2; ++dir) {
+                        const bool open_d = dir ? open_n : open_p;
+                        const double hit = dir ? neg_r : pos_r;
+                        if (open_d || hit < INF) continue;
+                        double& bnd = dir ? bn[j] : bp[j];
+                        bool& ex = dir ? ex_n : ex_p;
+                        if (inside) {
+                            ex = true;                                   // parity: it hits, somewhere beyond Rc
+                            if (!(bnd <= Rcd)) { if (dir) lbn[j] = fminf(lbn[j], Rc); else lbp[j] = fminf(lbp[j], Rc); }
+                        } else {
+                            // far hits cannot lower the minimum (bnd <= Rc); whether one EXISTS only matters if the
+                            // point-ring distance would (main.cpp:696)
+                            if (!have_d) {
+                                dist_r = window_dist(tl, Pc, px, py, m, j0, fmin(pos_r, neg_r));
+                                if (!(dist_r <= Rcd)) dist_r = dist_scan(tl, Pc, px, py, m, j0 / SB, fmin(dist_r, fmin(pos_r, neg_r)));
+                                have_d = true;
+                            }
+                            if (dist_r >= bnd) ex = true;                // irrelevant either way: treat as settled
+                            else {
+                                double ubp = INF, ubn = INF, pr = INF, nr = INF;
+                                ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, j0 / SB, dir == 0, dir == 1, true, ubp, ubn, pr, nr, ray_tests);
+                                ex = dir ? (nr < INF) : (pr < INF);
+                            }
+                        }
+                    }
+                } else {
+                    // ---------------- general search (first build, failed certificate, redo pass) ----------------
+                    const bool bounded_p = (bp[j] < INF), bounded_n = (bn[j] < INF);
+                    const int hs = ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, j0 / SB, true, true, false, bp[j], bn[j], pos_r, neg_r, ray_tests);
+                    ex_p = (pos_r < INF) || (bounded_p && inside);
+                    ex_n = (neg_r < INF) || (bounded_n && inside);
+                    const bool redo_p = !ex_p && bounded_p, redo_n = !ex_n && bounded_n;
+                    if (redo_p || redo_n) {
+                        double ubp = INF, ubn = INF, pr = INF, nr = INF;
+                        if (redo_p) { ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, j0 / SB, true, false, true, ubp, ubn, pr, nr, ray_tests); ex_p = (pr < INF); }
+                        if (redo_n) { ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, j0 / SB, false, true, true, ubp, ubn, pr, nr, ray_tests); ex_n = (nr < INF); }
+                    }
+                    // refresh the state of this sample for this ring
+                    if (first) {
+                        const bool in = closed && inside_ring(tl, Pc, px, py, m);
+                        hw = (hw & ~(1u << (26 + ring))) | ((in ? 1u : 0u) << (26 + ring));
+                    }
+                    if (hs >= 0) {
+                        j0 = hs;
+                        const float c = clearance_scan(tl, px, py, m, j0) - disp;
+                        const unsigned cq = (c >= 63.75f) ? 255u : (c > 0.f ? (unsigned)(c * 4.f) : 0u);
+                        cw = (unsigned short)((cw & ~(0xffu << (8 * ring))) | (cq << (8 * ring)));
+                        hw = (hw & ~(0x1fffu << hshift)) | ((unsigned)j0 << hshift) | (1u << (28 + ring));
+                    } else {
+                        hw &= ~(1u << (28 + ring));
+                    }
+                    sHint[i] = hw; sClr[i] = cw;
+                }
+                // a ring some ray misses entirely: nearest point-segment distance (main.cpp:696)
+                if (!ex_p || !ex_n) {
+                    if (!have_d) dist_r = dist_scan(tl, Pc, px, py, m, j0 / SB, fmin(pos_r, neg_r));
+                    if (!ex_p) dfp[j] = fmin(dfp[j], dist_r);
+                    if (!ex_n) dfn[j] = fmin(dfn[j], dist_r);
+                }
             }
-            const bool inside = parity_ok && closed && ((hw >> (28 + ring)) & 1u);
-            double pos_r = INF, neg_r = INF;
-            const bool bounded_p = (bp[j] < INF), bounded_n = (bn[j] < INF);
-            int hb = ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, hint, true, true, false, bp[j], bn[j], pos_r, neg_r, ray_tests);
-            // does a hit exist at all?  found / known by parity / searched without a bound / must search again
-            bool ex_p = (pos_r < INF), ex_n = (neg_r < INF);
-            if (!ex_p && bounded_p) { if (inside) ex_p = true; }
-            if (!ex_n && bounded_n) { if (inside) ex_n = true; }
-            // (a bound that became finite DURING this scan came from this ring: then pos_r < INF)
-            const bool redo_p = !ex_p && bounded_p, redo_n = !ex_n && bounded_n;
-            if (redo_p || redo_n) {
-                double ubp = INF, ubn = INF, pr = INF, nr = INF;
-                if (redo_p) { ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, hint, true, false, true, ubp, ubn, pr, nr, ray_tests); ex_p = (pr < INF); }
-                if (redo_n) { ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, hint, false, true, true, ubp, ubn, pr, nr, ray_tests); ex_n = (nr < INF); }
+        }
+        if (pass == 0) {
+            // a pending "exists, value >= lb" that could undercut the minimum found: redo that sample in full
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                if (tid + j * T >= N) continue;
+                if ((double)lbp[j] < fmin(bp[j], dfp[j]) || (double)lbn[j] < fmin(bn[j], dfn[j])) flagged |= (1u << j);
             }
-            if (!ex_p || !ex_n) {
-                const double d = dist_scan(tl, Pc, px, py, m, (hb >= 0) ? hb : hint, fmin(pos_r, neg_r));
-                if (!ex_p) dfp[j] = fmin(dfp[j], d);
-                if (!ex_n) dfn[j] = fmin(dfn[j], d);
-            }
-            if (hb >= 0) hint = hb;
-            hw = (hw & ~(0x3fffu << hshift)) | ((unsigned)hint << hshift);
-            sHint[i] = hw;
         }
     }
     // hi/lo (main.cpp:704-710), handed to the blocked layout through region B
@@ -1099,6 +1314,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     double* sExL = reinterpret_cast<double*>(scr + kScrExL);
     int* sMisc = reinterpret_cast<int*>(scr + kScrMisc);
     unsigned* sHint = reinterpret_cast<unsigned*>(scr + kScrBytes);
+    unsigned short* sClr = reinterpret_cast<unsigned short*>(scr + kScrBytes + (size_t)NP * 4);
 
     if ((int)blockIdx.x >= n_list) return;
     const int jid = job_list[blockIdx.x];
@@ -1175,11 +1391,11 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     double lo[K], hi[K];
     // initial corridor from the centre line: guard uses the veh_width ARGUMENT (main.cpp:706 / 930)
     constexpr int CAPF = fast_tile_cap(NP);
-    const bool fast_rays = (segO0 - segI0 <= CAPF) && (segE - segO0 <= CAPF) && (CAPF / SB < 16384);
+    const bool fast_rays = (segO0 - segI0 <= CAPF) && (segE - segO0 <= CAPF) && (CAPF < 8192);
     const bool parity_ok = (C.veh_width_arg * 0.5 + C.safety_margin_m >= 0.0) && (C.veh_width_m * 0.5 + C.safety_margin_m >= 0.0);
-    for (int i = tid; i < NP; i += T) sHint[i] = 0u;
+    for (int i = tid; i < NP; i += T) { sHint[i] = 0u; sClr[i] = 0; }
     if (fast_rays)
-        corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, true, parity_ok, B.seg, segI0, segO0, segE,
+        corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, true, parity_ok, B.seg, B.center_xy + 2 * s0, segI0, segO0, segE,
                                   C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
     else
         corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,
@@ -1325,7 +1541,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
         block_sync<T>();
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
         if (fast_rays)
-            corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, false, parity_ok, B.seg, segI0, segO0, segE,
+            corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, B.seg, B.center_xy + 2 * s0, segI0, segO0, segE,
                                       C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
         else
             corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,

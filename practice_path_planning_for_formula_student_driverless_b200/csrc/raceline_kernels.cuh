@@ -779,10 +779,14 @@ __device__ __forceinline__ bool ray_box(const float4 bx, float px, float py, flo
 // scan one ring for one sample.  bp/bn: running nearest +n / -n hit over both rings (pruning bound);
 // pos_r/neg_r: nearest hit found on THIS ring (INF if none inside the bound).  hint: box to start at.
 // Returns the segment of the nearest hit (-1 if none).
-__device__ __noinline__ int ray_scan(const RayTile& tl, double2 P, double nx, double ny, float px, float py, float fnx, float fny,
+__device__ __noinline__ int ray_scan(const RayTile& tl_in, double2 P, double nx, double ny, float px, float py, float fnx, float fny,
                                         float m, int hint, bool wp, bool wn, bool first_hit_only,
-                                        double& bp, double& bn, double& pos_r, double& neg_r, long long& tests)
+                                        double& bp_io, double& bn_io, double& pos_io, double& neg_io, long long& tests_io)
 {
+    // a real function (one copy): keep the tile description and the in/out values in registers
+    const RayTile tl = tl_in;
+    double bp = bp_io, bn = bn_io, pos_r = pos_io, neg_r = neg_io;
+    int tests = 0;
     const double INF = dinf();
     const float anx = fabsf(fnx), any = fabsf(fny);
     float bpf = (bp < INF) ? __double2float_ru(bp) : __int_as_float(0x7f800000);
@@ -817,27 +821,30 @@ __device__ __noinline__ int ray_scan(const RayTile& tl, double2 P, double nx, do
                             pos_r = fmin(pos_r, t);
                             if (t < bp) { bp = t; bpf = __double2float_ru(t); }
                             if (t < best_abs) { best_abs = t; best_box = s; }
-                            if (first_hit_only) return best_box;
+                            if (first_hit_only) goto done;
                         }
                     } else if (t < 0.0) {                                       // -n ray: t' = -t
                         if (wn) {
                             neg_r = fmin(neg_r, -t);
                             if (-t < bn) { bn = -t; bnf = __double2float_ru(-t); }
                             if (-t < best_abs) { best_abs = -t; best_box = s; }
-                            if (first_hit_only) return best_box;
+                            if (first_hit_only) goto done;
                         }
                     }
                 }
             }
         }
     }
+done:
+    bp_io = bp; bn_io = bn; pos_io = pos_r; neg_io = neg_r; tests_io += tests;
     return best_box;
 }
 
 // nearest point-segment distance to the ring (minDistanceToSegments_global, main.cpp:501-512); ub: any known
 // upper bound (a hit point lies on the ring) or INF.
-__device__ __noinline__ double dist_scan(const RayTile& tl, double2 P, float px, float py, float m, int hint, double ub)
+__device__ __noinline__ double dist_scan(const RayTile& tl_in, double2 P, float px, float py, float m, int hint, double ub)
 {
+    const RayTile tl = tl_in;
     const double INF = dinf();
     double best2 = INF;
     float boundf = (ub < INF) ? __double2float_ru(ub) * (1.f + 1e-5f) + m : __int_as_float(0x7f800000);
@@ -885,8 +892,9 @@ __device__ __noinline__ double dist_scan(const RayTile& tl, double2 P, float px,
 }
 
 // parity of the crossings of the +x ray from P with a CLOSED chain (vertices shared bit for bit): P inside?
-__device__ __noinline__ bool inside_ring(const RayTile& tl, double2 P, float px, float py, float m)
+__device__ __noinline__ bool inside_ring(const RayTile& tl_in, double2 P, float px, float py, float m)
 {
+    const RayTile tl = tl_in;
     int cnt = 0;
     for (int sb = 0; sb < tl.nsup; ++sb) {
         const float4 sx = tl.supF[sb];
@@ -1074,8 +1082,9 @@ __device__ __forceinline__ double window_dist(const RayTile& tl, double2 P, floa
 }
 
 // conservative (rounded down) distance from p to every segment of the ring outside the window of j0
-__device__ __noinline__ float clearance_scan(const RayTile& tl, float px, float py, float m, int j0)
+__device__ __noinline__ float clearance_scan(const RayTile& tl_in, float px, float py, float m, int j0)
 {
+    const RayTile tl = tl_in;
     const int M = tl.nt;
     if (M <= 2 * kWin + 1) return 3e18f;
     float best = 3e18f;   // distance, not squared

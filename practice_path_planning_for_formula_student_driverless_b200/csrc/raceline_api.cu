@@ -14,12 +14,17 @@
 
 using rl::DevBatch;
 
+constexpr int kMaxChunks = 8;
+
 struct rl_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;   // own_stream or the caller's
     std::string err;
     rl_batch* scratch = nullptr;     // reused by rl_solve_batch and the single-problem entry points
+    // pipeline of rl_solve_batch: H2D | kernels (two streams, so consecutive chunks overlap their tails) | D2H
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_k[2] = {nullptr, nullptr};
+    cudaEvent_t ev_start = nullptr, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_end[4] = {};
 };
 
 namespace {
@@ -41,7 +46,7 @@ struct DevArr {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct ClassList { int cls; bool exact; int begin; int count; };
+struct ClassList { int cls; bool exact; int begin; int count; int chunk; };
 
 }  // namespace
 
@@ -63,6 +68,9 @@ struct rl_batch {
     std::vector<int> joblist;
     std::vector<ClassList> lists;
     std::vector<std::pair<int, int>> skipped;   // (job, status) for jobs no kernel covers
+    int n_chunks = 1;
+    std::vector<int> chunk_job0;                // [n_chunks+1] job ranges of the chunks
+    std::vector<int> chunk_tmax;                // [n_chunks] highest track index a chunk touches
     void release()
     {
         d_samp_off.release(); d_seg_off.release(); d_job_off.release(); d_center.release(); d_seg.release();
@@ -116,7 +124,7 @@ int validate_desc(rl_ctx* c, const rl_batch_desc* d)
 }
 
 // size the buffers, classify the jobs, upload the (small) plan arrays
-int plan_batch(rl_batch* b, const rl_batch_desc* d)
+int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
 {
     rl_ctx* c = b->ctx;
     b->n_tracks = d->n_tracks; b->n_params = d->n_params; b->n_jobs = d->n_jobs;
@@ -129,26 +137,34 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d)
     }
     b->rows = b->job_off[d->n_jobs];
 
-    // job lists per (class, exact); min-time jobs first (they run longer: better tail)
+    // job lists per chunk and (class, exact); min-time jobs first (they run longer: better tail)
     b->lists.clear(); b->joblist.clear(); b->skipped.clear();
-    std::vector<std::vector<int>> bucket(rl::kNumClasses * 2);
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < d->n_jobs; ++j) {
-            const rl_job& jb = d->jobs[j];
-            if ((pass == 0) != (jb.stage == RL_STAGE_MINTIME)) continue;
-            const int t = jb.track;
-            const long long n = d->samp_off[t + 1] - d->samp_off[t];
-            if (n == 0) { b->skipped.push_back({j, RL_OK}); continue; }   // empty Result, main.cpp:689 / 912
-            const int cls = rl::class_for_n((int)n);
-            if (cls < 0 || !d->track_closed[t]) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
-            const bool exact = (n == (long long)rl::kClasses[cls].T * rl::kClasses[cls].K);
-            bucket[cls * 2 + (exact ? 1 : 0)].push_back(j);
+    n_chunks = std::max(1, std::min(n_chunks, std::min(kMaxChunks, d->n_jobs)));
+    b->n_chunks = n_chunks;
+    b->chunk_job0.assign((size_t)n_chunks + 1, 0);
+    b->chunk_tmax.assign((size_t)n_chunks, -1);
+    for (int c = 0; c <= n_chunks; ++c) b->chunk_job0[c] = (int)(((long long)d->n_jobs * c) / n_chunks);
+    for (int c = 0; c < n_chunks; ++c) {
+        std::vector<std::vector<int>> bucket(rl::kNumClasses * 2);
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int j = b->chunk_job0[c]; j < b->chunk_job0[c + 1]; ++j) {
+                const rl_job& jb = d->jobs[j];
+                if ((pass == 0) != (jb.stage == RL_STAGE_MINTIME)) continue;
+                const int t = jb.track;
+                b->chunk_tmax[c] = std::max(b->chunk_tmax[c], t);
+                const long long n = d->samp_off[t + 1] - d->samp_off[t];
+                if (n == 0) { b->skipped.push_back({j, RL_OK}); continue; }   // empty Result, main.cpp:689 / 912
+                const int cls = rl::class_for_n((int)n);
+                if (cls < 0 || !d->track_closed[t]) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
+                const bool exact = (n == (long long)rl::kClasses[cls].T * rl::kClasses[cls].K);
+                bucket[cls * 2 + (exact ? 1 : 0)].push_back(j);
+            }
         }
-    }
-    for (int k = 0; k < rl::kNumClasses * 2; ++k) {
-        if (bucket[k].empty()) continue;
-        b->lists.push_back({k / 2, (k & 1) != 0, (int)b->joblist.size(), (int)bucket[k].size()});
-        b->joblist.insert(b->joblist.end(), bucket[k].begin(), bucket[k].end());
+        for (int k = 0; k < rl::kNumClasses * 2; ++k) {
+            if (bucket[k].empty()) continue;
+            b->lists.push_back({k / 2, (k & 1) != 0, (int)b->joblist.size(), (int)bucket[k].size(), c});
+            b->joblist.insert(b->joblist.end(), bucket[k].begin(), bucket[k].end());
+        }
     }
 
     RL_CUDA(c, b->d_samp_off.ensure((size_t)d->n_tracks + 1));
@@ -293,6 +309,12 @@ void rl_destroy(rl_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->scratch) { rl_batch_destroy(c->scratch); c->scratch = nullptr; }
+    if (c->s_in) {
+        cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out); cudaStreamDestroy(c->s_k[0]); cudaStreamDestroy(c->s_k[1]);
+        cudaEventDestroy(c->ev_start);
+        for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_k[i]); }
+        for (int i = 0; i < 4; ++i) cudaEventDestroy(c->ev_end[i]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -406,6 +428,24 @@ void rl_batch_destroy(rl_batch* b)
     delete b;
 }
 
+static int ensure_pipeline(rl_ctx* c)
+{
+    if (c->s_in) return RL_OK;
+    RL_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    RL_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) RL_CUDA(c, cudaStreamCreateWithFlags(&c->s_k[i], cudaStreamNonBlocking));
+    RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxChunks; ++i) {
+        RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 4; ++i) RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_end[i], cudaEventDisableTiming));
+    return RL_OK;
+}
+
+// Host buffers in, host buffers out.  The batch is cut into up to kMaxChunks job ranges; chunk k's inputs go up
+// on one stream while chunk k-1 computes and chunk k-2's results come down, all bracketed by the context's
+// stream (so events the caller records on it time the whole call).
 int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
 {
     if (!c || !o) return RL_ERR_ARG;
@@ -419,11 +459,71 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
         c->scratch->ctx = c;
     }
     rl_batch* b = c->scratch;
-    st = plan_batch(b, d);
-    if (st == RL_OK) st = upload_inputs(b, d);
-    if (st == RL_OK) st = rl_batch_solve(b);
-    if (st == RL_OK) st = rl_batch_download(b, o);
-    if (st == RL_OK) st = rl_batch_sync(b);
+    st = ensure_pipeline(c);
+    if (st != RL_OK) return st;
+    const int want_chunks = std::max(1, std::min(kMaxChunks, d->n_jobs / 1024));
+    // the small plan arrays travel on the context stream before the pipeline starts
+    st = plan_batch(b, d, want_chunks);
+    if (st != RL_OK) return st;
+    cudaStream_t s0 = c->stream;
+    RL_CUDA(c, cudaMemcpyAsync(b->d_samp_off.p, d->samp_off, sizeof(long long) * ((size_t)d->n_tracks + 1), cudaMemcpyHostToDevice, s0));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_seg_off.p, d->seg_off, sizeof(long long) * ((size_t)2 * d->n_tracks + 1), cudaMemcpyHostToDevice, s0));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_L.p, d->track_L, sizeof(double) * (size_t)d->n_tracks, cudaMemcpyHostToDevice, s0));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_closed.p, d->track_closed, sizeof(int) * (size_t)d->n_tracks, cudaMemcpyHostToDevice, s0));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_params.p, d->params, sizeof(rl_params) * (size_t)d->n_params, cudaMemcpyHostToDevice, s0));
+    RL_CUDA(c, cudaMemcpyAsync(b->d_jobs.p, d->jobs, sizeof(rl_job) * (size_t)d->n_jobs, cudaMemcpyHostToDevice, s0));
+    RL_CUDA(c, cudaEventRecord(c->ev_start, s0));
+    RL_CUDA(c, cudaStreamWaitEvent(c->s_in, c->ev_start, 0));
+    RL_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_start, 0));
+    for (int i = 0; i < 2; ++i) RL_CUDA(c, cudaStreamWaitEvent(c->s_k[i], c->ev_start, 0));
+
+    const DevBatch B = dev_view(b);
+    int up_t = 0;   // tracks [0, up_t) are already queued for upload
+    size_t li = 0;
+    for (int k = 0; k < b->n_chunks; ++k) {
+        // ---- inputs of the tracks this chunk is the first to touch ----
+        const int t1 = b->chunk_tmax[k] + 1;
+        if (t1 > up_t) {
+            const long long a0 = d->samp_off[up_t], a1 = d->samp_off[t1], g0 = d->seg_off[2 * up_t], g1 = d->seg_off[2 * t1];
+            if (a1 > a0)
+                RL_CUDA(c, cudaMemcpyAsync(b->d_center.p + 2 * a0, d->center_xy + 2 * a0, sizeof(double) * 2 * (size_t)(a1 - a0), cudaMemcpyHostToDevice, c->s_in));
+            if (g1 > g0)
+                RL_CUDA(c, cudaMemcpyAsync(b->d_seg.p + 4 * g0, d->seg + 4 * g0, sizeof(double) * 4 * (size_t)(g1 - g0), cudaMemcpyHostToDevice, c->s_in));
+            up_t = t1;
+        }
+        RL_CUDA(c, cudaEventRecord(c->ev_in[k], c->s_in));
+        // ---- kernels ----
+        cudaStream_t sk = c->s_k[k & 1];
+        RL_CUDA(c, cudaStreamWaitEvent(sk, c->ev_in[k], 0));
+        for (; li < b->lists.size() && b->lists[li].chunk == k; ++li) {
+            const ClassList& l = b->lists[li];
+            const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, l.cls, l.exact, sk);
+            if (e != 0) return cuda_fail(c, (cudaError_t)e, "solve_kernel launch");
+        }
+        RL_CUDA(c, cudaEventRecord(c->ev_k[k], sk));
+        // ---- results of this chunk's rows ----
+        RL_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
+        const int j0 = b->chunk_job0[k], j1 = b->chunk_job0[k + 1];
+        const size_t r0 = (size_t)b->job_off[j0], nr = (size_t)(b->job_off[j1] - b->job_off[j0]);
+        if (nr) {
+            if (o->xy) RL_CUDA(c, cudaMemcpyAsync(o->xy + 2 * r0, b->d_xy.p + 2 * r0, 16 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->heading) RL_CUDA(c, cudaMemcpyAsync(o->heading + r0, b->d_heading.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->curvature) RL_CUDA(c, cudaMemcpyAsync(o->curvature + r0, b->d_curv.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->alpha_total) RL_CUDA(c, cudaMemcpyAsync(o->alpha_total + r0, b->d_atot.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->alpha_last) RL_CUDA(c, cudaMemcpyAsync(o->alpha_last + r0, b->d_alast.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->v) RL_CUDA(c, cudaMemcpyAsync(o->v + r0, b->d_v.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->ax) RL_CUDA(c, cudaMemcpyAsync(o->ax + r0, b->d_ax.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+        }
+        if (o->stats && j1 > j0)
+            RL_CUDA(c, cudaMemcpyAsync(o->stats + j0, b->d_stats.p + j0, sizeof(rl_job_stats) * (size_t)(j1 - j0), cudaMemcpyDeviceToHost, c->s_out));
+    }
+    // join everything back into the context stream
+    cudaStream_t tails[4] = {c->s_in, c->s_k[0], c->s_k[1], c->s_out};
+    for (int i = 0; i < 4; ++i) {
+        RL_CUDA(c, cudaEventRecord(c->ev_end[i], tails[i]));
+        RL_CUDA(c, cudaStreamWaitEvent(s0, c->ev_end[i], 0));
+    }
+    st = rl_batch_sync(b);
     if (st != RL_OK) return st;
     for (auto& sk : b->skipped)
         if (sk.second != RL_OK) return fail(c, sk.second, "a job's shape is not covered by the kernels (open track or N too large)");

@@ -277,3 +277,32 @@ def test_dropin_binary_matches_reference_binary(tmp_path, goldens):
     # the stages the drop-in does not touch are byte-identical
     for name in ("centerline.csv", "centerline_with_geom.csv", "centerline_inner_from_mids.csv"):
         assert open(outs["ref"][0] / name).read() == open(outs["b200"][0] / name).read()
+
+
+def test_pipelined_host_path_matches_resident_path(ctx):
+    """rl_solve_batch cuts large batches into chunks (H2D | kernels | D2H overlap); same bits as one resident solve."""
+    nt, n = 1300, 64
+    center, seg, L, m = rl.synth_tracks(nt, n, seed_base=77)
+    samp_off = np.arange(nt + 1, dtype=np.int64) * n
+    seg_off = np.arange(2 * nt + 1, dtype=np.int64) * m
+    jobs = [(t, 0, st) for t in range(nt) for st in (MC, MT)]                 # 2600 jobs -> 2 chunks
+    cfg = rl.Config()
+    pb = rl.PackedBatch.from_arrays(samp_off, seg_off, center, seg, L, np.ones(nt, np.int32), [cfg.to_params()], jobs)
+    ctx.solve_batch(pb)
+    got = {k: getattr(pb, "out_" + k).copy() for k in ("xy", "heading", "curvature", "alpha_total", "alpha_last", "v", "ax")}
+    laps = np.array([pb.out_stats[j].lap_time for j in range(pb.n_jobs)])
+    acc = np.array([pb.out_stats[j].accepted for j in range(pb.n_jobs)])
+    dev = rl.DeviceBatch(ctx, pb)
+    dev.solve(); dev.download(); dev.sync()
+    for k, v in got.items():
+        ref = getattr(pb, "out_" + k)
+        mask = np.ones(len(ref), bool)
+        if k in ("v", "ax"):                       # rows of min-curv jobs are left untouched
+            mask = np.repeat(np.array([j[2] == MT for j in jobs]), n)
+        assert np.array_equal(v[mask], ref[mask]), k
+    assert np.array_equal(laps, [pb.out_stats[j].lap_time for j in range(pb.n_jobs)])
+    assert np.array_equal(acc, [pb.out_stats[j].accepted for j in range(pb.n_jobs)])
+    dev.close()
+    tr = rl.Track(center.reshape(nt, n, 2)[1299], seg.reshape(nt, 2, m, 4)[1299, 0], seg.reshape(nt, 2, m, 4)[1299, 1], L[1299])
+    o = oracle_ref(MT, tr, cfg.to_params())
+    assert_result_close(pb.result(2 * 1299 + 1), o, "o_", True, tag="last job of the last chunk")

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -14,7 +15,7 @@
 
 using rl::DevBatch;
 
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 4;
 
 struct rl_ctx {
     int device = 0;
@@ -22,9 +23,16 @@ struct rl_ctx {
     cudaStream_t stream = nullptr;   // own_stream or the caller's
     std::string err;
     rl_batch* scratch = nullptr;     // reused by rl_solve_batch and the single-problem entry points
-    // pipeline of rl_solve_batch: H2D | kernels (two streams, so consecutive chunks overlap their tails) | D2H
-    cudaStream_t s_in = nullptr, s_out = nullptr, s_k[2] = {nullptr, nullptr};
-    cudaEvent_t ev_start = nullptr, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_end[4] = {};
+    // pipeline of rl_solve_batch: H2D | kernels | D2H.  One compute stream per chunk, with DESCENDING priority:
+    // chunk k+1 fills the SMs chunk k's tail leaves idle, but never delays chunk k (whose results can then go
+    // down while chunk k+1 still computes).  Equal priorities would share the SMs and finish all chunks last.
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_k[kMaxChunks] = {};
+    int n_prio = 1;
+    // a D2H copy into PAGEABLE memory blocks the host until it has run, which would serialise the whole pipeline;
+    // the per-job stats therefore land in this pinned staging area first
+    rl_job_stats* h_stats = nullptr;
+    size_t h_stats_cap = 0;
+    cudaEvent_t ev_start = nullptr, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_end[kMaxChunks + 2] = {};
 };
 
 namespace {
@@ -310,11 +318,12 @@ void rl_destroy(rl_ctx* c)
     cudaSetDevice(c->device);
     if (c->scratch) { rl_batch_destroy(c->scratch); c->scratch = nullptr; }
     if (c->s_in) {
-        cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out); cudaStreamDestroy(c->s_k[0]); cudaStreamDestroy(c->s_k[1]);
+        cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
         cudaEventDestroy(c->ev_start);
-        for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_k[i]); }
-        for (int i = 0; i < 4; ++i) cudaEventDestroy(c->ev_end[i]);
+        for (int i = 0; i < kMaxChunks; ++i) { cudaStreamDestroy(c->s_k[i]); cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_k[i]); }
+        for (int i = 0; i < kMaxChunks + 2; ++i) cudaEventDestroy(c->ev_end[i]);
     }
+    if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -433,19 +442,23 @@ static int ensure_pipeline(rl_ctx* c)
     if (c->s_in) return RL_OK;
     RL_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     RL_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) RL_CUDA(c, cudaStreamCreateWithFlags(&c->s_k[i], cudaStreamNonBlocking));
+    int lo_p = 0, hi_p = 0;   // numerically lowest value = highest priority
+    RL_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    c->n_prio = std::max(1, std::min(kMaxChunks, lo_p - hi_p + 1));
+    for (int i = 0; i < kMaxChunks; ++i)
+        RL_CUDA(c, cudaStreamCreateWithPriority(&c->s_k[i], cudaStreamNonBlocking, std::min(lo_p, hi_p + i)));
     RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
     for (int i = 0; i < kMaxChunks; ++i) {
         RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
     }
-    for (int i = 0; i < 4; ++i) RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_end[i], cudaEventDisableTiming));
+    for (int i = 0; i < kMaxChunks + 2; ++i) RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_end[i], cudaEventDisableTiming));
     return RL_OK;
 }
 
 // Host buffers in, host buffers out.  The batch is cut into up to kMaxChunks job ranges; chunk k's inputs go up
-// on one stream while chunk k-1 computes and chunk k-2's results come down, all bracketed by the context's
-// stream (so events the caller records on it time the whole call).
+// while chunk k-1 computes and chunk k-2's results come down, all bracketed by the context's stream (so events
+// the caller records on it time the whole call).
 int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
 {
     if (!c || !o) return RL_ERR_ARG;
@@ -461,7 +474,8 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
     rl_batch* b = c->scratch;
     st = ensure_pipeline(c);
     if (st != RL_OK) return st;
-    const int want_chunks = std::max(1, std::min(kMaxChunks, d->n_jobs / 1024));
+    int want_chunks = std::max(1, std::min(c->n_prio, d->n_jobs / 1024));
+    if (const char* e = std::getenv("RL_SOLVE_CHUNKS")) want_chunks = std::max(1, std::min(kMaxChunks, std::atoi(e)));   // tuning knob
     // the small plan arrays travel on the context stream before the pipeline starts
     st = plan_batch(b, d, want_chunks);
     if (st != RL_OK) return st;
@@ -475,8 +489,15 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
     RL_CUDA(c, cudaEventRecord(c->ev_start, s0));
     RL_CUDA(c, cudaStreamWaitEvent(c->s_in, c->ev_start, 0));
     RL_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_start, 0));
-    for (int i = 0; i < 2; ++i) RL_CUDA(c, cudaStreamWaitEvent(c->s_k[i], c->ev_start, 0));
+    for (int i = 0; i < kMaxChunks; ++i) RL_CUDA(c, cudaStreamWaitEvent(c->s_k[i], c->ev_start, 0));
 
+    if (o->stats && (size_t)d->n_jobs > c->h_stats_cap) {
+        if (c->h_stats) cudaFreeHost(c->h_stats);
+        c->h_stats = nullptr; c->h_stats_cap = 0;
+        const size_t want = (size_t)d->n_jobs + (size_t)d->n_jobs / 8 + 16;
+        RL_CUDA(c, cudaHostAlloc((void**)&c->h_stats, want * sizeof(rl_job_stats), cudaHostAllocDefault));
+        c->h_stats_cap = want;
+    }
     const DevBatch B = dev_view(b);
     int up_t = 0;   // tracks [0, up_t) are already queued for upload
     size_t li = 0;
@@ -493,7 +514,7 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
         }
         RL_CUDA(c, cudaEventRecord(c->ev_in[k], c->s_in));
         // ---- kernels ----
-        cudaStream_t sk = c->s_k[k & 1];
+        cudaStream_t sk = c->s_k[k];
         RL_CUDA(c, cudaStreamWaitEvent(sk, c->ev_in[k], 0));
         for (; li < b->lists.size() && b->lists[li].chunk == k; ++li) {
             const ClassList& l = b->lists[li];
@@ -515,16 +536,17 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
             if (o->ax) RL_CUDA(c, cudaMemcpyAsync(o->ax + r0, b->d_ax.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
         }
         if (o->stats && j1 > j0)
-            RL_CUDA(c, cudaMemcpyAsync(o->stats + j0, b->d_stats.p + j0, sizeof(rl_job_stats) * (size_t)(j1 - j0), cudaMemcpyDeviceToHost, c->s_out));
+            RL_CUDA(c, cudaMemcpyAsync(c->h_stats + j0, b->d_stats.p + j0, sizeof(rl_job_stats) * (size_t)(j1 - j0), cudaMemcpyDeviceToHost, c->s_out));
     }
     // join everything back into the context stream
-    cudaStream_t tails[4] = {c->s_in, c->s_k[0], c->s_k[1], c->s_out};
-    for (int i = 0; i < 4; ++i) {
-        RL_CUDA(c, cudaEventRecord(c->ev_end[i], tails[i]));
+    for (int i = 0; i < kMaxChunks + 2; ++i) {
+        cudaStream_t tail = (i < kMaxChunks) ? c->s_k[i] : (i == kMaxChunks ? c->s_in : c->s_out);
+        RL_CUDA(c, cudaEventRecord(c->ev_end[i], tail));
         RL_CUDA(c, cudaStreamWaitEvent(s0, c->ev_end[i], 0));
     }
     st = rl_batch_sync(b);
     if (st != RL_OK) return st;
+    if (o->stats) std::memcpy(o->stats, c->h_stats, sizeof(rl_job_stats) * (size_t)d->n_jobs);
     for (auto& sk : b->skipped)
         if (sk.second != RL_OK) return fail(c, sk.second, "a job's shape is not covered by the kernels (open track or N too large)");
     return RL_OK;

@@ -54,7 +54,7 @@ struct DevArr {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct ClassList { int cls; bool exact; int begin; int count; int chunk; };
+struct ClassList { int cls; int mode; int begin; int count; int chunk; };
 
 }  // namespace
 
@@ -153,7 +153,7 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
     b->chunk_tmax.assign((size_t)n_chunks, -1);
     for (int c = 0; c <= n_chunks; ++c) b->chunk_job0[c] = (int)(((long long)d->n_jobs * c) / n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
-        std::vector<std::vector<int>> bucket(rl::kNumClasses * 2);
+        std::vector<std::vector<int>> bucket(rl::kNumClasses * 3);
         for (int pass = 0; pass < 2; ++pass) {
             for (int j = b->chunk_job0[c]; j < b->chunk_job0[c + 1]; ++j) {
                 const rl_job& jb = d->jobs[j];
@@ -163,14 +163,15 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
                 const long long n = d->samp_off[t + 1] - d->samp_off[t];
                 if (n == 0) { b->skipped.push_back({j, RL_OK}); continue; }   // empty Result, main.cpp:689 / 912
                 const int cls = rl::class_for_n((int)n);
-                if (cls < 0 || !d->track_closed[t]) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
+                if (cls < 0) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
                 const bool exact = (n == (long long)rl::kClasses[cls].T * rl::kClasses[cls].K);
-                bucket[cls * 2 + (exact ? 1 : 0)].push_back(j);
+                const int mode = !d->track_closed[t] ? 2 : (exact ? 1 : 0);   // open | closed exact-fit | closed ragged
+                bucket[cls * 3 + mode].push_back(j);
             }
         }
-        for (int k = 0; k < rl::kNumClasses * 2; ++k) {
+        for (int k = 0; k < rl::kNumClasses * 3; ++k) {
             if (bucket[k].empty()) continue;
-            b->lists.push_back({k / 2, (k & 1) != 0, (int)b->joblist.size(), (int)bucket[k].size(), c});
+            b->lists.push_back({k / 3, k % 3, (int)b->joblist.size(), (int)bucket[k].size(), c});
             b->joblist.insert(b->joblist.end(), bucket[k].begin(), bucket[k].end());
         }
     }
@@ -391,7 +392,7 @@ int rl_batch_solve(rl_batch* b)
     cudaSetDevice(c->device);
     const DevBatch B = dev_view(b);
     for (const ClassList& l : b->lists) {
-        const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, l.cls, l.exact, c->stream);
+        const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, l.cls, l.mode, c->stream);
         if (e != 0) return cuda_fail(c, (cudaError_t)e, "solve_kernel launch");
     }
     return RL_OK;
@@ -518,7 +519,7 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
         RL_CUDA(c, cudaStreamWaitEvent(sk, c->ev_in[k], 0));
         for (; li < b->lists.size() && b->lists[li].chunk == k; ++li) {
             const ClassList& l = b->lists[li];
-            const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, l.cls, l.exact, sk);
+            const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, l.cls, l.mode, sk);
             if (e != 0) return cuda_fail(c, (cudaError_t)e, "solve_kernel launch");
         }
         RL_CUDA(c, cudaEventRecord(c->ev_k[k], sk));
@@ -548,7 +549,7 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
     if (st != RL_OK) return st;
     if (o->stats) std::memcpy(o->stats, c->h_stats, sizeof(rl_job_stats) * (size_t)d->n_jobs);
     for (auto& sk : b->skipped)
-        if (sk.second != RL_OK) return fail(c, sk.second, "a job's shape is not covered by the kernels (open track or N too large)");
+        if (sk.second != RL_OK) return fail(c, sk.second, "a job's shape is not covered by the kernels (N too large)");
     return RL_OK;
 }
 

@@ -55,9 +55,9 @@ inline size_t smem_bytes_for_class(int T, int K)
            + np * 6;    /* per-sample corridor state: anchor segments + parity bits (4 B), clearances (2 B) */
 }
 
-// launches job_list[0..n_list) (indices into B.jobs) with the kernel of class `cls`
-// (exact = every job in the list has N == T*K).  Returns a cudaError_t as int.
-int launch_solve(const DevBatch& B, const int* job_list, int n_list, int cls, bool exact, void* stream);
+// launches job_list[0..n_list) (indices into B.jobs) with the kernel of class `cls` and mode
+// 0 = closed track, 1 = closed track and every job has N == T*K, 2 = open track.  Returns a cudaError_t as int.
+int launch_solve(const DevBatch& B, const int* job_list, int n_list, int cls, int mode, void* stream);
 int configure_kernels();  // sets max dynamic shared memory on every instantiation
 int launch_fp64_peak(double* d_out, int blocks, int threads, int iters, void* stream);
 

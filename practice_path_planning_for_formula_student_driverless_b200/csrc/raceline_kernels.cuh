@@ -136,25 +136,45 @@ struct Part {
 };
 
 // ---- per-sample geometry ---------------------------------------------------------------------------
-// normals_from_points_generic (closed branch), main.cpp:581-593
-__device__ __forceinline__ void normal_closed(double2 Pm, double2 Pp, int N, double& nx, double& ny)
+// kernel modes: 0 = closed track, ragged N; 1 = closed track, N == T*K exactly; 2 = open track (ragged)
+constexpr int kModeClosed = 0, kModeExact = 1, kModeOpen = 2;
+
+// normals_from_points_generic, main.cpp:581-593 (closed: periodic central difference; open: one-sided ends)
+__device__ __forceinline__ void normal_at(const double2* sP, int i, int N, bool closed, double& nx, double& ny)
 {
-    double tx = (Pp.x - Pm.x) * 0.5, ty = (Pp.y - Pm.y) * 0.5;
+    double tx, ty;
     if (N == 1) { tx = 1.0; ty = 0.0; }
+    else if (closed) {
+        const double2 Pm = sP[(i == 0) ? N - 1 : i - 1], Pp = sP[(i == N - 1) ? 0 : i + 1];
+        tx = (Pp.x - Pm.x) * 0.5; ty = (Pp.y - Pm.y) * 0.5;
+    } else if (i == 0) { tx = sP[1].x - sP[0].x; ty = sP[1].y - sP[0].y; }
+    else if (i == N - 1) { tx = sP[N - 1].x - sP[N - 2].x; ty = sP[N - 1].y - sP[N - 2].y; }
+    else { tx = (sP[i + 1].x - sP[i - 1].x) * 0.5; ty = (sP[i + 1].y - sP[i - 1].y) * 0.5; }
     if (sqrt(tx * tx + ty * ty) < 1e-15) { tx = 1.0; ty = 0.0; }
     const double nvx = -ty, nvy = tx;
     const double len = sqrt(nvx * nvx + nvy * nvy);
     if (len < 1e-15) { nx = 0.0; ny = 0.0; }
     else { nx = nvx / len; ny = nvy / len; }
 }
-// the `deriv` lambda (closed branch), main.cpp:599-603 / 625-629
-__device__ __forceinline__ void derivs_closed(double2 Pm, double2 Pc, double2 Pp, double h, int N,
-                                              double& xp, double& yp, double& xpp, double& ypp)
+// the `deriv` lambda, main.cpp:599-613 / 625-639
+__device__ __forceinline__ void derivs_at(const double2* sP, int i, int N, double h, bool closed,
+                                          double& xp, double& yp, double& xpp, double& ypp)
 {
     if (N == 1) { xp = 1.0; yp = 0.0; xpp = 0.0; ypp = 0.0; return; }
     const double h2 = 2 * h, hh = h * h;
-    xp = (Pp.x - Pm.x) / h2; yp = (Pp.y - Pm.y) / h2;
-    xpp = (Pp.x - 2 * Pc.x + Pm.x) / hh; ypp = (Pp.y - 2 * Pc.y + Pm.y) / hh;
+    if (closed || (i > 0 && i < N - 1)) {
+        const double2 Pm = sP[(i == 0) ? N - 1 : i - 1], Pc = sP[i], Pp = sP[(i == N - 1) ? 0 : i + 1];
+        xp = (Pp.x - Pm.x) / h2; yp = (Pp.y - Pm.y) / h2;
+        xpp = (Pp.x - 2 * Pc.x + Pm.x) / hh; ypp = (Pp.y - 2 * Pc.y + Pm.y) / hh;
+    } else if (i == 0) {
+        xp = (sP[1].x - sP[0].x) / h; yp = (sP[1].y - sP[0].y) / h;
+        if (N >= 3) { xpp = (sP[2].x - 2 * sP[1].x + sP[0].x) / hh; ypp = (sP[2].y - 2 * sP[1].y + sP[0].y) / hh; }
+        else { xpp = 0.0; ypp = 0.0; }
+    } else {
+        xp = (sP[N - 1].x - sP[N - 2].x) / h; yp = (sP[N - 1].y - sP[N - 2].y) / h;
+        if (N >= 3) { xpp = (sP[N - 1].x - 2 * sP[N - 2].x + sP[N - 3].x) / hh; ypp = (sP[N - 1].y - 2 * sP[N - 2].y + sP[N - 3].y) / hh; }
+        else { xpp = 0.0; ypp = 0.0; }
+    }
 }
 // pow(max(1e-12, q), 1.5), main.cpp:617 / 647
 __device__ __forceinline__ double pow15(double q)
@@ -162,8 +182,6 @@ __device__ __forceinline__ double pow15(double q)
     const double s = fmax(1e-12, q);
     return s * sqrt(s);
 }
-__device__ __forceinline__ double2 sp_prev(const double2* sP, int i, int N) { return sP[(i == 0) ? N - 1 : i - 1]; }
-__device__ __forceinline__ double2 sp_next(const double2* sP, int i, int N) { return sP[(i == N - 1) ? 0 : i + 1]; }
 
 // ---- v(s) profile pieces: the ax_max_at lambda, main.cpp:797-824 -----------------------------------
 struct VPar {
@@ -203,7 +221,7 @@ __device__ __forceinline__ double f_brk(const VPar& q, double vi, double ki)
 // sX: 6*T doubles of exchange space.  Returns v[] (blocked); *rounds += relaxation rounds.
 template <int T, int K>
 __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, const double (&kap)[K], double (&v)[K],
-                                                 int max_iters, double* sX, int& rounds)
+                                                 int max_iters, double* sX, int& rounds, bool closed)
 {
     double* sVL = sX;           // [2][T] last-slot value of each thread
     double* sVF = sX + 2 * T;   // [2][T] first-slot value
@@ -259,7 +277,7 @@ __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, 
             if (!block_or<T>(changed)) break;
         }
         // closed-loop wrap: v[0] = min(v[0], f_acc(v[N-1])), main.cpp:834-839
-        if (tid == 0) v[0] = fmin(v[0], f_acc(q, sVL[b * T + pt.tL], kapL));
+        if (closed && tid == 0) v[0] = fmin(v[0], f_acc(q, sVL[b * T + pt.tL], kapL));
         // ---------------- backward sweep (main.cpp:841-845) ----------------
 #pragma unroll
         for (int k = 0; k < K; ++k) v0[k] = v[k];
@@ -285,7 +303,7 @@ __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, 
             if (!block_or<T>(changed)) break;
         }
         // closed-loop wrap: v[N-1] = min(v[N-1], f_brk(v[0])), main.cpp:846-850
-        if (tid == pt.Tact - 1) {
+        if (closed && tid == pt.Tact - 1) {
             const double w = f_brk(q, sVF[b * T + pt.tR], kapR);
 #pragma unroll
             for (int k = 0; k < K; ++k) if (k == cnt - 1) v[k] = fmin(v[k], w);
@@ -299,7 +317,7 @@ __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, 
 // ax and lap time, main.cpp:854-860.  Returns the block-wide lap time; ax[] per owned slot.
 template <int T, int K>
 __device__ __forceinline__ double lap_and_ax(const Part& pt, const VPar& q, const double (&v)[K], double (&ax)[K],
-                                             double* sX, double* sred)
+                                             double* sX, double* sred, bool closed)
 {
     double* sVF = sX;
     sVF[pt.tid] = v[0];
@@ -310,9 +328,9 @@ __device__ __forceinline__ double lap_and_ax(const Part& pt, const VPar& q, cons
     for (int k = 0; k < K; ++k) {
         ax[k] = 0.0;
         if (k < pt.cnt) {
-            double v1 = vnext_edge;
-            if (k + 1 < K) { if (k + 1 < pt.cnt) v1 = v[k + 1]; }
             const double v0 = v[k];
+            double v1 = (!closed && pt.tid == pt.Tact - 1) ? v0 : vnext_edge;   // open: j = i at the last sample (main.cpp:856)
+            if (k + 1 < K) { if (k + 1 < pt.cnt) v1 = v[k + 1]; }
             ax[k] = (v1 * v1 - v0 * v0) / (2.0 * q.h);
             t += q.h / fmax(1e-6, v0);
         }
@@ -331,21 +349,32 @@ __device__ __forceinline__ double lap_and_ax(const Part& pt, const VPar& q, cons
 // Returns gh = grad/2 and accumulates Jz = sum zhat^2, Sd = sum d^2 over the OWNED slots.
 struct Halo { double l0, l1, r0, r1; };
 
-template <int T, int K, bool EXACT>
-__device__ __forceinline__ void eval_window(const double (&x)[K], const Halo& hh, int cnt,
+template <int T, int K, int MODE>
+__device__ __forceinline__ void eval_window(const double (&x)[K], const Halo& hh, const Part& pt,
                                             const double* __restrict__ sC0, const double* __restrict__ sCp,
                                             const double* __restrict__ sCm, const double (&cL)[3], const double (&cR)[3],
                                             double lamJ, double& Jz, double& Sd, double (&gh)[K])
 {
+    constexpr bool EXACT = (MODE == kModeExact), OPEN = (MODE == kModeOpen);
+    const int cnt = pt.cnt;
+    // open tracks (DiffOpsOpen, main.cpp:560-579): the stencils are one-sided at the two ends.  With ghost
+    // values a[-1] := a[0], a[N] := a[N-1], zero stencil coefficients on the ghosts and end coefficients built by
+    // the kernel, zhat keeps the closed form; the smoothing term gets weight 4 on the end samples
+    // ((a1-a0)/h = 2 d/(2h)) and ghost terms e[-1] := -e[0], e[N] := -e[N-1], which is exactly D1^T D1.
+    const bool endL = OPEN && (pt.tid == 0), endR = OPEN && (pt.tid == pt.Tact - 1);
     double w[K + 4];
     w[0] = hh.l0; w[1] = hh.l1;
 #pragma unroll
     for (int k = 0; k < K; ++k) w[2 + k] = x[k];
     w[K + 2] = hh.r0; w[K + 3] = hh.r1;
+    if (OPEN) {
+        if (endL) { w[0] = x[0]; w[1] = x[0]; }
+    }
     if (!EXACT) {
 #pragma unroll
         for (int k = 1; k < K; ++k)
-            if (cnt == k) { w[2 + k] = hh.r0; w[3 + k] = hh.r1; }
+            if (cnt == k) { w[2 + k] = (OPEN && endR) ? x[k - 1] : hh.r0; w[3 + k] = (OPEN && endR) ? x[k - 1] : hh.r1; }
+        if (OPEN && endR && cnt == K) { w[K + 2] = x[K - 1]; w[K + 3] = x[K - 1]; }
     }
     double z[K + 2], s[K + 2], d[K + 2], pp[K + 2], mm[K + 2];
 #pragma unroll
@@ -361,6 +390,30 @@ __device__ __forceinline__ void eval_window(const double (&x)[K], const Halo& hh
         pp[p] = cp * z[p];
         mm[p] = cm * z[p];
     }
+    if (OPEN) {
+        // e[p] = weight * d[p] (weight relative to lamJ); positions: p = 0 is sample start-1, p = k+1 is slot k
+        double e[K + 2];
+#pragma unroll
+        for (int p = 0; p < K + 2; ++p) {
+            const bool is_end = (endL && p == 1) || (endR && p == cnt);
+            e[p] = is_end ? 4.0 * d[p] : d[p];
+        }
+        if (endL) e[0] = -e[1];
+#pragma unroll
+        for (int p = 2; p < K + 2; ++p) if (endR && p == cnt + 1) e[p] = -e[p - 1];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int p = k + 1;
+            double t = pp[p - 1] + mm[p + 1];
+            t = fma(-s[p], z[p], t);
+            gh[k] = fma(lamJ, e[p - 1] - e[p + 1], t);
+            if (k < cnt) {
+                Jz = fma(z[p], z[p], Jz);
+                Sd = fma(e[p], d[p], Sd);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int p = k + 1;
@@ -375,9 +428,10 @@ __device__ __forceinline__ void eval_window(const double (&x)[K], const Halo& hh
 }
 
 // first two / last two owned samples of a thread (what its neighbours need as halos)
-template <int K, bool EXACT>
+template <int K, int MODE>
 __device__ __forceinline__ void edge_values(const double (&x)[K], int cnt, double& F0, double& F1, double& L0, double& L1)
 {
+    constexpr bool EXACT = (MODE == kModeExact);
     F0 = x[0];
     F1 = x[1];
     if (EXACT) { L0 = x[K - 2]; L1 = x[K - 1]; }
@@ -391,11 +445,11 @@ __device__ __forceinline__ void edge_values(const double (&x)[K], int cnt, doubl
 }
 
 // shuffle part of the halo exchange + publication of the warp-edge values (before the barrier)
-template <int T, int K, bool EXACT>
+template <int T, int K, int MODE>
 __device__ __forceinline__ Halo halo_send(const double (&x)[K], const Part& pt, double* sExF, double* sExL)
 {
     double F0, F1, L0, L1;
-    edge_values<K, EXACT>(x, pt.cnt, F0, F1, L0, L1);
+    edge_values<K, MODE>(x, pt.cnt, F0, F1, L0, L1);
     Halo h;
     h.l0 = __shfl_sync(kFull, L0, pt.srcL);
     h.l1 = __shfl_sync(kFull, L1, pt.srcL);
@@ -439,14 +493,14 @@ struct PgdCtx {
 // Evaluate the trial xa (halos ha), form the next trial xb = clamp(xa - step*g) speculatively, exchange its
 // halos and reduce (J(xa), g_prev.(xa - a)) through ONE barrier, then take the Armijo decision (main.cpp:734).
 // Returns true when xa is accepted: the stash then holds xa and xb/hb is the next trial.
-template <int T, int K, bool EXACT>
+template <int T, int K, int MODE>
 __device__ __forceinline__ bool pgd_half(const Part& pt, const double (&xa)[K], const Halo& ha, double (&xb)[K], Halo& hb,
                                          const double* sLo, const double* sHi, const double (&cL)[3],
                                          const double (&cR)[3], PgdCtx<K>& c)
 {
     double gh[K];
     double Jz = 0.0, Sd = 0.0;
-    eval_window<T, K, EXACT>(xa, ha, pt.cnt, c.sC0, c.sCp, c.sCm, cL, cR, c.lamJ, Jz, Sd, gh);
+    eval_window<T, K, MODE>(xa, ha, pt, c.sC0, c.sCp, c.sCm, cL, cR, c.lamJ, Jz, Sd, gh);
     double Jn = fma(c.lamJ, Sd, Jz);
     double dec2p = 0.0;
 #pragma unroll
@@ -455,7 +509,7 @@ __device__ __forceinline__ bool pgd_half(const Part& pt, const double (&xa)[K], 
         dec2p = fma(gh[k], xn - xa[k], dec2p);
         xb[k] = xn;
     }
-    hb = halo_send<T, K, EXACT>(xb, pt, c.sExF + c.ph * 32, c.sExL + c.ph * 32);
+    hb = halo_send<T, K, MODE>(xb, pt, c.sExF + c.ph * 32, c.sExL + c.ph * 32);
     double dec = c.decp;
     block_sum2<T>(Jn, dec, c.sRed + c.ph * 32, pt.lane, pt.warp);
     halo_recv<T>(hb, pt, c.sExF + c.ph * 32, c.sExL + c.ph * 32);
@@ -480,7 +534,7 @@ __device__ __forceinline__ bool pgd_half(const Part& pt, const double (&xa)[K], 
 // and x is accepted ~98% of the time), its halos are exchanged and (J(x), g_prev.(x-a)) are reduced through
 // the same barrier.  The trial alternates between two register arrays (x, y) so that an accept moves no data.
 // On a reject the step halves and the trial is rebuilt from the stashed accepted alpha.
-template <int T, int K, bool EXACT>
+template <int T, int K, int MODE>
 __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, const double* sHi,
                                             const double (&cL)[3], const double (&cR)[3],
                                             const double* sC0, const double* sCp, const double* sCm, double* sSt,
@@ -502,7 +556,7 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
         // ---- J and gradient at alpha = 0 (main.cpp:724 / 997), first trial into x ----
         double gh[K];
         double Jz = 0.0, Sd = 0.0;
-        eval_window<T, K, EXACT>(x, hx, pt.cnt, sC0, sCp, sCm, cL, cR, lamJ, Jz, Sd, gh);
+        eval_window<T, K, MODE>(x, hx, pt, sC0, sCp, sCm, cL, cR, lamJ, Jz, Sd, gh);
         o.ev++;
         double Jt = fma(lamJ, Sd, Jz);
         double decp = 0.0;
@@ -512,7 +566,7 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
             decp = fma(gh[k], xn, decp);
             x[k] = xn;
         }
-        hx = halo_send<T, K, EXACT>(x, pt, sExF + c.ph * 32, sExL + c.ph * 32);
+        hx = halo_send<T, K, MODE>(x, pt, sExF + c.ph * 32, sExL + c.ph * 32);
         double zero = 0.0;
         block_sum2<T>(Jt, zero, sRed + c.ph * 32, pt.lane, pt.warp);
         halo_recv<T>(hx, pt, sExF + c.ph * 32, sExL + c.ph * 32);
@@ -524,8 +578,8 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
     int it = 0, bt = 0;
     bool in_x = true;    // which array holds the current trial
     while (it < max_inner) {
-        const bool acc = in_x ? pgd_half<T, K, EXACT>(pt, x, hx, y, hy, sLo, sHi, cL, cR, c)
-                              : pgd_half<T, K, EXACT>(pt, y, hy, x, hx, sLo, sHi, cL, cR, c);
+        const bool acc = in_x ? pgd_half<T, K, MODE>(pt, x, hx, y, hy, sLo, sHi, cL, cR, c)
+                              : pgd_half<T, K, MODE>(pt, y, hy, x, hx, sLo, sHi, cL, cR, c);
         o.ev++;
         if (acc) {
             in_x = !in_x;
@@ -539,12 +593,12 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
             double a[K], gh[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) a[k] = sSt[k * T];
-            Halo ha = halo_send<T, K, EXACT>(a, pt, sExF + c.ph * 32, sExL + c.ph * 32);
+            Halo ha = halo_send<T, K, MODE>(a, pt, sExF + c.ph * 32, sExL + c.ph * 32);
             block_sync<T>();
             halo_recv<T>(ha, pt, sExF + c.ph * 32, sExL + c.ph * 32);
             c.ph ^= 1;
             double jz = 0.0, sd = 0.0;
-            eval_window<T, K, EXACT>(a, ha, pt.cnt, sC0, sCp, sCm, cL, cR, lamJ, jz, sd, gh);
+            eval_window<T, K, MODE>(a, ha, pt, sC0, sCp, sCm, cL, cR, lamJ, jz, sd, gh);
             double decp = 0.0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -553,7 +607,7 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
                 x[k] = xn;
             }
             c.decp = decp;
-            hx = halo_send<T, K, EXACT>(x, pt, sExF + c.ph * 32, sExL + c.ph * 32);
+            hx = halo_send<T, K, MODE>(x, pt, sExF + c.ph * 32, sExL + c.ph * 32);
             block_sync<T>();
             halo_recv<T>(hx, pt, sExF + c.ph * 32, sExL + c.ph * 32);
             c.ph ^= 1;
@@ -575,7 +629,7 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
 // (minDistanceToSegments_global, main.cpp:501-512), pruned by box lower bounds.
 // Results are returned in the BLOCKED layout through region B.
 template <int T, int K>
-__device__ __forceinline__ void corridor_build_tiled(const Part& pt, const double2* sP, double* sB, uint64_t* mbar, uint32_t& bar_phase,
+__device__ __forceinline__ void corridor_build_tiled(const Part& pt, const double2* sP, double* sB, uint64_t* mbar, uint32_t& bar_phase, bool closed,
                                                const double* __restrict__ gseg, long long segI0, long long segO0, long long segE,
                                                double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests)
 {
@@ -642,7 +696,7 @@ __device__ __forceinline__ void corridor_build_tiled(const Part& pt, const doubl
                     const double2 Pc = sP[i];
                     if (pass == 0) {
                         double nx, ny;
-                        normal_closed(sp_prev(sP, i, N), sp_next(sP, i, N), N, nx, ny);
+                        normal_at(sP, i, N, closed, nx, ny);
                         double bp = pos[j], bn = neg[j];
                         for (int bq = 0; bq < nblk; ++bq) {
                             const double cx = sBox[4 * bq], cy = sBox[4 * bq + 1], hx = sBox[4 * bq + 2], hy = sBox[4 * bq + 3];
@@ -1117,7 +1171,7 @@ __device__ __noinline__ float clearance_scan(const RayTile& tl_in, float px, flo
 
 template <int T, int K>
 __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double2* sP, double* sB, uint64_t* mbar, uint32_t& bar_phase,
-                                                    int* sMisc, unsigned* sHint, unsigned short* sClr, bool first, bool parity_ok,
+                                                    int* sMisc, unsigned* sHint, unsigned short* sClr, bool first, bool parity_ok, bool closed,
                                                     const double* __restrict__ gseg, const double* __restrict__ gcenter,
                                                     long long segI0, long long segO0, long long segE,
                                                     double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests)
@@ -1154,8 +1208,8 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                 continue;
             }
             RayTile tl;
-            bool closed;
-            const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, closed);
+            bool chain;   // the ring's segments form a closed chain
+            const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, chain);
             const int hshift = 13 * ring;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
@@ -1164,14 +1218,14 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                 if (pass == 1 && !((flagged >> j) & 1u)) continue;
                 const double2 Pc = sP[i];
                 double nx, ny;
-                normal_closed(sp_prev(sP, i, N), sp_next(sP, i, N), N, nx, ny);
+                normal_at(sP, i, N, closed, nx, ny);
                 const float px = (float)(Pc.x - org.x), py = (float)(Pc.y - org.y), fnx = (float)nx, fny = (float)ny;
                 const float m = m0 + 2e-6f * fmaxf(fabsf(px), fabsf(py));
                 unsigned hw = sHint[i];
                 unsigned short cw = sClr[i];
                 int j0 = (int)((hw >> hshift) & 0x1fffu);
                 if (j0 >= mr) j0 = 0;
-                const bool inside = parity_ok && closed && ((hw >> (26 + ring)) & 1u);
+                const bool inside = parity_ok && chain && ((hw >> (26 + ring)) & 1u);
                 // displacement from the centre-line position the clearance refers to
                 const double cx0 = gcenter[2 * i], cy0 = gcenter[2 * i + 1];
                 const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
@@ -1251,7 +1305,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                     }
                     // refresh the state of this sample for this ring
                     if (first) {
-                        const bool in = closed && inside_ring(tl, Pc, px, py, m);
+                        const bool in = chain && inside_ring(tl, Pc, px, py, m);
                         hw = (hw & ~(1u << (26 + ring))) | ((in ? 1u : 0u) << (26 + ring));
                     }
                     if (hs >= 0) {
@@ -1308,11 +1362,12 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
 }
 
 // ---- the solver kernel ------------------------------------------------------------------------------------
-template <int T, int K, bool EXACT>
+template <int T, int K, int MODE>
 __global__ void __launch_bounds__(T, (512 / T) > 16 ? 16 : (512 / T))
 solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
 {
     constexpr int NP = T * K;
+    constexpr bool EXACT = (MODE == kModeExact), OPEN = (MODE == kModeOpen);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* sP = reinterpret_cast<double2*>(smem_raw);
     double* sB = reinterpret_cast<double*>(smem_raw + (size_t)NP * 16);
@@ -1336,6 +1391,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     const long long row0 = B.job_off[jid];
     const bool mt = (job.stage == RL_STAGE_MINTIME);
     const double h = B.track_L[trk] / (double)N;
+    const bool closed = (MODE != kModeOpen);
 
     // ---- blocked partition of the N samples over the threads ----
     Part pt;
@@ -1404,10 +1460,10 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     const bool parity_ok = (C.veh_width_arg * 0.5 + C.safety_margin_m >= 0.0) && (C.veh_width_m * 0.5 + C.safety_margin_m >= 0.0);
     for (int i = tid; i < NP; i += T) { sHint[i] = 0u; sClr[i] = 0; }
     if (fast_rays)
-        corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, true, parity_ok, B.seg, B.center_xy + 2 * s0, segI0, segO0, segE,
+        corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, true, parity_ok, closed, B.seg, B.center_xy + 2 * s0, segI0, segO0, segE,
                                   C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
     else
-        corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,
+        corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                    C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
 
     double* sC0 = sB + tid;
@@ -1423,10 +1479,9 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
             A1[k] = 0.0; A2[k] = 0.0; N0[k] = 0.0; Wd[k] = 1.0;
             if (k < cnt) {
                 const int i = start + k;
-                const double2 Pm = sp_prev(sP, i, N), Pc = sP[i], Pp = sp_next(sP, i, N);
                 double nx, ny, xp, yp, xpp, ypp;
-                normal_closed(Pm, Pp, N, nx, ny);
-                derivs_closed(Pm, Pc, Pp, h, N, xp, yp, xpp, ypp);
+                normal_at(sP, i, N, closed, nx, ny);
+                derivs_at(sP, i, N, h, closed, xp, yp, xpp, ypp);
                 A1[k] = nx * ypp - ny * xpp;          // main.cpp:644-646
                 A2[k] = xp * ny - yp * nx;
                 N0[k] = xp * ypp - yp * xpp;
@@ -1453,9 +1508,9 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
 #pragma unroll
             for (int k = 0; k < K; ++k) kap[k] = (k < cnt) ? N0[k] / Wd[k] : 0.0;    // kappa, main.cpp:618
             block_sync<T>();   // region B is free: lo/hi are in registers, coefficients not yet built
-            vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds);
+            vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed);
             block_sync<T>();
-            lap_outer = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32);
+            lap_outer = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32, closed);
             ph ^= 1;
             double v_avg = 0.0;
             if (C.time_weight_use_inv_v) {            // main.cpp:951
@@ -1497,6 +1552,12 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
                 c0 = gw * N0[k];
                 const double c1 = gw * A1[k] * inv2h, c2 = gw * A2[k] * invh2;
                 cp = c1 + c2; cm = c2 - c1;
+                if (OPEN) {   // DiffOpsOpen, main.cpp:563-575: D1 one-sided with 1/h at the ends, D2 zero there
+                    const int i = start + k;
+                    if (N == 1) { cp = 0.0; cm = 0.0; }
+                    else if (i == 0) { cp = 2.0 * c1; cm = 0.0; }
+                    else if (i == N - 1) { cp = 0.0; cm = -2.0 * c1; }
+                }
             }
             sC0[k * T] = c0; sCp[k * T] = cp; sCm[k * T] = cm;
         }
@@ -1508,12 +1569,16 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
             cL[0] = b0[kl * T]; cL[1] = b0[NP + kl * T]; cL[2] = b0[2 * NP + kl * T];
             cR[0] = br[0]; cR[1] = br[NP]; cR[2] = br[2 * NP];
         }
+        if (OPEN) {   // nothing beyond the two ends of an open track
+            if (tid == 0) { cL[0] = 0.0; cL[1] = 0.0; cL[2] = 0.0; }
+            if (tid == pt.Tact - 1) { cR[0] = 0.0; cR[1] = 0.0; cR[2] = 0.0; }
+        }
         if (!EXACT) {
             // the first unused slot mirrors the right neighbour's first sample (position cnt+1 of the window)
             if (cnt < K && cnt > 0) { sC0[cnt * T] = cR[0]; sCp[cnt * T] = cR[1]; sCm[cnt * T] = cR[2]; }
         }
         // =================== projected gradient with Armijo (main.cpp:723-742 / 996-1026) ===================
-        const PgdOut po = pgd_outer<T, K, EXACT>(pt, sLo, sHi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,
+        const PgdOut po = pgd_outer<T, K, MODE>(pt, sLo, sHi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,
                                                  C.step_init, C.step_min, C.armijo_c, C.max_inner_iters);
         acc_total += po.acc; bt_total += po.bt; ev_total += po.ev;
         if (tid == 0 && outer < RL_MAX_OUTER_LOG) {
@@ -1537,7 +1602,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
                 const int i = start + k;
                 const double al = sSt[k * T];
                 double nx, ny;
-                normal_closed(sp_prev(sP, i, N), sp_next(sP, i, N), N, nx, ny);
+                normal_at(sP, i, N, closed, nx, ny);
                 const double2 Pc = sP[i];
                 Pn[k].x = Pc.x + nx * al; Pn[k].y = Pc.y + ny * al;
                 B.alpha_total[row0 + i] += al;
@@ -1550,10 +1615,10 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
         block_sync<T>();
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
         if (fast_rays)
-            corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, B.seg, B.center_xy + 2 * s0, segI0, segO0, segE,
+            corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, segI0, segO0, segE,
                                       C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
         else
-            corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, B.seg, segI0, segO0, segE,
+            corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                        C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
     }
 
@@ -1564,7 +1629,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
         const int i = tid + j * T;
         if (i < N) {
             double xp, yp, xpp, ypp;
-            derivs_closed(sp_prev(sP, i, N), sP[i], sp_next(sP, i, N), h, N, xp, yp, xpp, ypp);
+            derivs_at(sP, i, N, h, closed, xp, yp, xpp, ypp);
             B.heading[row0 + i] = atan2(yp, xp);
             B.curvature[row0 + i] = (xp * ypp - yp * xpp) / pow15(xp * xp + yp * yp);
         }
@@ -1579,14 +1644,14 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
             if (k < cnt) {
                 const int i = start + k;
                 double xp, yp, xpp, ypp;
-                derivs_closed(sp_prev(sP, i, N), sP[i], sp_next(sP, i, N), h, N, xp, yp, xpp, ypp);
+                derivs_at(sP, i, N, h, closed, xp, yp, xpp, ypp);
                 kap[k] = (xp * ypp - yp * xpp) / pow15(xp * xp + yp * yp);
             }
         }
         block_sync<T>();
-        vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds);
+        vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed);
         block_sync<T>();
-        lap = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32);
+        lap = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32, closed);
         ph ^= 1;
 #pragma unroll
         for (int k = 0; k < K; ++k)
@@ -1613,23 +1678,26 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
 }  // namespace
 }  // namespace rl
 
-// one translation unit per thread count T instantiates its two kernels (ragged and exact-fit) through this macro
+// one translation unit per thread count T instantiates its three kernels (closed ragged, closed exact-fit, open)
 #define RL_INSTANTIATE(T, K)                                                                                          \
     namespace rl {                                                                                                    \
-    int launch_solve_##T(const DevBatch& B, const int* job_list, int n_list, bool exact, void* stream)               \
+    int launch_solve_##T(const DevBatch& B, const int* job_list, int n_list, int mode, void* stream)                 \
     {                                                                                                                 \
         const size_t smem = smem_bytes_for_class(T, K);                                                               \
         cudaStream_t s = (cudaStream_t)stream;                                                                        \
-        if (exact) solve_kernel<T, K, true><<<n_list, T, smem, s>>>(B, job_list, n_list);                             \
-        else solve_kernel<T, K, false><<<n_list, T, smem, s>>>(B, job_list, n_list);                                  \
+        if (mode == 1) solve_kernel<T, K, 1><<<n_list, T, smem, s>>>(B, job_list, n_list);                            \
+        else if (mode == 2) solve_kernel<T, K, 2><<<n_list, T, smem, s>>>(B, job_list, n_list);                       \
+        else solve_kernel<T, K, 0><<<n_list, T, smem, s>>>(B, job_list, n_list);                                      \
         return (int)cudaGetLastError();                                                                               \
     }                                                                                                                 \
     int configure_solve_##T()                                                                                         \
     {                                                                                                                 \
         const int smem = (int)smem_bytes_for_class(T, K);                                                             \
-        cudaError_t e = cudaFuncSetAttribute(solve_kernel<T, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        cudaError_t e = cudaFuncSetAttribute(solve_kernel<T, K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         if (e == cudaSuccess)                                                                                         \
-            e = cudaFuncSetAttribute(solve_kernel<T, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   \
+            e = cudaFuncSetAttribute(solve_kernel<T, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
+        if (e == cudaSuccess)                                                                                         \
+            e = cudaFuncSetAttribute(solve_kernel<T, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
         return (int)e;                                                                                                \
     }                                                                                                                 \
     }

@@ -11,6 +11,7 @@ Also written:
                                  P_max_W, w_time_gain, plus the inv-v weighting switch) solved by the
                                  reference through `ref_harness solve`; pins the port off-default.
   competition_map2_n1000.npz  -- the same map with samples forced to 1000 (a larger, ragged N).
+  open_<map>.npz              -- open-track mode (closed=false, polyline edges), solved by the reference.
 
 Usage:  python tests/golden/make_golden.py         (needs /root/reference)
 """
@@ -136,6 +137,35 @@ def sweep_golden(base):
     return out
 
 
+def open_golden(base):
+    """Open-track mode (cfg is_closed_track=false, main.cpp:54): the same map driven as an open path with
+    polyline edges (edges::polylineEdges, main.cpp:256), solved by the reference itself."""
+    n = base["n"]
+    inner = np.concatenate([base["inner_seg"][:-1, :2], base["inner_seg"][1:, :2]], axis=1)
+    outer = np.concatenate([base["outer_seg"][:-1, :2], base["outer_seg"][1:, :2]], axis=1)
+    p = oracle.default_params()
+    jobs = np.array([[0, 0, RL_STAGE_MINCURV], [0, 0, RL_STAGE_MINTIME]])
+    with tempfile.TemporaryDirectory() as td:
+        bf, rf = os.path.join(td, "b.bin"), os.path.join(td, "r.bin")
+        batchfile.write_rlb1(bf, [0, n], [0, len(inner), len(inner) + len(outer)], [base["L"]], [0], base["center_xy"],
+                             np.concatenate([inner, outer]), params_row(p)[None, :], jobs)
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_harness"), "solve", bf, rf], check=True, capture_output=True)
+        res = batchfile.read_rlr1(rf)
+    out = {"center_xy": base["center_xy"], "inner_seg": inner, "outer_seg": outer, "L": base["L"], "n": n}
+    for pre, r, stage in (("mc", res[0], RL_STAGE_MINCURV), ("mt", res[1], RL_STAGE_MINTIME)):
+        o = oracle.solve(stage, base["center_xy"], inner, outer, base["L"], False, p)
+        for k in (FIELDS_MT if pre == "mt" else FIELDS_MC):
+            if not np.array_equal(o[k].view(np.uint64), r[k].view(np.uint64)):
+                raise SystemExit(f"[open {pre}] oracle port differs from reference in {k}: {np.abs(o[k]-r[k]).max():.3e}")
+            out[f"{pre}_{k}"] = r[k]
+        out[f"{pre}_accepted"] = o["stats"].accepted
+        out[f"{pre}_backtracks"] = o["stats"].backtracks
+    if oracle.solve(RL_STAGE_MINTIME, base["center_xy"], inner, outer, base["L"], False, p)["lap_time"] != res[1]["lap_time"]:
+        raise SystemExit("[open] lap differs")
+    out["mt_lap_time"] = res[1]["lap_time"]
+    return out
+
+
 def main():
     if not os.path.exists(f"{REF}/src/main.cpp"):
         raise SystemExit("the reference is not mounted; goldens can only be regenerated in the build container")
@@ -154,6 +184,11 @@ def main():
     base = dict(np.load(os.path.join(OUT, "competition_map2.npz")))
     base = {k: (v.item() if v.ndim == 0 else v) for k, v in base.items()}
     np.savez_compressed(os.path.join(OUT, "sweep_competition_map2.npz"), **sweep_golden(base))
+    print("open-track mode on competition_map1 and training_map")
+    for name in ("competition_map1", "training_map"):
+        b = dict(np.load(os.path.join(OUT, name + ".npz")))
+        b = {k: (v.item() if v.ndim == 0 else v) for k, v in b.items()}
+        np.savez_compressed(os.path.join(OUT, f"open_{name}.npz"), **open_golden(b))
     print("oracle port == reference, bit for bit, on every golden case")
 
 

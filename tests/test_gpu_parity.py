@@ -171,9 +171,9 @@ def test_errors_and_unsupported(ctx, goldens):
     with pytest.raises(rl.RacelineError) as e:
         rl.solve_batch([tr], [rl.Config()], [(0, 0, 7)], ctx=ctx)
     assert e.value.status == rl.RL_ERR_ARG
-    open_tr = rl.Track(tr.center_xy, tr.inner_seg, tr.outer_seg, tr.L, closed=False)
+    big = rl.Track(np.zeros((5000, 2)), tr.inner_seg, tr.outer_seg, 9000.0)       # N > 4096: no kernel covers it yet
     with pytest.raises(rl.RacelineError) as e:
-        rl.solve_batch([open_tr], [rl.Config()], [(0, 0, MC)], ctx=ctx)
+        rl.solve_batch([big], [rl.Config()], [(0, 0, MC)], ctx=ctx)
     assert e.value.status == rl.RL_ERR_UNSUPPORTED
     assert lib().rl_solve_batch(ctx._h, None, None) == rl.RL_ERR_ARG
     # the context is still usable after errors
@@ -306,3 +306,36 @@ def test_pipelined_host_path_matches_resident_path(ctx):
     tr = rl.Track(center.reshape(nt, n, 2)[1299], seg.reshape(nt, 2, m, 4)[1299, 0], seg.reshape(nt, 2, m, 4)[1299, 1], L[1299])
     o = oracle_ref(MT, tr, cfg.to_params())
     assert_result_close(pb.result(2 * 1299 + 1), o, "o_", True, tag="last job of the last chunk")
+
+
+@pytest.mark.parametrize("name", ["open_competition_map1", "open_training_map"])
+def test_open_track_parity_vs_reference(ctx, name):
+    """closed=false (cfg is_closed_track, main.cpp:54): one-sided stencils at the ends, polyline edges, no wrap."""
+    g = load_golden(name)
+    tr = rl.Track(g["center_xy"], g["inner_seg"], g["outer_seg"], g["L"], closed=False)
+    res = rl.solve_batch([tr], [rl.Config()], [(0, 0, MC), (0, 0, MT)], ctx=ctx)
+    for st, pre, r in ((MC, "mc_", res[0]), (MT, "mt_", res[1])):
+        assert_result_close(r, g, pre, st == MT, tag=(name, pre))
+        assert r.stats.accepted == g[pre + "accepted"] and r.stats.backtracks == g[pre + "backtracks"], (name, pre)
+    assert abs(res[1].lap_time - g["mt_lap_time"]) <= TOL_LAP_REL * g["mt_lap_time"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 33, 100, 257, 600, 2048])
+def test_open_tracks_vs_oracle(ctx, n):
+    """open paths of every size class: an arc of a synthetic track, rings opened at the same place."""
+    nn = max(n, 16)
+    center, seg, L, m = rl.synth_tracks(1, nn + 8, seed_base=0xB200 + 3 * n)
+    center, seg = center.reshape(nn + 8, 2), seg.reshape(2, m, 4)
+    keep = max(3, int(m * n / (nn + 8)))
+    tr = rl.Track(center[:n], rl.polyline_edges(seg[0, :keep + 2, :2]), rl.polyline_edges(seg[1, :keep + 2, :2]),
+                  L[0] * n / (nn + 8), closed=False)
+    cfg = rl.Config()
+    res = rl.solve_batch([tr], [cfg], [(0, 0, MC), (0, 0, MT)], ctx=ctx)
+    for st, r in zip((MC, MT), res):
+        o = oracle_ref(st, tr, cfg.to_params())
+        assert_result_close(r, o, "o_", st == MT, tag=("open", n, st))
+        assert r.stats.accepted == o["stats"].accepted, (n, st)
+        if not stalled(o["stats"]):
+            assert r.stats.backtracks == o["stats"].backtracks, (n, st)
+        if st == MT:
+            assert abs(r.lap_time - o["lap"]) <= TOL_LAP_REL * max(o["lap"], 1e-9)

@@ -92,3 +92,16 @@ def test_corridor_fallback_when_ray_misses():
     lo, hi = oracle.corridor(np.array([[0.0, 0.0]]), np.array([[1.0, 0.0]]), ring, far, 0.5)
     assert abs(hi[0] - 1.5) < 1e-12          # +n hits the box at 2
     assert abs(lo[0] + 1.5) < 1e-12          # -n misses the box: nearest distance 2 < wall at 50
+
+
+@pytest.mark.parametrize("name", ["open_competition_map1", "open_training_map"])
+def test_oracle_matches_reference_bitwise_open_track(name):
+    """open-track mode (DiffOpsOpen main.cpp:560-579, one-sided normals/derivatives, no wrap in the v(s) passes)."""
+    g = load_golden(name)
+    p = oracle.default_params()
+    for stage, pre, extra in ((RL_STAGE_MINCURV, "mc_", ()), (RL_STAGE_MINTIME, "mt_", ("v", "ax"))):
+        r = oracle.solve(stage, g["center_xy"], g["inner_seg"], g["outer_seg"], g["L"], False, p)
+        for k in ("xy", "heading", "curvature", "alpha_total", "alpha_last") + extra:
+            assert np.array_equal(r[k], g[pre + k]), (name, pre + k)
+        assert r["stats"].accepted == g[pre + "accepted"] and r["stats"].backtracks == g[pre + "backtracks"]
+    assert r["lap_time"] == g["mt_lap_time"]

@@ -15,9 +15,9 @@ LIB = os.path.join(CSRC, "libraceline_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-SOURCES = ["raceline_inst_256.cu", "raceline_inst_512.cu", "raceline_inst_128.cu", "raceline_inst_64.cu", "raceline_inst_32.cu",
+SOURCES = ["raceline_inst_256.cu", "raceline_inst_cluster.cu", "raceline_inst_512.cu", "raceline_inst_128.cu", "raceline_inst_64.cu", "raceline_inst_32.cu",
            "raceline_dispatch.cu", "raceline_api.cu", "synth_tracks.cpp"]
-HEADERS = [os.path.join(CSRC, "raceline_device.h"), os.path.join(CSRC, "raceline_kernels.cuh"),
+HEADERS = [os.path.join(CSRC, "raceline_device.h"), os.path.join(CSRC, "raceline_kernels.cuh"), os.path.join(CSRC, "raceline_cluster.cuh"),
            os.path.join(HERE, "..", "include", "raceline_b200.h")]
 
 

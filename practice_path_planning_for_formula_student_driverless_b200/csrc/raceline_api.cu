@@ -154,6 +154,9 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
     for (int c = 0; c <= n_chunks; ++c) b->chunk_job0[c] = (int)(((long long)d->n_jobs * c) / n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
         std::vector<std::vector<int>> bucket(rl::kNumClasses * 3);
+        std::vector<std::vector<int>> cbucket(2 * (rl::kMaxClusterSize + 1));   // [cs][mode] cluster launches
+        int force_cs = 0;
+        if (const char* e = std::getenv("RL_FORCE_CLUSTER")) force_cs = std::atoi(e);   // test hook: cluster kernel on shorter tracks
         for (int pass = 0; pass < 2; ++pass) {
             for (int j = b->chunk_job0[c]; j < b->chunk_job0[c + 1]; ++j) {
                 const rl_job& jb = d->jobs[j];
@@ -163,6 +166,8 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
                 const long long n = d->samp_off[t + 1] - d->samp_off[t];
                 if (n == 0) { b->skipped.push_back({j, RL_OK}); continue; }   // empty Result, main.cpp:689 / 912
                 const int cls = rl::class_for_n((int)n);
+                const int cs = (d->track_closed[t] && (cls < 0 || force_cs > 0)) ? rl::cluster_size_for_n(n, force_cs) : 0;
+                if (cs > 0) { cbucket[2 * cs + (n == 2048ll * cs ? 1 : 0)].push_back(j); continue; }
                 if (cls < 0) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
                 const bool exact = (n == (long long)rl::kClasses[cls].T * rl::kClasses[cls].K);
                 const int mode = !d->track_closed[t] ? 2 : (exact ? 1 : 0);   // open | closed exact-fit | closed ragged
@@ -173,6 +178,11 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
             if (bucket[k].empty()) continue;
             b->lists.push_back({k / 3, k % 3, (int)b->joblist.size(), (int)bucket[k].size(), c});
             b->joblist.insert(b->joblist.end(), bucket[k].begin(), bucket[k].end());
+        }
+        for (size_t k = 0; k < cbucket.size(); ++k) {
+            if (cbucket[k].empty()) continue;
+            b->lists.push_back({rl::kClusterClassBase + (int)(k / 2), (int)(k % 2), (int)b->joblist.size(), (int)cbucket[k].size(), c});
+            b->joblist.insert(b->joblist.end(), cbucket[k].begin(), cbucket[k].end());
         }
     }
 

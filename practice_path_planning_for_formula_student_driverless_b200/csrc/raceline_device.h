@@ -55,6 +55,26 @@ inline size_t smem_bytes_for_class(int T, int K)
            + np * 6;    /* per-sample corridor state: anchor segments + parity bits (4 B), clearances (2 B) */
 }
 
+// Long tracks (N > 4096): one thread-block cluster of `cs` CTAs (256 threads x 8 samples) per job, see
+// raceline_cluster.cuh.  Every CTA of the cluster needs between 512 and 2048 samples.  Returns 0 when no cluster
+// size fits.  `force` > 0 (test hook RL_FORCE_CLUSTER) asks for exactly that size.
+constexpr int kMaxClusterSize = 8;
+constexpr int kClusterClassBase = 100;   // ClassList.cls = kClusterClassBase + cs for cluster launches
+inline int cluster_size_for_n(long long n, int force = 0)
+{
+    const int sizes[3] = {2, 4, 8};
+    for (int i = 0; i < 3; ++i) {
+        const int cs = sizes[i];
+        if (force > 0 && cs != force) continue;
+        if (force <= 0 && cs == 2) continue;   // N <= 4096 belongs to the single-CTA kernels
+        if (n >= 512ll * cs && n <= 2048ll * cs) return cs;
+    }
+    return 0;
+}
+// mode 0 = ragged chunks, 1 = every chunk holds exactly 2048 samples.  Returns a cudaError_t as int.
+int launch_solve_cluster(const DevBatch& B, const int* job_list, int n_list, int cs, int mode, void* stream);
+int configure_solve_cluster();
+
 // launches job_list[0..n_list) (indices into B.jobs) with the kernel of class `cls` and mode
 // 0 = closed track, 1 = closed track and every job has N == T*K, 2 = open track.  Returns a cudaError_t as int.
 int launch_solve(const DevBatch& B, const int* job_list, int n_list, int cls, int mode, void* stream);

@@ -33,12 +33,14 @@ int configure_kernels()
     if (!e) e = configure_solve_128();
     if (!e) e = configure_solve_256();
     if (!e) e = configure_solve_512();
+    if (!e) e = configure_solve_cluster();
     return e;
 }
 
 int launch_solve(const DevBatch& B, const int* job_list, int n_list, int cls, int mode, void* stream)
 {
     if (n_list <= 0) return 0;
+    if (cls >= kClusterClassBase) return launch_solve_cluster(B, job_list, n_list, cls - kClusterClassBase, mode, stream);
     switch (kClasses[cls].T) {
         case 32: return launch_solve_32(B, job_list, n_list, mode, stream);
         case 64: return launch_solve_64(B, job_list, n_list, mode, stream);

@@ -139,6 +139,15 @@ struct Part {
 // kernel modes: 0 = closed track, ragged N; 1 = closed track, N == T*K exactly; 2 = open track (ragged)
 constexpr int kModeClosed = 0, kModeExact = 1, kModeOpen = 2;
 
+// tangent -> unit normal with the degenerate-case rules of main.cpp:588-592
+__device__ __forceinline__ void normal_from_tangent(double tx, double ty, double& nx, double& ny)
+{
+    if (sqrt(tx * tx + ty * ty) < 1e-15) { tx = 1.0; ty = 0.0; }
+    const double nvx = -ty, nvy = tx;
+    const double len = sqrt(nvx * nvx + nvy * nvy);
+    if (len < 1e-15) { nx = 0.0; ny = 0.0; }
+    else { nx = nvx / len; ny = nvy / len; }
+}
 // normals_from_points_generic, main.cpp:581-593 (closed: periodic central difference; open: one-sided ends)
 __device__ __forceinline__ void normal_at(const double2* sP, int i, int N, bool closed, double& nx, double& ny)
 {
@@ -150,11 +159,15 @@ __device__ __forceinline__ void normal_at(const double2* sP, int i, int N, bool 
     } else if (i == 0) { tx = sP[1].x - sP[0].x; ty = sP[1].y - sP[0].y; }
     else if (i == N - 1) { tx = sP[N - 1].x - sP[N - 2].x; ty = sP[N - 1].y - sP[N - 2].y; }
     else { tx = (sP[i + 1].x - sP[i - 1].x) * 0.5; ty = (sP[i + 1].y - sP[i - 1].y) * 0.5; }
-    if (sqrt(tx * tx + ty * ty) < 1e-15) { tx = 1.0; ty = 0.0; }
-    const double nvx = -ty, nvy = tx;
-    const double len = sqrt(nvx * nvx + nvy * nvy);
-    if (len < 1e-15) { nx = 0.0; ny = 0.0; }
-    else { nx = nvx / len; ny = nvy / len; }
+    normal_from_tangent(tx, ty, nx, ny);
+}
+// central-difference derivatives of the `deriv` lambda (interior / periodic case), main.cpp:599-603 / 625-629
+__device__ __forceinline__ void derivs_central(double2 Pm, double2 Pc, double2 Pp, double h,
+                                               double& xp, double& yp, double& xpp, double& ypp)
+{
+    const double h2 = 2 * h, hh = h * h;
+    xp = (Pp.x - Pm.x) / h2; yp = (Pp.y - Pm.y) / h2;
+    xpp = (Pp.x - 2 * Pc.x + Pm.x) / hh; ypp = (Pp.y - 2 * Pc.y + Pm.y) / hh;
 }
 // the `deriv` lambda, main.cpp:599-613 / 625-639
 __device__ __forceinline__ void derivs_at(const double2* sP, int i, int N, double h, bool closed,
@@ -163,9 +176,7 @@ __device__ __forceinline__ void derivs_at(const double2* sP, int i, int N, doubl
     if (N == 1) { xp = 1.0; yp = 0.0; xpp = 0.0; ypp = 0.0; return; }
     const double h2 = 2 * h, hh = h * h;
     if (closed || (i > 0 && i < N - 1)) {
-        const double2 Pm = sP[(i == 0) ? N - 1 : i - 1], Pc = sP[i], Pp = sP[(i == N - 1) ? 0 : i + 1];
-        xp = (Pp.x - Pm.x) / h2; yp = (Pp.y - Pm.y) / h2;
-        xpp = (Pp.x - 2 * Pc.x + Pm.x) / hh; ypp = (Pp.y - 2 * Pc.y + Pm.y) / hh;
+        derivs_central(sP[(i == 0) ? N - 1 : i - 1], sP[i], sP[(i == N - 1) ? 0 : i + 1], h, xp, yp, xpp, ypp);
     } else if (i == 0) {
         xp = (sP[1].x - sP[0].x) / h; yp = (sP[1].y - sP[0].y) / h;
         if (N >= 3) { xpp = (sP[2].x - 2 * sP[1].x + sP[0].x) / hh; ypp = (sP[2].y - 2 * sP[1].y + sP[0].y) / hh; }

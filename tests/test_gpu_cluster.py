@@ -1,0 +1,112 @@
+"""GPU parity tests of the long-track path: one thread-block cluster per job (raceline_cluster.cuh).
+
+The cluster kernel serves N in (4096, 16384] (BASELINE configs[4] is N = 16,384).  RL_FORCE_CLUSTER=<cs> routes
+shorter closed tracks through it as well, so that every cluster size and the ragged / exact-fit chunkings can be
+checked against the pinned oracle at sizes the CPU finishes in seconds.  Same tolerances as test_gpu_parity.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import practice_path_planning_for_formula_student_driverless_b200 as rl
+from conftest import TOL_ALPHA, TOL_LAP_REL, assert_result_close
+from test_gpu_parity import MC, MT, oracle_ref, stalled
+
+pytestmark = pytest.mark.gpu
+
+
+def _tracks(nt, n, seed):
+    center, seg, L, m = rl.synth_tracks(nt, n, seed_base=seed)
+    center, seg = center.reshape(nt, n, 2), seg.reshape(nt, 2, m, 4)
+    return [rl.Track(center[i], seg[i, 0], seg[i, 1], L[i]) for i in range(nt)]
+
+
+def _check(r, tr, st, cfg, tag):
+    o = oracle_ref(st, tr, cfg.to_params())
+    assert_result_close(r, o, "o_", st == MT, tag=tag)
+    assert r.stats.status == 0 and r.stats.n == tr.center_xy.shape[0]
+    assert r.stats.accepted == o["stats"].accepted, tag
+    if not stalled(o["stats"]):
+        assert r.stats.backtracks == o["stats"].backtracks, tag
+        assert [int(x) for x in r.stats.bt_outer[:14]] == [int(x) for x in o["stats"].bt_outer[:14]], tag
+    if st == MT:
+        assert abs(r.lap_time - o["lap"]) <= TOL_LAP_REL * o["lap"], tag
+
+
+@pytest.mark.parametrize("cs,n", [(2, 1024), (2, 1100), (2, 4096), (4, 2500), (4, 3000), (8, 4100)])
+def test_forced_cluster_vs_oracle(ctx, cs, n, monkeypatch):
+    """every cluster size, ragged and exact-fit chunks, on tracks the single-CTA kernels could also solve"""
+    monkeypatch.setenv("RL_FORCE_CLUSTER", str(cs))
+    tracks = _tracks(2, n, 0xC100 + n)
+    cfg = rl.Config()
+    jobs = [(0, 0, MC), (0, 0, MT), (1, 0, MT)]
+    res = rl.solve_batch(tracks, [cfg], jobs, ctx=ctx)
+    monkeypatch.delenv("RL_FORCE_CLUSTER")
+    for (t, _, st), r in zip(jobs, res):
+        _check(r, tracks[t], st, cfg, ("cluster", cs, n, t, st))
+    # and the same bits as the single-CTA kernel on the same problem where that kernel exists
+    if n <= 4096:
+        res1 = rl.solve_batch(tracks, [cfg], jobs, ctx=ctx)
+        for a, b in zip(res, res1):
+            assert a.stats.accepted == b.stats.accepted and a.stats.backtracks == b.stats.backtracks
+            assert np.max(np.abs(a.alpha_total - b.alpha_total)) < 1e-9
+            if a.v is not None and b.v is not None and a.lap_time:
+                assert abs(a.lap_time - b.lap_time) <= 1e-9 * b.lap_time
+
+
+def test_forced_cluster_config_variants(ctx, monkeypatch):
+    """inverse-speed weights (a third cluster-wide reduction), heavy backtracking and early stops on the cluster path"""
+    monkeypatch.setenv("RL_FORCE_CLUSTER", "2")
+    tracks = _tracks(1, 1300, 0xC177)
+    cfgs = [rl.Config(time_weight_use_inv_v=True, inv_v_gain=0.4), rl.Config(step_init=40.0),
+            rl.Config(step_init=40.0, step_min=10.0, max_outer_iters=2), rl.Config(max_vpass_iters=1, P_max_W=20000.0)]
+    jobs = [(0, 0, MT), (0, 1, MC), (0, 1, MT), (0, 2, MC), (0, 3, MT)]
+    res = rl.solve_batch(tracks, cfgs, jobs, ctx=ctx)
+    for (t, c, st), r in zip(jobs, res):
+        _check(r, tracks[t], st, cfgs[c], ("cluster-cfg", c, st))
+
+
+def test_long_track_natural_dispatch(ctx):
+    """N = 5000 (4 CTAs, ragged chunks) takes the cluster kernel without any hook; batched with short tracks"""
+    long_tr = _tracks(1, 5000, 0xC500)[0]
+    short = _tracks(1, 300, 0xC501)[0]
+    cfg = rl.Config()
+    jobs = [(0, 0, MC), (1, 0, MT), (0, 0, MT)]
+    res = rl.solve_batch([long_tr, short], [cfg], jobs, ctx=ctx)
+    for (t, _, st), r in zip(jobs, res):
+        _check(r, [long_tr, short][t], st, cfg, ("long", t, st))
+
+
+def test_baseline_config5_shape(ctx):
+    """BASELINE configs[4] shape: N = 16,384 samples, M = 7447 cones per ring, 8 CTAs per track.  Size-independent
+    properties on a few tracks, bit-reproducibility, and (unless RL_SKIP_SLOW) one min-time solve against the oracle."""
+    nt, n = 3, 16384
+    center, seg, L, m = rl.synth_tracks(nt, n, seed_base=0xB200)
+    assert m == 7447
+    samp_off = np.arange(nt + 1, dtype=np.int64) * n
+    seg_off = np.arange(2 * nt + 1, dtype=np.int64) * m
+    cfg = rl.Config()
+    jobs = [(t, 0, st) for t in range(nt) for st in (MC, MT)]
+    pb = rl.PackedBatch.from_arrays(samp_off, seg_off, center, seg, L, np.ones(nt, np.int32), [cfg.to_params()], jobs)
+    dev = rl.DeviceBatch(ctx, pb)
+    dev.solve(); dev.download(); dev.sync()
+    first = [pb.result(j) for j in range(pb.n_jobs)]
+    a_tot = pb.out_alpha_total.copy(); xy = pb.out_xy.copy()
+    for j, r in enumerate(first):
+        st = r.stats
+        assert st.status == 0 and st.n == n and st.outer_done == 14 and 0 < st.accepted <= 14 * 120
+        for o in range(14):
+            assert st.Jend[o] <= st.J0[o] * (1 + 1e-12)
+        c0 = center.reshape(nt, n, 2)[jobs[j][0]]
+        assert np.all(np.isfinite(r.raceline)) and np.max(np.linalg.norm(r.raceline - c0, axis=1)) < 2.0
+        if jobs[j][2] == MT:
+            assert np.all(r.v > 0) and np.all(r.v <= cfg.v_cap_mps + 1e-12)
+            assert abs(r.lap_time - np.sum((L[jobs[j][0]] / n) / r.v)) <= 1e-9 * r.lap_time
+    dev.solve(); dev.download(); dev.sync()
+    assert np.array_equal(a_tot, pb.out_alpha_total) and np.array_equal(xy, pb.out_xy)
+    dev.close()
+    if os.environ.get("RL_SKIP_SLOW"):
+        return
+    tr = rl.Track(center.reshape(nt, n, 2)[1], seg.reshape(nt, 2, m, 4)[1, 0], seg.reshape(nt, 2, m, 4)[1, 1], L[1])
+    _check(first[3], tr, MT, cfg, ("config5", 1, MT))

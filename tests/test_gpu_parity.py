@@ -171,9 +171,13 @@ def test_errors_and_unsupported(ctx, goldens):
     with pytest.raises(rl.RacelineError) as e:
         rl.solve_batch([tr], [rl.Config()], [(0, 0, 7)], ctx=ctx)
     assert e.value.status == rl.RL_ERR_ARG
-    big = rl.Track(np.zeros((5000, 2)), tr.inner_seg, tr.outer_seg, 9000.0)       # N > 4096: no kernel covers it yet
+    big = rl.Track(np.zeros((20000, 2)), tr.inner_seg, tr.outer_seg, 36000.0)    # N > 16384: beyond one portable cluster
     with pytest.raises(rl.RacelineError) as e:
         rl.solve_batch([big], [rl.Config()], [(0, 0, MC)], ctx=ctx)
+    assert e.value.status == rl.RL_ERR_UNSUPPORTED
+    big_open = rl.Track(np.zeros((5000, 2)), tr.inner_seg, tr.outer_seg, 9000.0, closed=False)   # open long tracks: not covered
+    with pytest.raises(rl.RacelineError) as e:
+        rl.solve_batch([big_open], [rl.Config()], [(0, 0, MC)], ctx=ctx)
     assert e.value.status == rl.RL_ERR_UNSUPPORTED
     assert lib().rl_solve_batch(ctx._h, None, None) == rl.RL_ERR_ARG
     # the context is still usable after errors

@@ -36,6 +36,8 @@ sys.path.insert(0, ROOT)
 N_SAMPLES = 2048
 M_PER_RING = 931
 SEED_BASE = 0xB200
+WORKLOAD = ("BASELINE configs[3]: synthetic closed tracks, N=2048 samples, M=931 cones/ring, default Config, "
+            "min-curv + min-time per track")
 METRIC = "raceline_solves_per_s"
 UNIT = "solves/s"
 
@@ -225,6 +227,9 @@ def bench_ours(args):
     launches = dev.launches_per_solve * args.steps
     flops_step = algorithmic_flops(pb.out_stats, pb.n_jobs, jobs[:, 2])
     lap_mean = float(np.mean([pb.out_stats[j].lap_time for j in range(1, pb.n_jobs, 2)]))
+    diag = {"exist_scans_per_job": float(np.mean([pb.out_stats[j].exist_scans for j in range(pb.n_jobs)])),
+            "ray_tests_per_job": float(np.mean([pb.out_stats[j].ray_tests for j in range(pb.n_jobs)])),
+            "vpass_rounds_per_mt_job": float(np.mean([pb.out_stats[j].vpass_rounds for j in range(1, pb.n_jobs, 2)]))}
 
     # ---- end to end: pinned host buffers through rl_solve_batch ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -263,17 +268,18 @@ def bench_ours(args):
     except Exception:
         pass
 
+    if N_SAMPLES != 2048:
+        traffic = None     # the committed ncu capture is of the N=2048 kernel
     out = None
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[3]: synthetic closed tracks, N=2048 samples, M=931 cones/ring, default Config, "
-                                   "min-curv + min-time per track", "tracks_per_gpu": tpg, "tracks_total": total_solves_step,
+            "config": {"workload": WORKLOAD, "tracks_per_gpu": tpg, "tracks_total": total_solves_step,
                        "n_samples": N_SAMPLES, "m_per_ring": M_PER_RING, "seed_base": SEED_BASE,
                        "l2": "inputs larger than L2 (%.0f MB per GPU)" % (pb.h2d_bytes / 1e6), "parallelism": f"dp{world}",
-                       "mean_lap_s": lap_mean, "gen_s": round(gen_s, 2)},
+                       "mean_lap_s": lap_mean, "gen_s": round(gen_s, 2), "kernel_diag": diag},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
                          "peak_source": "DFMA throughput measured in this run (rl_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
@@ -318,8 +324,7 @@ def bench_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[3]: synthetic closed tracks, N=2048 samples, M=931 cones/ring, default Config, "
-                               "min-curv + min-time per track", "n_samples": N_SAMPLES, "m_per_ring": M_PER_RING,
+        "config": {"workload": WORKLOAD, "n_samples": N_SAMPLES, "m_per_ring": M_PER_RING,
                    "seed_base": SEED_BASE, "tracks_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(len(cores), per_step), "kind": kind,
                          "sample": f"{per_step} tracks per step (the first tracks of the GPU batch), one pinned process per core"},
@@ -340,7 +345,21 @@ def main():
     ap.add_argument("--cpu-tracks-per-core", type=int, default=4)
     ap.add_argument("--ref-tracks-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-long", action="store_true")
+    ap.add_argument("--workload", default="n2048", choices=["n2048", "n16384"],
+                    help="n2048 = BASELINE configs[3] (the metric's configuration); n16384 = configs[4], the long-track stress "
+                         "(one 8-CTA cluster per job; 1024 tracks per GPU = 8192 at 8 GPUs)")
     args = ap.parse_args()
+    global N_SAMPLES, M_PER_RING, WORKLOAD
+    if args.workload == "n16384":
+        N_SAMPLES, M_PER_RING = 16384, 7447
+        WORKLOAD = ("BASELINE configs[4]: long-track stress, synthetic closed tracks, N=16384 samples, M=7447 cones/ring, "
+                    "default Config, min-curv + min-time per track, one 8-CTA cluster per job")
+        if args.tracks_per_gpu == 8192:
+            args.tracks_per_gpu = 1024
+        if not args.cpu_baseline_long:
+            args.no_cpu_baseline = True      # ~3 core-minutes per solve on the CPU: opt in with --cpu-baseline-long
+        args.cpu_tracks_per_core = 1
     if args.impl == "reference":
         bench_reference(args)
     else:

@@ -102,7 +102,7 @@ typedef struct rl_job_stats {
     int32_t backtracks;   /* Armijo step halvings, all outers (main.cpp:737)    */
     int32_t evals;        /* cost/grad evaluations (main.cpp:724, 732)          */
     int32_t vpass_rounds; /* device diagnostic: relaxation rounds of the v(s) passes */
-    int32_t reserved;
+    int32_t exist_scans;  /* device diagnostic: full "does this ray hit the ring at all" searches (main.cpp:696 semantics) */
     int64_t ray_tests;    /* device diagnostic: exact FP64 ray/segment tests run */
     double lap_time;      /* min-time: final predicted lap (main.cpp:1047); else 0 */
     double J0[RL_MAX_OUTER_LOG];        /* cost at alpha=0 per outer (main.cpp:724, 997)  */

@@ -40,7 +40,7 @@ class RlJob(C.Structure):
 class RlJobStats(C.Structure):
     _fields_ = [
         ("status", _I), ("n", _I), ("outer_done", _I), ("accepted", _I), ("backtracks", _I), ("evals", _I),
-        ("vpass_rounds", _I), ("reserved", _I), ("ray_tests", C.c_int64), ("lap_time", _D),
+        ("vpass_rounds", _I), ("exist_scans", _I), ("ray_tests", C.c_int64), ("lap_time", _D),
         ("J0", _D * RL_MAX_OUTER_LOG), ("Jend", _D * RL_MAX_OUTER_LOG), ("lap_outer", _D * RL_MAX_OUTER_LOG),
         ("acc_outer", _I * RL_MAX_OUTER_LOG), ("bt_outer", _I * RL_MAX_OUTER_LOG),
     ]

@@ -559,7 +559,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
         sFlag[0] = 0; sFlag[1] = 0; sFlag[2] = 0;
         if (cl.rank == 0) {
             st->status = RL_OK; st->n = N; st->outer_done = 0; st->accepted = 0; st->backtracks = 0; st->evals = 0;
-            st->vpass_rounds = 0; st->reserved = 0; st->ray_tests = 0; st->lap_time = 0.0;
+            st->vpass_rounds = 0; st->exist_scans = 0; st->ray_tests = 0; st->lap_time = 0.0;
             for (int o = 0; o < RL_MAX_OUTER_LOG; ++o) {
                 st->J0[o] = 0.0; st->Jend[o] = 0.0; st->lap_outer[o] = 0.0; st->acc_outer[o] = 0; st->bt_outer[o] = 0;
             }

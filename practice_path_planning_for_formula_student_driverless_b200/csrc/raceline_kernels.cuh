@@ -113,19 +113,33 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 // Deterministic block-wide sum of two values; the result is bit-identical in every thread.
 // Contains exactly one block barrier (a warp barrier for single-warp CTAs).
+// Warp stage: ONE packed butterfly for both values (after the first exchange lanes 0-15 carry `a`, lanes 16-31 carry
+// `b`): 5 dependent shuffle steps instead of 10.  Block stage: the per-warp pairs are added as a balanced tree, so
+// the adds of one level are independent (a serial `+=` chain costs one FP64 latency per warp).
 template <int T>
 __device__ __forceinline__ void block_sum2(double& a, double& b, double* sred, int lane, int warp)
 {
-    a = warp_sum(a);
-    b = warp_sum(b);
-    if (T > 32) {
-        if (lane == 0) { sred[2 * warp] = a; sred[2 * warp + 1] = b; }
-        __syncthreads();
-        double sa = 0.0, sb = 0.0;
+    const bool hi_half = (lane & 16) != 0;
+    const double keep = hi_half ? b : a, send = hi_half ? a : b;
+    double v = keep + __shfl_xor_sync(kFull, send, 16);
 #pragma unroll
-        for (int w = 0; w < T / 32; ++w) { sa += sred[2 * w]; sb += sred[2 * w + 1]; }
-        a = sa; b = sb;
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if (T > 32) {
+        constexpr int NW = T / 32;
+        if ((lane & 15) == 0) sred[2 * warp + (lane >> 4)] = v;
+        __syncthreads();
+        double2 e[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) e[w] = reinterpret_cast<const double2*>(sred)[w];
+#pragma unroll
+        for (int n = NW / 2; n > 0; n >>= 1) {
+#pragma unroll
+            for (int w = 0; w < n; ++w) { e[w].x = e[2 * w].x + e[2 * w + 1].x; e[w].y = e[2 * w].y + e[2 * w + 1].y; }
+        }
+        a = e[0].x; b = e[0].y;
     } else {
+        a = __shfl_sync(kFull, v, 0);
+        b = __shfl_sync(kFull, v, 16);
         __syncwarp();
     }
 }
@@ -1180,12 +1194,158 @@ __device__ __noinline__ float clearance_scan(const RayTile& tl_in, float px, flo
     return best;
 }
 
+// ---- existence certificates ---------------------------------------------------------------------------------
+// "Does the ray that points AWAY from a ring hit that ring anywhere?" decides whether safe_ray falls back to the
+// point-ring distance (main.cpp:696), and the answer is needed again at every corridor build for about half the
+// samples.  It is stable between builds, so a full search leaves a certificate per sample (16 bytes, kept in the
+// job's heading and curvature rows until the final geometry pass overwrites them):
+//   FAR(f)      the ray hit segment f: re-test that one segment exactly; a hit anywhere is a hit;
+//   CONE(A,d,c) the ray missed: the ring has no point inside the cone with apex A (on the ray's line, between the ring
+//               behind the sample and the sample), axis d (the ray direction then) and cos(half-angle) = c.  A later ray
+//               whose origin lies in the cone and whose direction is within the half-angle of d stays inside the
+//               (convex) cone: still a miss.
+// A certificate that does not apply falls back to the full search (and is rebuilt), so results never change.
+constexpr unsigned kCertNone = 0u, kCertFar = 1u, kCertCone = 2u, kCertNoCone = 3u;
+
+// can the box be skipped: no point of it is seen from the apex under a smaller angle to the axis than acos(cbest)
+__device__ __forceinline__ bool cone_prune(const float4 bx, float ax, float ay, float dx, float dy, float cbest)
+{
+    const float cx = bx.x - ax, cy = bx.y - ay;
+    const float R2 = bx.z * bx.z + bx.w * bx.w;       // boxes are already inflated by the FP32 margin
+    const float r2 = cx * cx + cy * cy;
+    if (r2 <= R2 * 1.001f) return false;              // apex inside (or at) the box's disk
+    const float ir = rsqrtf(r2);
+    const float ct = (cx * dx + cy * dy) * ir, so = sqrtf(R2) * ir * (1.f + 1e-6f);
+    const float co = sqrtf(fmaxf(0.f, 1.f - so * so));
+    if (ct >= co - 1e-5f) return false;               // the axis passes through (or close to) the disk
+    const float st = sqrtf(fmaxf(0.f, 1.f - ct * ct));
+    return ct * co + st * so + 1e-5f <= cbest;        // cos(theta_c - omega), rounded up
+}
+
+// largest cosine of the angle between the unit axis (dx,dy) and any point of the ring seen from the apex (ax,ay)
+// (tile coordinates), rounded UP.  Returns 2 when no cone exists (a segment crosses the axis ahead of the apex, or
+// FP32 cannot tell).  Along a segment that does not cross the forward axis the angle is extremal at its end points.
+__device__ __noinline__ float cone_scan(const RayTile& tl_in, float ax, float ay, float dx, float dy, float m, int hint)
+{
+    const RayTile tl = tl_in;
+    const float e = 2.f * m + 1e-6f;
+    // a cone wider than 30 degrees is never needed (and never wider than 90: only a CONVEX cone keeps
+    // origin + t*direction inside), so everything outside the 30-degree cone is skipped from the start
+    float cbest = 0.8660254f;
+    int sb0 = hint / SU;
+    if (sb0 >= tl.nsup) sb0 = 0;
+    for (int q = 0; q < tl.nsup; ++q) {
+        int sb = sb0 + q;
+        if (sb >= tl.nsup) sb -= tl.nsup;
+        if (cone_prune(tl.supF[sb], ax, ay, dx, dy, cbest)) continue;
+        const int b1 = min(tl.nblk, sb * SU + SU);
+        for (int b = sb * SU; b < b1; ++b) {
+            if (cone_prune(tl.boxF[b], ax, ay, dx, dy, cbest)) continue;
+            const int s1 = min(tl.nt, b * SB + SB);
+            for (int s = b * SB; s < s1; ++s) {
+                const float4 f = tl.segF[s];
+                const float ux = f.x - ax, uy = f.y - ay, wx = f.z - ax, wy = f.w - ay;
+                const float t1 = ux * dx + uy * dy, c1 = ux * dy - uy * dx;    // along / across the axis
+                const float t2 = wx * dx + wy * dy, c2 = wx * dy - wy * dx;
+                const float r1 = sqrtf(ux * ux + uy * uy), r2 = sqrtf(wx * wx + wy * wy);
+                if (r1 <= 8.f * e || r2 <= 8.f * e) return 2.f;               // apex (almost) on the ring
+                if (!((c1 > e && c2 > e) || (c1 < -e && c2 < -e))) {
+                    // the segment meets the axis LINE: fine only if it does so clearly behind the apex
+                    const float ds = c1 - c2;
+                    if (fabsf(ds) < 16.f * e) return 2.f;
+                    const float tc = t1 + (t2 - t1) * __fdividef(c1, ds);
+                    if (tc > -e * (4.f + 2.f * __fdividef(fabsf(t2 - t1), fabsf(ds)))) return 2.f;
+                }
+                const float k1 = __fdividef(t1 + e, r1) + 2e-6f, k2 = __fdividef(t2 + e, r2) + 2e-6f;
+                cbest = fmaxf(cbest, fmaxf(k1, k2));
+            }
+        }
+    }
+    return cbest;
+}
+
+struct ExQuery {
+    double2 P; double nx, ny, cx0, cy0, ox, oy, guard, toward;
+    unsigned long long cert, apex;      // the sample's certificate words (loaded early by the caller)
+    float px, py, m;
+    int j0, ring, dir, i, mr;
+};
+// unit axis of a CONE certificate from its two 16-bit components (the same bits at creation and at every check)
+__device__ __forceinline__ void cert_axis(unsigned w1, double& dx, double& dy)
+{
+    const float fx = (float)(short)(w1 & 0xffffu), fy = (float)(short)(w1 >> 16);
+    const float rs = rsqrtf(fmaxf(1.f, fx * fx + fy * fy));
+    dx = (double)(fx * rs); dy = (double)(fy * rs);
+}
+// does the ray of direction `dir` (0: +n, 1: -n) from the sample hit the ring at all?  (certificates: see above)
+// certificate word: w0 = state[1:0] | ring[2] | dir[3] | cos(half-angle) [31:16];  w1 = cone axis (2 x int16) or the
+// far-hit segment; apex word: the cone apex relative to the centre-line sample, 2 floats.
+__device__ __noinline__ bool far_hit_exists(const RayTile& tl, const ExQuery& qy, unsigned long long* __restrict__ gcert,
+                                            unsigned long long* __restrict__ gapex, long long& tests_io, int& scans_io)
+{
+    const double INF = dinf();
+    const int i = qy.i, dir = qy.dir;
+    const double2 Pc = qy.P;
+    const double nx = qy.nx, ny = qy.ny;
+    const unsigned w0 = (unsigned)qy.cert, w1 = (unsigned)(qy.cert >> 32);
+    const unsigned key = ((unsigned)qy.ring << 2) | ((unsigned)dir << 3);
+    const bool mine = ((w0 & 0xCu) == key) && ((w0 & 3u) != kCertNone);
+    const double sg = dir ? -1.0 : 1.0;
+    long long tests = 0;
+    if (mine && (w0 & 3u) == kCertFar) {
+        const int f = (int)w1;
+        if (f < qy.mr) {
+            double tp = INF, tn = INF; int s_p = -1, s_n = -1;
+            seg_hit(tl.segD + 4 * f, Pc, nx, ny, tp, tn, f, s_p, s_n, tests);
+            if ((dir ? tn : tp) < INF) { tests_io += tests; return true; }
+        }
+    } else if (mine && (w0 & 3u) == kCertCone) {
+        double d0x, d0y;
+        cert_axis(w1, d0x, d0y);
+        const double cc = (double)(w0 >> 16) * (1.0 / 32767.0) - 1.0 + 2e-6;
+        const double ux = (Pc.x - qy.cx0) - (double)__uint_as_float((unsigned)qy.apex);
+        const double uy = (Pc.y - qy.cy0) - (double)__uint_as_float((unsigned)(qy.apex >> 32));
+        if (ux * d0x + uy * d0y >= sqrt(ux * ux + uy * uy) * cc && sg * (nx * d0x + ny * d0y) >= cc) return false;
+    }
+    // ---- no certificate applies: full search, then leave a certificate for the next builds ----
+    double ubp = INF, ubn = INF, pr = INF, nr = INF;
+    const int hs = ray_scan(tl, Pc, nx, ny, qy.px, qy.py, (float)nx, (float)ny, qy.m, qy.j0 / SB, dir == 0, dir == 1, true, ubp, ubn, pr, nr, tests);
+    tests_io += tests;
+    ++scans_io;
+    const bool ex = dir ? (nr < INF) : (pr < INF);
+    if (!mine && (w0 & 3u) != kCertNone) {
+        // the slot serves another (ring, direction) of this sample: leave it alone
+    } else if (ex) {
+        gcert[i] = ((unsigned long long)(unsigned)hs << 32) | (unsigned long long)(key | kCertFar);
+    } else if (!(mine && (w0 & 3u) == kCertNoCone)) {
+        // a miss: look for a ring-free cone about the current ray, apex on the ray's line between the ring (behind the
+        // sample) and every later path position (the path keeps at least `guard` away from the ring)
+        const int qx = __double2int_rn(sg * nx * 32767.0), qyy = __double2int_rn(sg * ny * 32767.0);
+        const unsigned nw1 = ((unsigned)qx & 0xffffu) | ((unsigned)qyy << 16);
+        double d0x, d0y;
+        cert_axis(nw1, d0x, d0y);
+        const double back = (qy.toward < INF) ? fmax(0.0, qy.toward - fmax(0.05, 0.5 * qy.guard)) : 0.0;
+        const float oxf = (float)((Pc.x - qy.cx0) - back * d0x), oyf = (float)((Pc.y - qy.cy0) - back * d0y);
+        const double axd = qy.cx0 + (double)oxf, ayd = qy.cy0 + (double)oyf;     // the apex, exactly as every later check sees it
+        const float cb = cone_scan(tl, (float)(axd - qy.ox), (float)(ayd - qy.oy), (float)d0x, (float)d0y, qy.m, qy.j0 / SB);
+        unsigned nw0 = key | kCertNoCone;
+        if (cb < 0.9995f) {
+            const unsigned qc = (unsigned)ceilf((cb + 1.f) * 32767.f + 0.5f);
+            if (qc < 65535u) nw0 = key | kCertCone | (qc << 16);
+        }
+        gcert[i] = ((unsigned long long)nw1 << 32) | (unsigned long long)nw0;
+        gapex[i] = ((unsigned long long)__float_as_uint(oyf) << 32) | (unsigned long long)__float_as_uint(oxf);
+    }
+    return ex;
+}
+
 template <int T, int K>
 __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double2* sP, double* sB, uint64_t* mbar, uint32_t& bar_phase,
                                                     int* sMisc, unsigned* sHint, unsigned short* sClr, bool first, bool parity_ok, bool closed,
                                                     const double* __restrict__ gseg, const double* __restrict__ gcenter,
+                                                    unsigned long long* __restrict__ gcert, unsigned long long* __restrict__ gapex,
                                                     long long segI0, long long segO0, long long segE,
-                                                    double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests)
+                                                    double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests, int& ex_scans)
 {
     constexpr int NP = T * K;
     const int N = pt.N, tid = pt.tid;
@@ -1195,7 +1355,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
     double bp[K], bn[K], dfp[K], dfn[K];
     float lbp[K], lbn[K];          // "a hit exists on some ring, value unknown but >= lb" (parity certificate)
     unsigned flagged = 0u;         // bit j: sample j must be redone by the general search
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < K; ++j) { bp[j] = INF; bn[j] = INF; dfp[j] = INF; dfn[j] = INF; lbp[j] = FINF; lbn[j] = FINF; }
     // ring order: the ring the samples lie INSIDE of goes first (its far hits are settled by parity, and the
     // bounds it produces let the other ring skip most existence questions)
@@ -1205,7 +1365,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
             if (!block_or<T>(flagged != 0u)) break;
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < K; ++j)
                 if ((flagged >> j) & 1u) { bp[j] = INF; bn[j] = INF; dfp[j] = INF; dfn[j] = INF; lbp[j] = FINF; lbn[j] = FINF; }
         }
@@ -1214,7 +1374,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
             const long long base = ring ? segO0 : segI0;
             const int mr = (int)(ring ? (segE - segO0) : (segO0 - segI0));
             if (mr == 0) {   // safe_ray on an empty ring returns 0 (main.cpp:696-698)
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < K; ++j) { dfp[j] = 0.0; dfn[j] = 0.0; }
                 continue;
             }
@@ -1222,7 +1382,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
             bool chain;   // the ring's segments form a closed chain
             const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, chain);
             const int hshift = 13 * ring;
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < K; ++j) {
                 const int i = tid + j * T;
                 if (i >= N) continue;
@@ -1239,6 +1399,8 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                 const bool inside = parity_ok && chain && ((hw >> (26 + ring)) & 1u);
                 // displacement from the centre-line position the clearance refers to
                 const double cx0 = gcenter[2 * i], cy0 = gcenter[2 * i + 1];
+                unsigned long long cert_w = 0ull, apex_w = 0ull;
+                if (!first) { cert_w = gcert[i]; apex_w = gapex[i]; }   // issued early: only the existence branch reads them
                 const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
                 float Rc = 0.f;
                 if (pass == 0 && !first && ((hw >> (28 + ring)) & 1u)) {
@@ -1296,9 +1458,13 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                             }
                             if (dist_r >= bnd) ex = true;                // irrelevant either way: treat as settled
                             else {
-                                double ubp = INF, ubn = INF, pr = INF, nr = INF;
-                                ray_scan(tl, Pc, nx, ny, px, py, fnx, fny, m, j0 / SB, dir == 0, dir == 1, true, ubp, ubn, pr, nr, ray_tests);
-                                ex = dir ? (nr < INF) : (pr < INF);
+                                // ---- existence of a far hit: certificate first, full search otherwise ----
+                                ExQuery qy;
+                                qy.P = Pc; qy.nx = nx; qy.ny = ny; qy.px = px; qy.py = py; qy.m = m; qy.j0 = j0; qy.ring = ring; qy.dir = dir;
+                                qy.i = i; qy.mr = mr; qy.cx0 = cx0; qy.cy0 = cy0; qy.ox = org.x; qy.oy = org.y;
+                                qy.guard = guard; qy.toward = dir ? pos_r : neg_r; qy.cert = cert_w; qy.apex = apex_w;
+                                ex = far_hit_exists(tl, qy, gcert, gapex, ray_tests, ex_scans);
+                                cert_w = gcert[i]; apex_w = gapex[i];     // the other direction of this ring may ask next
                             }
                         }
                     }
@@ -1340,7 +1506,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
         }
         if (pass == 0) {
             // a pending "exists, value >= lb" that could undercut the minimum found: redo that sample in full
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < K; ++j) {
                 if (tid + j * T >= N) continue;
                 if ((double)lbp[j] < fmin(bp[j], dfp[j]) || (double)lbn[j] < fmin(bn[j], dfn[j])) flagged |= (1u << j);
@@ -1351,7 +1517,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
     block_sync<T>();
     double* sLoS = sB;
     double* sHiS = sB + NP;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < K; ++j) {
         const int i = tid + j * T;
         if (i < N) {
@@ -1427,7 +1593,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         st->status = RL_OK; st->n = N; st->outer_done = 0; st->accepted = 0; st->backtracks = 0; st->evals = 0;
-        st->vpass_rounds = 0; st->reserved = 0; st->ray_tests = 0; st->lap_time = 0.0;
+        st->vpass_rounds = 0; st->exist_scans = 0; st->ray_tests = 0; st->lap_time = 0.0;
         for (int o = 0; o < RL_MAX_OUTER_LOG; ++o) {
             st->J0[o] = 0.0; st->Jend[o] = 0.0; st->lap_outer[o] = 0.0; st->acc_outer[o] = 0; st->bt_outer[o] = 0;
         }
@@ -1460,7 +1626,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     const double inv2h = 1.0 / (2 * h), invh2 = 1.0 / (h * h);          // DiffOps, main.cpp:547
     const double lamJ = C.lambda_smooth * inv2h * inv2h;
     long long ray_tests = 0;
-    int vrounds = 0, ph = 0;
+    int vrounds = 0, ph = 0, ex_scans = 0;
     int acc_total = 0, bt_total = 0, ev_total = 0;
     const int max_outer = C.max_outer_iters;
 
@@ -1470,9 +1636,13 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     const bool fast_rays = (segO0 - segI0 <= CAPF) && (segE - segO0 <= CAPF) && (CAPF < 8192);
     const bool parity_ok = (C.veh_width_arg * 0.5 + C.safety_margin_m >= 0.0) && (C.veh_width_m * 0.5 + C.safety_margin_m >= 0.0);
     for (int i = tid; i < NP; i += T) { sHint[i] = 0u; sClr[i] = 0; }
+    // per-sample existence certificates (see corridor_build_fast) live in the heading and curvature rows until the final geometry pass
+    unsigned long long* gcert = reinterpret_cast<unsigned long long*>(B.heading + row0);
+    unsigned long long* gapex = reinterpret_cast<unsigned long long*>(B.curvature + row0);
+    for (int i = tid; i < N; i += T) gcert[i] = 0ull;
     if (fast_rays)
-        corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, true, parity_ok, closed, B.seg, B.center_xy + 2 * s0, segI0, segO0, segE,
-                                  C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+        corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, true, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex, segI0, segO0, segE,
+                                  C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests, ex_scans);
     else
         corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                    C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
@@ -1626,8 +1796,8 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
         block_sync<T>();
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
         if (fast_rays)
-            corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, segI0, segO0, segE,
-                                      C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+            corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex, segI0, segO0, segE,
+                                      C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests, ex_scans);
         else
             corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                        C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
@@ -1675,12 +1845,12 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
 
     // counters
     {
-        double rt = (double)ray_tests, dz = 0.0;
-        block_sum2<T>(rt, dz, sRed + ph * 32, pt.lane, pt.warp);
+        double rt = (double)ray_tests, es = (double)ex_scans;
+        block_sum2<T>(rt, es, sRed + ph * 32, pt.lane, pt.warp);
         ph ^= 1;
         if (tid == 0) {
             st->outer_done = max_outer; st->accepted = acc_total; st->backtracks = bt_total; st->evals = ev_total;
-            st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap;
+            st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap; st->exist_scans = (int)es;
         }
     }
 }

@@ -19,6 +19,7 @@ constexpr int kMaxChunks = 4;
 
 struct rl_ctx {
     int device = 0;
+    int n_sm = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;   // own_stream or the caller's
     std::string err;
@@ -54,7 +55,7 @@ struct DevArr {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct ClassList { int cls; int mode; int begin; int count; int chunk; };
+struct ClassList { int cls; int mode; int begin; int count; int chunk; int item_begin; int n_items; };
 
 }  // namespace
 
@@ -65,7 +66,7 @@ struct rl_batch {
     // device inputs
     DevArr<long long> d_samp_off, d_seg_off, d_job_off;
     DevArr<double> d_center, d_seg, d_L;
-    DevArr<int> d_closed, d_joblist;
+    DevArr<int> d_closed, d_joblist, d_itemoff;
     DevArr<rl_params> d_params;
     DevArr<rl_job> d_jobs;
     // device outputs
@@ -73,7 +74,7 @@ struct rl_batch {
     DevArr<rl_job_stats> d_stats;
     // host-side plan
     std::vector<long long> job_off;
-    std::vector<int> joblist;
+    std::vector<int> joblist, itemoff;
     std::vector<ClassList> lists;
     std::vector<std::pair<int, int>> skipped;   // (job, status) for jobs no kernel covers
     int n_chunks = 1;
@@ -82,13 +83,15 @@ struct rl_batch {
     void release()
     {
         d_samp_off.release(); d_seg_off.release(); d_job_off.release(); d_center.release(); d_seg.release();
-        d_L.release(); d_closed.release(); d_joblist.release(); d_params.release(); d_jobs.release();
+        d_L.release(); d_closed.release(); d_joblist.release(); d_itemoff.release(); d_params.release(); d_jobs.release();
         d_xy.release(); d_heading.release(); d_curv.release(); d_atot.release(); d_alast.release();
         d_v.release(); d_ax.release(); d_stats.release();
     }
 };
 
 namespace {
+
+int c_sm(const rl_batch* b);
 
 int fail(rl_ctx* c, int status, const std::string& msg)
 {
@@ -145,43 +148,54 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
     }
     b->rows = b->job_off[d->n_jobs];
 
-    // job lists per chunk and (class, exact); min-time jobs first (they run longer: better tail)
-    b->lists.clear(); b->joblist.clear(); b->skipped.clear();
+    // job lists per chunk and (class, mode), in batch order; consecutive jobs on the same track form one ITEM (one CTA
+    // works through the chain and keeps what it learnt about the track's corridor), as long as enough items remain to
+    // fill the device several times over
+    b->lists.clear(); b->joblist.clear(); b->itemoff.clear(); b->skipped.clear();
     n_chunks = std::max(1, std::min(n_chunks, std::min(kMaxChunks, d->n_jobs)));
     b->n_chunks = n_chunks;
     b->chunk_job0.assign((size_t)n_chunks + 1, 0);
     b->chunk_tmax.assign((size_t)n_chunks, -1);
+    int max_chain = 8;
+    if (const char* e = std::getenv("RL_MAX_CHAIN")) max_chain = std::max(1, std::atoi(e));   // tuning / test knob
     for (int c = 0; c <= n_chunks; ++c) b->chunk_job0[c] = (int)(((long long)d->n_jobs * c) / n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
         std::vector<std::vector<int>> bucket(rl::kNumClasses * 3);
         std::vector<std::vector<int>> cbucket(2 * (rl::kMaxClusterSize + 1));   // [cs][mode] cluster launches
         int force_cs = 0;
         if (const char* e = std::getenv("RL_FORCE_CLUSTER")) force_cs = std::atoi(e);   // test hook: cluster kernel on shorter tracks
-        for (int pass = 0; pass < 2; ++pass) {
-            for (int j = b->chunk_job0[c]; j < b->chunk_job0[c + 1]; ++j) {
-                const rl_job& jb = d->jobs[j];
-                if ((pass == 0) != (jb.stage == RL_STAGE_MINTIME)) continue;
-                const int t = jb.track;
-                b->chunk_tmax[c] = std::max(b->chunk_tmax[c], t);
-                const long long n = d->samp_off[t + 1] - d->samp_off[t];
-                if (n == 0) { b->skipped.push_back({j, RL_OK}); continue; }   // empty Result, main.cpp:689 / 912
-                const int cls = rl::class_for_n((int)n);
-                const int cs = (d->track_closed[t] && (cls < 0 || force_cs > 0)) ? rl::cluster_size_for_n(n, force_cs) : 0;
-                if (cs > 0) { cbucket[2 * cs + (n == 2048ll * cs ? 1 : 0)].push_back(j); continue; }
-                if (cls < 0) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
-                const bool exact = (n == (long long)rl::kClasses[cls].T * rl::kClasses[cls].K);
-                const int mode = !d->track_closed[t] ? 2 : (exact ? 1 : 0);   // open | closed exact-fit | closed ragged
-                bucket[cls * 3 + mode].push_back(j);
-            }
+        for (int j = b->chunk_job0[c]; j < b->chunk_job0[c + 1]; ++j) {
+            const rl_job& jb = d->jobs[j];
+            const int t = jb.track;
+            b->chunk_tmax[c] = std::max(b->chunk_tmax[c], t);
+            const long long n = d->samp_off[t + 1] - d->samp_off[t];
+            if (n == 0) { b->skipped.push_back({j, RL_OK}); continue; }   // empty Result, main.cpp:689 / 912
+            const int cls = rl::class_for_n((int)n);
+            const int cs = (d->track_closed[t] && (cls < 0 || force_cs > 0)) ? rl::cluster_size_for_n(n, force_cs) : 0;
+            if (cs > 0) { cbucket[2 * cs + (n == 2048ll * cs ? 1 : 0)].push_back(j); continue; }
+            if (cls < 0) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
+            const bool exact = (n == (long long)rl::kClasses[cls].T * rl::kClasses[cls].K);
+            const int mode = !d->track_closed[t] ? 2 : (exact ? 1 : 0);   // open | closed exact-fit | closed ragged
+            bucket[cls * 3 + mode].push_back(j);
         }
         for (int k = 0; k < rl::kNumClasses * 3; ++k) {
             if (bucket[k].empty()) continue;
-            b->lists.push_back({k / 3, k % 3, (int)b->joblist.size(), (int)bucket[k].size(), c});
+            const int slots = std::max(1, c_sm(b) * rl::ctas_per_sm(k / 3));
+            const int chain = std::max(1, std::min(max_chain, (int)(bucket[k].size() / (size_t)(6 * slots))));
+            ClassList l = {k / 3, k % 3, (int)b->joblist.size(), (int)bucket[k].size(), c, (int)b->itemoff.size(), 0};
+            int run = 0, last_t = -1;
+            for (size_t q = 0; q < bucket[k].size(); ++q) {
+                const int t = d->jobs[bucket[k][q]].track;
+                if (q == 0 || t != last_t || run >= chain) { b->itemoff.push_back((int)q); ++l.n_items; run = 0; }
+                last_t = t; ++run;
+            }
+            b->itemoff.push_back((int)bucket[k].size());
+            b->lists.push_back(l);
             b->joblist.insert(b->joblist.end(), bucket[k].begin(), bucket[k].end());
         }
         for (size_t k = 0; k < cbucket.size(); ++k) {
             if (cbucket[k].empty()) continue;
-            b->lists.push_back({rl::kClusterClassBase + (int)(k / 2), (int)(k % 2), (int)b->joblist.size(), (int)cbucket[k].size(), c});
+            b->lists.push_back({rl::kClusterClassBase + (int)(k / 2), (int)(k % 2), (int)b->joblist.size(), (int)cbucket[k].size(), c, 0, 0});
             b->joblist.insert(b->joblist.end(), cbucket[k].begin(), cbucket[k].end());
         }
     }
@@ -196,6 +210,7 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
     RL_CUDA(c, b->d_params.ensure((size_t)d->n_params));
     RL_CUDA(c, b->d_jobs.ensure((size_t)d->n_jobs));
     RL_CUDA(c, b->d_joblist.ensure(b->joblist.size() + 1));
+    RL_CUDA(c, b->d_itemoff.ensure(b->itemoff.size() + 1));
     const size_t rows = (size_t)b->rows + 2;
     RL_CUDA(c, b->d_xy.ensure(2 * rows));
     RL_CUDA(c, b->d_heading.ensure(rows));
@@ -210,6 +225,8 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
     RL_CUDA(c, cudaMemcpyAsync(b->d_job_off.p, b->job_off.data(), sizeof(long long) * b->job_off.size(), cudaMemcpyHostToDevice, s));
     if (!b->joblist.empty())
         RL_CUDA(c, cudaMemcpyAsync(b->d_joblist.p, b->joblist.data(), sizeof(int) * b->joblist.size(), cudaMemcpyHostToDevice, s));
+    if (!b->itemoff.empty())
+        RL_CUDA(c, cudaMemcpyAsync(b->d_itemoff.p, b->itemoff.data(), sizeof(int) * b->itemoff.size(), cudaMemcpyHostToDevice, s));
     RL_CUDA(c, cudaMemsetAsync(b->d_stats.p, 0, sizeof(rl_job_stats) * (size_t)d->n_jobs, s));
     for (auto& sk : b->skipped) {
         const int t = d->jobs[sk.first].track;
@@ -241,6 +258,8 @@ int upload_inputs(rl_batch* b, const rl_batch_desc* d)
     RL_CUDA(c, cudaMemcpyAsync(b->d_jobs.p, d->jobs, sizeof(rl_job) * (size_t)d->n_jobs, cudaMemcpyHostToDevice, s));
     return RL_OK;
 }
+
+int c_sm(const rl_batch* b) { return b->ctx ? b->ctx->n_sm : 148; }
 
 DevBatch dev_view(const rl_batch* b)
 {
@@ -300,12 +319,13 @@ rl_ctx* rl_create(int device, int* status)
 {
     int st = RL_OK;
     rl_ctx* c = nullptr;
-    int n = 0;
+    int n = 0, n_sm_probe = 148;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0 || device < 0 || device >= n) { cudaGetLastError(); st = RL_ERR_NODEVICE; }
     if (st == RL_OK) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) st = RL_ERR_NODEVICE;   // sm_100a only
+        else n_sm_probe = prop.multiProcessorCount;
     }
     if (st == RL_OK && cudaSetDevice(device) != cudaSuccess) st = RL_ERR_CUDA;
     if (st == RL_OK) {
@@ -314,6 +334,7 @@ rl_ctx* rl_create(int device, int* status)
     }
     if (st == RL_OK) {
         c->device = device;
+        c->n_sm = n_sm_probe;
         if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) st = RL_ERR_CUDA;
         c->stream = c->own_stream;
         if (st == RL_OK && rl::configure_kernels() != 0) st = RL_ERR_CUDA;
@@ -402,7 +423,7 @@ int rl_batch_solve(rl_batch* b)
     cudaSetDevice(c->device);
     const DevBatch B = dev_view(b);
     for (const ClassList& l : b->lists) {
-        const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, l.cls, l.mode, c->stream);
+        const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, b->d_itemoff.p + l.item_begin, l.n_items, l.cls, l.mode, c->stream);
         if (e != 0) return cuda_fail(c, (cudaError_t)e, "solve_kernel launch");
     }
     return RL_OK;
@@ -529,7 +550,7 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
         RL_CUDA(c, cudaStreamWaitEvent(sk, c->ev_in[k], 0));
         for (; li < b->lists.size() && b->lists[li].chunk == k; ++li) {
             const ClassList& l = b->lists[li];
-            const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, l.cls, l.mode, sk);
+            const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, b->d_itemoff.p + l.item_begin, l.n_items, l.cls, l.mode, sk);
             if (e != 0) return cuda_fail(c, (cudaError_t)e, "solve_kernel launch");
         }
         RL_CUDA(c, cudaEventRecord(c->ev_k[k], sk));

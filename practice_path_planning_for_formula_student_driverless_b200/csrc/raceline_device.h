@@ -76,8 +76,12 @@ int launch_solve_cluster(const DevBatch& B, const int* job_list, int n_list, int
 int configure_solve_cluster();
 
 // launches job_list[0..n_list) (indices into B.jobs) with the kernel of class `cls` and mode
-// 0 = closed track, 1 = closed track and every job has N == T*K, 2 = open track.  Returns a cudaError_t as int.
-int launch_solve(const DevBatch& B, const int* job_list, int n_list, int cls, int mode, void* stream);
+// 0 = closed track, 1 = closed track and every job has N == T*K, 2 = open track.  One CTA per ITEM: item k is the chain
+// job_list[item_off[k] .. item_off[k+1]) of jobs on the same track (item_off has n_items+1 entries, relative to
+// job_list).  Cluster classes take one job per cluster and ignore the items.  Returns a cudaError_t as int.
+int launch_solve(const DevBatch& B, const int* job_list, int n_list, const int* item_off, int n_items, int cls, int mode, void* stream);
+// CTAs of class `cls` one SM holds at a time (registers and shared memory)
+inline int ctas_per_sm(int cls) { const int np = kClasses[cls].T * kClasses[cls].K; return np >= 4096 ? 1 : (4096 / np > 16 ? 16 : 4096 / np); }
 int configure_kernels();  // sets max dynamic shared memory on every instantiation
 int launch_fp64_peak(double* d_out, int blocks, int threads, int iters, void* stream);
 

@@ -6,7 +6,7 @@
 namespace rl {
 
 #define RL_DECL(T)                                                                                   \
-    int launch_solve_##T(const DevBatch& B, const int* job_list, int n_list, int mode, void* stream); \
+    int launch_solve_##T(const DevBatch& B, const int* job_list, const int* item_off, int n_items, int mode, void* stream); \
     int configure_solve_##T();
 RL_DECL(32) RL_DECL(64) RL_DECL(128) RL_DECL(256) RL_DECL(512)
 #undef RL_DECL
@@ -37,16 +37,16 @@ int configure_kernels()
     return e;
 }
 
-int launch_solve(const DevBatch& B, const int* job_list, int n_list, int cls, int mode, void* stream)
+int launch_solve(const DevBatch& B, const int* job_list, int n_list, const int* item_off, int n_items, int cls, int mode, void* stream)
 {
     if (n_list <= 0) return 0;
     if (cls >= kClusterClassBase) return launch_solve_cluster(B, job_list, n_list, cls - kClusterClassBase, mode, stream);
     switch (kClasses[cls].T) {
-        case 32: return launch_solve_32(B, job_list, n_list, mode, stream);
-        case 64: return launch_solve_64(B, job_list, n_list, mode, stream);
-        case 128: return launch_solve_128(B, job_list, n_list, mode, stream);
-        case 256: return launch_solve_256(B, job_list, n_list, mode, stream);
-        case 512: return launch_solve_512(B, job_list, n_list, mode, stream);
+        case 32: return launch_solve_32(B, job_list, item_off, n_items, mode, stream);
+        case 64: return launch_solve_64(B, job_list, item_off, n_items, mode, stream);
+        case 128: return launch_solve_128(B, job_list, item_off, n_items, mode, stream);
+        case 256: return launch_solve_256(B, job_list, item_off, n_items, mode, stream);
+        case 512: return launch_solve_512(B, job_list, item_off, n_items, mode, stream);
         default: return (int)cudaErrorInvalidValue;
     }
 }

@@ -1001,7 +1001,7 @@ __device__ __noinline__ bool inside_ring(const RayTile& tl_in, double2 P, float 
 template <int T, int K>
 __device__ __forceinline__ float ring_tile_build(const Part& pt, double* sB, uint64_t* mbar, uint32_t& bar_phase, int* sMisc,
                                                  const double* __restrict__ gseg, int mr, double ox, double oy,
-                                                 RayTile& tl, bool& closed)
+                                                 RayTile& tl, bool& closed, bool* linked = nullptr)
 {
     constexpr int NP = T * K;
     constexpr int CAP = fast_tile_cap(NP);
@@ -1022,11 +1022,13 @@ __device__ __forceinline__ float ring_tile_build(const Part& pt, double* sB, uin
     mbar_wait(mbar, bar_phase); bar_phase ^= 1;
     block_sync<T>();
     float emax = 0.f;
-    int ok = 1;
+    int ok = 1, lk = 1;
     for (int s = tid; s < mr; s += T) {
         const double x0 = segD[4 * s], y0 = segD[4 * s + 1], x1 = segD[4 * s + 2], y1 = segD[4 * s + 3];
         const int sn = (s + 1 == mr) ? 0 : s + 1;
-        ok &= (x1 == segD[4 * sn] && y1 == segD[4 * sn + 1]);
+        const bool same = (x1 == segD[4 * sn] && y1 == segD[4 * sn + 1]);
+        ok &= same;
+        if (s + 1 < mr) lk &= same;
         float4 f;
         f.x = (float)(x0 - ox); f.y = (float)(y0 - oy); f.z = (float)(x1 - ox); f.w = (float)(y1 - oy);
         segF[s] = f;
@@ -1034,6 +1036,7 @@ __device__ __forceinline__ float ring_tile_build(const Part& pt, double* sB, uin
     }
     atomicMax(&sMisc[0], __float_as_int(emax));
     closed = (T == 32) ? (__all_sync(kFull, ok) != 0) : (__syncthreads_and(ok) != 0);
+    if (linked) *linked = (T == 32) ? (__all_sync(kFull, lk) != 0) : (__syncthreads_and(lk) != 0);
     block_sync<T>();
     // second pass: (x1,y1) -> (vx,vy) once every thread has compared the shared vertices
     for (int s = tid; s < mr; s += T) {
@@ -1345,9 +1348,10 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                                                     const double* __restrict__ gseg, const double* __restrict__ gcenter,
                                                     unsigned long long* __restrict__ gcert, unsigned long long* __restrict__ gapex,
                                                     long long segI0, long long segO0, long long segE,
-                                                    double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests, int& ex_scans)
+                                                    double guard, unsigned mask, double (&loc)[K], double (&hic)[K],
+                                                    long long& ray_tests, int& ex_scans)
 {
-    constexpr int NP = T * K;
+    // mask: bit j = sample tid + j*T is to be (re)built; results go to loc/hic[j] (CONSECUTIVE mapping), others untouched
     const int N = pt.N, tid = pt.tid;
     const double INF = dinf();
     const float FINF = __int_as_float(0x7f800000);
@@ -1379,13 +1383,17 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                 continue;
             }
             RayTile tl;
-            bool chain;   // the ring's segments form a closed chain
-            const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, chain);
+            bool chain, linked;   // the ring's segments form a closed chain / consecutive segments share their vertex
+            const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, chain, &linked);
+            if (first && tid == 0) {   // per-ring constants for corridor_update
+                sMisc[8 + ring] = (chain ? 1 : 0) | (linked ? 2 : 0);
+                sMisc[10 + ring] = __float_as_int(m0);
+            }
             const int hshift = 13 * ring;
 #pragma unroll 1
             for (int j = 0; j < K; ++j) {
                 const int i = tid + j * T;
-                if (i >= N) continue;
+                if (i >= N || !((mask >> j) & 1u)) continue;
                 if (pass == 1 && !((flagged >> j) & 1u)) continue;
                 const double2 Pc = sP[i];
                 double nx, ny;
@@ -1508,26 +1516,39 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
             // a pending "exists, value >= lb" that could undercut the minimum found: redo that sample in full
 #pragma unroll 1
             for (int j = 0; j < K; ++j) {
-                if (tid + j * T >= N) continue;
+                if (tid + j * T >= N || !((mask >> j) & 1u)) continue;
                 if ((double)lbp[j] < fmin(bp[j], dfp[j]) || (double)lbn[j] < fmin(bn[j], dfn[j])) flagged |= (1u << j);
             }
         }
     }
-    // hi/lo (main.cpp:704-710), handed to the blocked layout through region B
-    block_sync<T>();
-    double* sLoS = sB;
-    double* sHiS = sB + NP;
+    // hi/lo (main.cpp:704-710)
 #pragma unroll 1
     for (int j = 0; j < K; ++j) {
         const int i = tid + j * T;
-        if (i < N) {
+        if (i < N && ((mask >> j) & 1u)) {
             const double dpos = fmin(bp[j], dfp[j]), dneg = fmin(bn[j], dfn[j]);
             double hv = fmax(0.0, fmax(0.0, dpos) - guard);
             double lv = -fmax(0.0, fmax(0.0, dneg) - guard);
             if (!isfinite(hv)) hv = 0.0;
             if (!isfinite(lv)) lv = 0.0;
-            sHiS[i] = hv; sLoS[i] = lv;
+            hic[j] = hv; loc[j] = lv;
         }
+    }
+}
+
+// corridor bounds from the consecutive mapping (sample tid + j*T) to the blocked layout, through region B
+template <int T, int K>
+__device__ __forceinline__ void corridor_stage_out(const Part& pt, double* sB, const double (&loc)[K], const double (&hic)[K],
+                                                   double (&lo)[K], double (&hi)[K])
+{
+    constexpr int NP = T * K;
+    block_sync<T>();
+    double* sLoS = sB;
+    double* sHiS = sB + NP;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int i = pt.tid + j * T;
+        if (i < pt.N) { sHiS[i] = hic[j]; sLoS[i] = loc[j]; }
     }
     block_sync<T>();
 #pragma unroll
@@ -1538,10 +1559,170 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
     block_sync<T>();
 }
 
+// ---- corridor update, common case (every build after the first) ------------------------------------------------
+// When both rings are vertex chains, everything a sample needs in the steady state lies in the 2*kWin+1 segments around
+// its anchor on each ring plus its certificates:
+//   * a window hit with t <= Rc (Rc = stored clearance - displacement) is that ring's nearest hit;
+//   * a ring without a window hit has no hit nearer than Rc: it cannot undercut a certified hit b <= Rc of the other
+//     ring; whether it has a hit AT ALL only matters when its point distance D < b (main.cpp:696), and then parity
+//     (sample inside a closed ring) or the existence certificate answers;
+//   * D itself is the window distance when that is <= Rc, and otherwise D > Rc >= b does not matter.
+// Both rings' vertices (16 B each) sit in region B together, so one pass over the samples does both rings with scalars
+// only, no searches and no calls.  A sample any certificate fails for is FLAGGED and rebuilt by corridor_build_fast,
+// which also refreshes its anchors / clearances / certificates.  Returns the flag mask (bit j = sample tid + j*T).
+template <int T, int K>
+__device__ __forceinline__ unsigned corridor_update(const Part& pt, const double2* sP, double* sB, const int* sMisc,
+                                                    const unsigned* sHint, const unsigned short* sClr, bool parity_ok, bool closed,
+                                                    const double* __restrict__ gseg, const double* __restrict__ gcenter,
+                                                    const unsigned long long* __restrict__ gcert, const unsigned long long* __restrict__ gapex,
+                                                    long long segI0, long long segO0, long long segE, double guard,
+                                                    double (&loc)[K], double (&hic)[K], long long& ray_tests)
+{
+    const int N = pt.N, tid = pt.tid;
+    const double INF = dinf();
+    const int M0 = (int)(segO0 - segI0), M1 = (int)(segE - segO0);
+    double2* V0 = reinterpret_cast<double2*>(sB);
+    double2* V1 = V0 + (M0 + 1);
+    block_sync<T>();   // region B is free
+    for (int q = tid; q <= M0; q += T)
+        V0[q] = (q < M0) ? *reinterpret_cast<const double2*>(gseg + 4 * (segI0 + q)) : *reinterpret_cast<const double2*>(gseg + 4 * (segI0 + M0 - 1) + 2);
+    for (int q = tid; q <= M1; q += T)
+        V1[q] = (q < M1) ? *reinterpret_cast<const double2*>(gseg + 4 * (segO0 + q)) : *reinterpret_cast<const double2*>(gseg + 4 * (segO0 + M1 - 1) + 2);
+    const double2 org = sP[0];
+    const int rf0 = sMisc[8], rf1 = sMisc[9];
+    const float mr0 = __int_as_float(sMisc[10]), mr1 = __int_as_float(sMisc[11]);
+    block_sync<T>();
+    unsigned flagged = 0u;
+    // one copy of the per-sample code (a runtime loop): the instruction cache matters more than the loop overhead
+#pragma unroll 1
+    for (int j = 0; j < K; ++j) {
+        const int i = tid + j * T;
+        loc[j] = 0.0; hic[j] = 0.0;
+        if (i >= N) continue;
+        const double2 Pc = sP[i];
+        double nx, ny;
+        normal_at(sP, i, N, closed, nx, ny);
+        const unsigned hw = sHint[i];
+        const unsigned cw = sClr[i];
+        const double cx0 = gcenter[2 * i], cy0 = gcenter[2 * i + 1];
+        const unsigned long long cert_w = gcert[i], apex_w = gapex[i];
+        const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
+        const float pmax = 2e-6f * fmaxf(fabsf((float)(Pc.x - org.x)), fabsf((float)(Pc.y - org.y))) + 1e-5f;
+        bool flag = false;
+        double w[2][2], Rc[2], wd[2];
+        bool ins[2];
+#pragma unroll
+        for (int ring = 0; ring < 2; ++ring) {
+            const int M = ring ? M1 : M0;
+            const double2* V = ring ? V1 : V0;
+            const int rf = ring ? rf1 : rf0;
+            const float m = (ring ? mr1 : mr0) * 1.001f + pmax;      // the FP32 margin the stored clearance was taken with
+            int j0 = (int)((hw >> (13 * ring)) & 0x1fffu);
+            if (j0 >= M) j0 = 0;
+            const unsigned cq = (cw >> (8 * ring)) & 0xffu;
+            const float rc = (cq == 255u ? 3e18f : 0.25f * (float)cq) - disp - 4.f * m;
+            if (!((hw >> (28 + ring)) & 1u) || !(rc > 0.f)) flag = true;
+            Rc[ring] = (double)rc;
+            ins[ring] = parity_ok && (rf & 1) && ((hw >> (26 + ring)) & 1u);
+            double pos = INF, neg = INF;
+            int sp_ = -1, sn_ = -1;
+            int sg = wrap_seg(j0 - kWin, M);
+#pragma unroll 1
+            for (int q = 0; q < 2 * kWin + 1; ++q) {
+                const double2 a = V[sg], b = V[sg + 1];
+                // side of the ray's line each end point lies on: both clearly on one side -> no hit (main.cpp:487-488)
+                const double ax = a.x - Pc.x, ay = a.y - Pc.y, bx = b.x - Pc.x, by = b.y - Pc.y;
+                const double sa = nx * ay - ny * ax, sb = nx * by - ny * bx;
+                const double tol = 1e-6 * (1.0 + fabs(ax) + fabs(ay));
+                if (!((sa > tol && sb > tol) || (sa < -tol && sb < -tol))) {
+                    const double sd[4] = {a.x, a.y, b.x - a.x, b.y - a.y};      // v = b - a as in main.cpp:482
+                    seg_hit(sd, Pc, nx, ny, pos, neg, sg, sp_, sn_, ray_tests);
+                }
+                sg = (sg + 1 == M) ? 0 : sg + 1;
+            }
+            w[ring][0] = pos; w[ring][1] = neg;
+            wd[ring] = -1.0;   // window distance not computed yet
+        }
+        double dres[2];
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            double b = INF;
+#pragma unroll
+            for (int ring = 0; ring < 2; ++ring) {
+                if (w[ring][dir] <= Rc[ring]) b = fmin(b, w[ring][dir]);
+                else if (w[ring][dir] < INF) flag = true;            // a window hit that is not certified nearest
+            }
+            double res = b;
+#pragma unroll
+            for (int ring = 0; ring < 2; ++ring) {
+                if (w[ring][dir] < INF) continue;
+                if (!(b <= Rc[ring])) { flag = true; continue; }    // nothing certified undercuts this ring's far hits
+                if (ins[ring]) continue;                             // parity: it hits, beyond Rc >= b
+                if (wd[ring] < 0.0) {
+                    // exact point-ring distance over the window (minDistanceToSegments_global body, main.cpp:504-509)
+                    const int M = ring ? M1 : M0;
+                    const double2* V = ring ? V1 : V0;
+                    int j0 = (int)((hw >> (13 * ring)) & 0x1fffu);
+                    if (j0 >= M) j0 = 0;
+                    int sg = wrap_seg(j0 - kWin, M);
+                    double best2 = INF;
+#pragma unroll 1
+                    for (int q = 0; q < 2 * kWin + 1; ++q) {
+                        const double2 a = V[sg], bb = V[sg + 1];
+                        const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
+                        best2 = fmin(best2, seg_dist2(sd, Pc));
+                        sg = (sg + 1 == M) ? 0 : sg + 1;
+                    }
+                    wd[ring] = sqrt(best2);
+                }
+                if (wd[ring] <= Rc[ring] && wd[ring] < b) {
+                    // the point distance would undercut: does this ray hit the ring anywhere?  (certificate or flag)
+                    const unsigned w0 = (unsigned)cert_w, w1 = (unsigned)(cert_w >> 32);
+                    const unsigned key = ((unsigned)ring << 2) | ((unsigned)dir << 3);
+                    const unsigned stt = ((w0 & 0xCu) == key) ? (w0 & 3u) : kCertNone;
+                    if (stt == kCertFar) {
+                        const int M = ring ? M1 : M0;
+                        const double2* V = ring ? V1 : V0;
+                        const int f = (int)w1;
+                        bool hit = false;
+                        if (f < M) {
+                            const double2 a = V[f], bb = V[f + 1];
+                            const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
+                            double tp = INF, tn = INF; int s_p = -1, s_n = -1;
+                            seg_hit(sd, Pc, nx, ny, tp, tn, f, s_p, s_n, ray_tests);
+                            hit = (dir ? tn : tp) < INF;
+                        }
+                        if (!hit) flag = true;
+                    } else if (stt == kCertCone) {
+                        double d0x, d0y;
+                        cert_axis(w1, d0x, d0y);
+                        const double cc = (double)(w0 >> 16) * (1.0 / 32767.0) - 1.0 + 2e-6;
+                        const double ux = (Pc.x - cx0) - (double)__uint_as_float((unsigned)apex_w);
+                        const double uy = (Pc.y - cy0) - (double)__uint_as_float((unsigned)(apex_w >> 32));
+                        const double sgd = dir ? -1.0 : 1.0;
+                        if (ux * d0x + uy * d0y >= sqrt(ux * ux + uy * uy) * cc && sgd * (nx * d0x + ny * d0y) >= cc) res = fmin(res, wd[ring]);
+                        else flag = true;
+                    } else flag = true;
+                }
+            }
+            dres[dir] = res;
+        }
+        if (flag) flagged |= (1u << j);
+        else {
+            double hv = fmax(0.0, fmax(0.0, dres[0]) - guard);
+            double lv = -fmax(0.0, fmax(0.0, dres[1]) - guard);
+            if (!isfinite(hv)) hv = 0.0;
+            if (!isfinite(lv)) lv = 0.0;
+            hic[j] = hv; loc[j] = lv;
+        }
+    }
+    return flagged;
+}
+
 // ---- the solver kernel ------------------------------------------------------------------------------------
 template <int T, int K, int MODE>
-__global__ void __launch_bounds__(T, (512 / T) > 16 ? 16 : (512 / T))
-solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
+__global__ void __launch_bounds__(T, (4096 / (T * K)) > 16 ? 16 : ((4096 / (T * K)) < 1 ? 1 : (4096 / (T * K))))
+solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __restrict__ item_off, int n_items)
 {
     constexpr int NP = T * K;
     constexpr bool EXACT = (MODE == kModeExact), OPEN = (MODE == kModeOpen);
@@ -1557,8 +1738,21 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     unsigned* sHint = reinterpret_cast<unsigned*>(scr + kScrBytes);
     unsigned short* sClr = reinterpret_cast<unsigned short*>(scr + kScrBytes + (size_t)NP * 4);
 
-    if ((int)blockIdx.x >= n_list) return;
-    const int jid = job_list[blockIdx.x];
+    // One CTA works through one ITEM = a short chain of jobs on the SAME track (typically its min-curvature and its
+    // min-time stage, or neighbouring Configs of a sweep).  Everything the corridor code learns about the track --
+    // anchor segments, clearances, parity bits (shared memory) and the existence certificates (handed from job to job
+    // in global memory) -- stays valid for the next job of the chain, whose first corridor build is then an update.
+    if ((int)blockIdx.x >= n_items) return;
+    const int it0 = item_off[blockIdx.x], it1 = item_off[blockIdx.x + 1];
+    uint32_t bar_phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int prev_trk = -1;
+    bool fast_update = false;   // corridor_update applies: both rings are vertex chains with more segments than a window
+  for (int itj = it0; itj < it1; ++itj) {
+    const int jid = job_list[itj];
     const rl_job job = B.jobs[jid];
     const rl_params& C = B.params[job.param];
     rl_job_stats* st = B.stats + jid;
@@ -1588,10 +1782,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     }
     const int tid = pt.tid, cnt = pt.cnt, start = pt.start;
 
-    uint32_t bar_phase = 0;
     if (tid == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         st->status = RL_OK; st->n = N; st->outer_done = 0; st->accepted = 0; st->backtracks = 0; st->evals = 0;
         st->vpass_rounds = 0; st->exist_scans = 0; st->ray_tests = 0; st->lap_time = 0.0;
         for (int o = 0; o < RL_MAX_OUTER_LOG; ++o) {
@@ -1635,15 +1826,37 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
     constexpr int CAPF = fast_tile_cap(NP);
     const bool fast_rays = (segO0 - segI0 <= CAPF) && (segE - segO0 <= CAPF) && (CAPF < 8192);
     const bool parity_ok = (C.veh_width_arg * 0.5 + C.safety_margin_m >= 0.0) && (C.veh_width_m * 0.5 + C.safety_margin_m >= 0.0);
-    for (int i = tid; i < NP; i += T) { sHint[i] = 0u; sClr[i] = 0; }
     // per-sample existence certificates (see corridor_build_fast) live in the heading and curvature rows until the final geometry pass
     unsigned long long* gcert = reinterpret_cast<unsigned long long*>(B.heading + row0);
     unsigned long long* gapex = reinterpret_cast<unsigned long long*>(B.curvature + row0);
-    for (int i = tid; i < N; i += T) gcert[i] = 0ull;
-    if (fast_rays)
-        corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, true, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex, segI0, segO0, segE,
-                                  C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests, ex_scans);
-    else
+    const bool same_track = fast_rays && (trk == prev_trk);   // the previous job of this chain left its corridor state behind
+    if (!same_track) {
+        for (int i = tid; i < NP; i += T) { sHint[i] = 0u; sClr[i] = 0; }
+        for (int i = tid; i < N; i += T) gcert[i] = 0ull;
+        fast_update = false;
+    }
+    if (fast_rays) {
+        const double guard0 = C.veh_width_arg * 0.5 + C.safety_margin_m;
+        double loc[K], hic[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { loc[j] = 0.0; hic[j] = 0.0; }
+        if (!same_track) {
+            if (tid == 0) { sMisc[8] = 0; sMisc[9] = 0; sMisc[10] = 0; sMisc[11] = 0; }
+            corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, true, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
+                                      segI0, segO0, segE, guard0, 0xffffffffu, loc, hic, ray_tests, ex_scans);
+        } else {
+            unsigned flagged = 0xffffffffu;
+            if (fast_update)
+                flagged = corridor_update<T, K>(pt, sP, sB, sMisc, sHint, sClr, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
+                                                segI0, segO0, segE, guard0, loc, hic, ray_tests);
+            if (block_or<T>(flagged != 0u))
+                corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
+                                          segI0, segO0, segE, guard0, flagged, loc, hic, ray_tests, ex_scans);
+        }
+        corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
+        if (!same_track)
+            fast_update = (sMisc[8] & 2) && (sMisc[9] & 2) && (segO0 - segI0 > 2 * kWin + 1) && (segE - segO0 > 2 * kWin + 1);
+    } else
         corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                    C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
 
@@ -1795,14 +2008,37 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
         for (int k = 0; k < K; ++k) if (k < cnt) sP[start + k] = Pn[k];
         block_sync<T>();
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
-        if (fast_rays)
-            corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex, segI0, segO0, segE,
-                                      C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests, ex_scans);
-        else
+        if (fast_rays) {
+            const double guard = C.veh_width_m * 0.5 + C.safety_margin_m;
+            double loc[K], hic[K];
+            unsigned flagged = 0xffffffffu;
+            if (fast_update)
+                flagged = corridor_update<T, K>(pt, sP, sB, sMisc, sHint, sClr, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
+                                                segI0, segO0, segE, guard, loc, hic, ray_tests);
+            else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) { loc[j] = 0.0; hic[j] = 0.0; }
+            }
+            if (block_or<T>(flagged != 0u))   // some certificate failed (or none exists yet): the searching path rebuilds those samples
+                corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
+                                          segI0, segO0, segE, guard, flagged, loc, hic, ray_tests, ex_scans);
+            corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
+        } else
             corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                        C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
     }
 
+    // the next job of the chain inherits the certificates (same thread, same samples: no barrier needed)
+    if (fast_rays && itj + 1 < it1) {
+        const int njid = job_list[itj + 1];
+        if (B.jobs[njid].track == trk) {
+            const long long nrow0 = B.job_off[njid];
+            unsigned long long* ncert = reinterpret_cast<unsigned long long*>(B.heading + nrow0);
+            unsigned long long* napex = reinterpret_cast<unsigned long long*>(B.curvature + nrow0);
+            for (int i = tid; i < N; i += T) { ncert[i] = gcert[i]; napex[i] = gapex[i]; }
+        }
+    }
+    prev_trk = trk;
     // =================== final geometry (main.cpp:761 / 1046) ===================
     block_sync<T>();
 #pragma unroll
@@ -1853,6 +2089,8 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
             st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap; st->exist_scans = (int)es;
         }
     }
+    block_sync<T>();   // the next job of the chain reuses the shared-memory regions
+  }
 }
 
 
@@ -1860,18 +2098,18 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
 }  // namespace rl
 
 // one translation unit per thread count T instantiates its three kernels (closed ragged, closed exact-fit, open)
-#define RL_INSTANTIATE(T, K)                                                                                          \
+#define RL_INSTANTIATE_AS(T, K, NAME)                                                                                          \
     namespace rl {                                                                                                    \
-    int launch_solve_##T(const DevBatch& B, const int* job_list, int n_list, int mode, void* stream)                 \
+    int launch_solve_##NAME(const DevBatch& B, const int* job_list, const int* item_off, int n_items, int mode, void* stream) \
     {                                                                                                                 \
         const size_t smem = smem_bytes_for_class(T, K);                                                               \
         cudaStream_t s = (cudaStream_t)stream;                                                                        \
-        if (mode == 1) solve_kernel<T, K, 1><<<n_list, T, smem, s>>>(B, job_list, n_list);                            \
-        else if (mode == 2) solve_kernel<T, K, 2><<<n_list, T, smem, s>>>(B, job_list, n_list);                       \
-        else solve_kernel<T, K, 0><<<n_list, T, smem, s>>>(B, job_list, n_list);                                      \
+        if (mode == 1) solve_kernel<T, K, 1><<<n_items, T, smem, s>>>(B, job_list, item_off, n_items);                \
+        else if (mode == 2) solve_kernel<T, K, 2><<<n_items, T, smem, s>>>(B, job_list, item_off, n_items);           \
+        else solve_kernel<T, K, 0><<<n_items, T, smem, s>>>(B, job_list, item_off, n_items);                          \
         return (int)cudaGetLastError();                                                                               \
     }                                                                                                                 \
-    int configure_solve_##T()                                                                                         \
+    int configure_solve_##NAME()                                                                                         \
     {                                                                                                                 \
         const int smem = (int)smem_bytes_for_class(T, K);                                                             \
         cudaError_t e = cudaFuncSetAttribute(solve_kernel<T, K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
@@ -1882,3 +2120,5 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
         return (int)e;                                                                                                \
     }                                                                                                                 \
     }
+
+#define RL_INSTANTIATE(T, K) RL_INSTANTIATE_AS(T, K, T)

@@ -842,6 +842,22 @@ struct RayTile {
     int nt, nblk, nsup;
 };
 
+// The searches below are real (noinline) functions, and a pointer that crosses a call is a GENERIC pointer: its loads
+// become LD.E (long scoreboard) although the tile lives in shared memory.  Rebuilding the pointers from the CTA's
+// extern shared array tells the compiler the address space again (LDS).
+template <class P>
+__device__ __forceinline__ const P* as_smem(const P* g)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    return reinterpret_cast<const P*>(smem_raw + (smem_u32(g) - smem_u32(smem_raw)));
+}
+__device__ __forceinline__ RayTile tile_in_smem(const RayTile& t)
+{
+    RayTile r = t;
+    r.segD = as_smem(t.segD); r.segF = as_smem(t.segF); r.boxF = as_smem(t.boxF); r.supF = as_smem(t.supF);
+    return r;
+}
+
 __device__ __forceinline__ bool ray_box(const float4 bx, float px, float py, float nx, float ny, float anx, float any,
                                         float m, float bp, float bn, bool wp, bool wn)
 {
@@ -863,7 +879,7 @@ __device__ __noinline__ int ray_scan(const RayTile& tl_in, double2 P, double nx,
                                         double& bp_io, double& bn_io, double& pos_io, double& neg_io, long long& tests_io)
 {
     // a real function (one copy): keep the tile description and the in/out values in registers
-    const RayTile tl = tl_in;
+    const RayTile tl = tile_in_smem(tl_in);
     double bp = bp_io, bn = bn_io, pos_r = pos_io, neg_r = neg_io;
     int tests = 0;
     const double INF = dinf();
@@ -923,7 +939,7 @@ done:
 // upper bound (a hit point lies on the ring) or INF.
 __device__ __noinline__ double dist_scan(const RayTile& tl_in, double2 P, float px, float py, float m, int hint, double ub)
 {
-    const RayTile tl = tl_in;
+    const RayTile tl = tile_in_smem(tl_in);
     const double INF = dinf();
     double best2 = INF;
     float boundf = (ub < INF) ? __double2float_ru(ub) * (1.f + 1e-5f) + m : __int_as_float(0x7f800000);
@@ -973,7 +989,7 @@ __device__ __noinline__ double dist_scan(const RayTile& tl_in, double2 P, float 
 // parity of the crossings of the +x ray from P with a CLOSED chain (vertices shared bit for bit): P inside?
 __device__ __noinline__ bool inside_ring(const RayTile& tl_in, double2 P, float px, float py, float m)
 {
-    const RayTile tl = tl_in;
+    const RayTile tl = tile_in_smem(tl_in);
     int cnt = 0;
     for (int sb = 0; sb < tl.nsup; ++sb) {
         const float4 sx = tl.supF[sb];
@@ -1166,7 +1182,7 @@ __device__ __forceinline__ double window_dist(const RayTile& tl, double2 P, floa
 // conservative (rounded down) distance from p to every segment of the ring outside the window of j0
 __device__ __noinline__ float clearance_scan(const RayTile& tl_in, float px, float py, float m, int j0)
 {
-    const RayTile tl = tl_in;
+    const RayTile tl = tile_in_smem(tl_in);
     const int M = tl.nt;
     if (M <= 2 * kWin + 1) return 3e18f;
     float best = 3e18f;   // distance, not squared
@@ -1230,7 +1246,7 @@ __device__ __forceinline__ bool cone_prune(const float4 bx, float ax, float ay, 
 // FP32 cannot tell).  Along a segment that does not cross the forward axis the angle is extremal at its end points.
 __device__ __noinline__ float cone_scan(const RayTile& tl_in, float ax, float ay, float dx, float dy, float m, int hint)
 {
-    const RayTile tl = tl_in;
+    const RayTile tl = tile_in_smem(tl_in);
     const float e = 2.f * m + 1e-6f;
     // a cone wider than 30 degrees is never needed (and never wider than 90: only a CONVEX cone keeps
     // origin + t*direction inside), so everything outside the 30-degree cone is skipped from the start
@@ -1360,7 +1376,8 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
     float lbp[K], lbn[K];          // "a hit exists on some ring, value unknown but >= lb" (parity certificate)
     unsigned flagged = 0u;         // bit j: sample j must be redone by the general search
 #pragma unroll 1
-    for (int j = 0; j < K; ++j) { bp[j] = INF; bn[j] = INF; dfp[j] = INF; dfn[j] = INF; lbp[j] = FINF; lbn[j] = FINF; }
+    for (int j = 0; j < K; ++j)
+        if ((mask >> j) & 1u) { bp[j] = INF; bn[j] = INF; dfp[j] = INF; dfn[j] = INF; lbp[j] = FINF; lbn[j] = FINF; }
     // ring order: the ring the samples lie INSIDE of goes first (its far hits are settled by parity, and the
     // bounds it produces let the other ring skip most existence questions)
     const unsigned h0 = sHint[0];
@@ -1570,6 +1587,162 @@ __device__ __forceinline__ void corridor_stage_out(const Part& pt, double* sB, c
 // Both rings' vertices (16 B each) sit in region B together, so one pass over the samples does both rings with scalars
 // only, no searches and no calls.  A sample any certificate fails for is FLAGGED and rebuilt by corridor_build_fast,
 // which also refreshes its anchors / clearances / certificates.  Returns the flag mask (bit j = sample tid + j*T).
+struct UpdCtx {
+    // byte offsets into the CTA's dynamic shared memory (pointers rebuilt from the extern array keep the loads LDS)
+    int oV0, oV1, oF0, oF1, oHint, oClr;
+    const double* gcenter; const unsigned long long* gcert; const unsigned long long* gapex;
+    double ox, oy, guard;
+    int N, M0, M1, rf0, rf1;
+    float mr0, mr1;
+    bool parity_ok, closed;
+};
+// one sample of corridor_update: true = FLAGGED (hv/lv untouched), else the corridor bounds hv >= 0 >= lv
+__device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, double& hv_out, double& lv_out, long long& tests_io)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const double2* sP = reinterpret_cast<const double2*>(smem_raw);
+    const double2* cV0 = reinterpret_cast<const double2*>(smem_raw + c.oV0);
+    const double2* cV1 = reinterpret_cast<const double2*>(smem_raw + c.oV1);
+    const float2* cF0 = reinterpret_cast<const float2*>(smem_raw + c.oF0);
+    const float2* cF1 = reinterpret_cast<const float2*>(smem_raw + c.oF1);
+    const double INF = dinf();
+    long long ray_tests = 0;
+    const double2 Pc = sP[i];
+    double nx, ny;
+    normal_at(sP, i, c.N, c.closed, nx, ny);
+    const unsigned hw = reinterpret_cast<const unsigned*>(smem_raw + c.oHint)[i];
+    const unsigned cw = reinterpret_cast<const unsigned short*>(smem_raw + c.oClr)[i];
+    const double cx0 = c.gcenter[2 * i], cy0 = c.gcenter[2 * i + 1];
+    const unsigned long long cert_w = c.gcert[i], apex_w = c.gapex[i];
+    const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
+    const float px = (float)(Pc.x - c.ox), py = (float)(Pc.y - c.oy), fnx = (float)nx, fny = (float)ny;
+    const float pmax = 2e-6f * fmaxf(fabsf(px), fabsf(py)) + 1e-5f;
+    bool flag = false;
+    double w[2][2], Rc[2], wd[2];
+    bool ins[2];
+#pragma unroll
+    for (int ring = 0; ring < 2; ++ring) {
+        const int M = ring ? c.M1 : c.M0;
+        const double2* V = ring ? cV1 : cV0;
+        const float2* F = ring ? cF1 : cF0;
+        const int rf = ring ? c.rf1 : c.rf0;
+        const float m = (ring ? c.mr1 : c.mr0) * 1.001f + pmax;      // the FP32 margin the stored clearance was taken with
+        int j0 = (int)((hw >> (13 * ring)) & 0x1fffu);
+        if (j0 >= M) j0 = 0;
+        const unsigned cq = (cw >> (8 * ring)) & 0xffu;
+        const float rc = (cq == 255u ? 3e18f : 0.25f * (float)cq) - disp - 4.f * m;
+        if (!((hw >> (28 + ring)) & 1u) || !(rc > 0.f)) flag = true;
+        Rc[ring] = (double)rc;
+        ins[ring] = c.parity_ok && (rf & 1) && ((hw >> (26 + ring)) & 1u);
+        double pos = INF, neg = INF;
+        int sp_ = -1, sn_ = -1;
+        int sg = wrap_seg(j0 - kWin, M);
+#pragma unroll 1
+        for (int q = 0; q < 2 * kWin + 1; ++q) {
+            // side of the ray's line each end point lies on (FP32, margin m): both clearly on one side -> no hit
+            const float2 fa = F[sg], fb = F[sg + 1];
+            const float sa = fnx * (fa.y - py) - fny * (fa.x - px), sb = fnx * (fb.y - py) - fny * (fb.x - px);
+            if (!(fminf(sa, sb) > m || fmaxf(sa, sb) < -m)) {
+                const double2 a = V[sg], b = V[sg + 1];
+                const double sd[4] = {a.x, a.y, b.x - a.x, b.y - a.y};      // v = b - a as in main.cpp:482
+                seg_hit(sd, Pc, nx, ny, pos, neg, sg, sp_, sn_, ray_tests);
+            }
+            sg = (sg + 1 == M) ? 0 : sg + 1;
+        }
+        w[ring][0] = pos; w[ring][1] = neg;
+        wd[ring] = -1.0;   // window distance not computed yet
+    }
+    double dres[2];
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        double b = INF;
+#pragma unroll
+        for (int ring = 0; ring < 2; ++ring) {
+            if (w[ring][dir] <= Rc[ring]) b = fmin(b, w[ring][dir]);
+            else if (w[ring][dir] < INF) flag = true;            // a window hit that is not certified nearest
+        }
+        double res = b;
+#pragma unroll
+        for (int ring = 0; ring < 2; ++ring) {
+            if (w[ring][dir] < INF) continue;
+            if (!(b <= Rc[ring])) { flag = true; continue; }    // nothing certified undercuts this ring's far hits
+            if (ins[ring]) continue;                             // parity: it hits, beyond Rc >= b
+            if (wd[ring] < 0.0) {
+                // exact point-ring distance over the window (minDistanceToSegments_global body, main.cpp:504-509)
+                const int M = ring ? c.M1 : c.M0;
+                const double2* V = ring ? cV1 : cV0;
+                const float2* F = ring ? cF1 : cF0;
+                const float m = (ring ? c.mr1 : c.mr0) * 1.001f + pmax;
+                int j0 = (int)((hw >> (13 * ring)) & 0x1fffu);
+                if (j0 >= M) j0 = 0;
+                const int sg0 = wrap_seg(j0 - kWin, M);
+                // FP32 first: only segments within a few margins of the FP32 minimum can hold the exact minimum
+                float dminf = 3e38f;
+                int sg = sg0;
+#pragma unroll 1
+                for (int q = 0; q < 2 * kWin + 1; ++q) {
+                    const float2 fa = F[sg], fb = F[sg + 1];
+                    dminf = fminf(dminf, seg_dist2_f(make_float4(fa.x, fa.y, fb.x, fb.y), px, py));
+                    sg = (sg + 1 == M) ? 0 : sg + 1;
+                }
+                const float lim = sqrtf(dminf) + 8.f * m;
+                const float lim2 = lim * lim * (1.f + 1e-5f);
+                double best2 = INF;
+                sg = sg0;
+#pragma unroll 1
+                for (int q = 0; q < 2 * kWin + 1; ++q) {
+                    const float2 fa = F[sg], fb = F[sg + 1];
+                    if (seg_dist2_f(make_float4(fa.x, fa.y, fb.x, fb.y), px, py) <= lim2) {
+                        const double2 a = V[sg], bb = V[sg + 1];
+                        const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
+                        best2 = fmin(best2, seg_dist2(sd, Pc));
+                    }
+                    sg = (sg + 1 == M) ? 0 : sg + 1;
+                }
+                wd[ring] = sqrt(best2);
+            }
+            if (wd[ring] <= Rc[ring] && wd[ring] < b) {
+                // the point distance would undercut: does this ray hit the ring anywhere?  (certificate or flag)
+                const unsigned w0 = (unsigned)cert_w, w1 = (unsigned)(cert_w >> 32);
+                const unsigned key = ((unsigned)ring << 2) | ((unsigned)dir << 3);
+                const unsigned stt = ((w0 & 0xCu) == key) ? (w0 & 3u) : kCertNone;
+                if (stt == kCertFar) {
+                    const int M = ring ? c.M1 : c.M0;
+                    const double2* V = ring ? cV1 : cV0;
+                    const int f = (int)w1;
+                    bool hit = false;
+                    if (f < M) {
+                        const double2 a = V[f], bb = V[f + 1];
+                        const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
+                        double tp = INF, tn = INF; int s_p = -1, s_n = -1;
+                        seg_hit(sd, Pc, nx, ny, tp, tn, f, s_p, s_n, ray_tests);
+                        hit = (dir ? tn : tp) < INF;
+                    }
+                    if (!hit) flag = true;
+                } else if (stt == kCertCone) {
+                    double d0x, d0y;
+                    cert_axis(w1, d0x, d0y);
+                    const double cc = (double)(w0 >> 16) * (1.0 / 32767.0) - 1.0 + 2e-6;
+                    const double ux = (Pc.x - cx0) - (double)__uint_as_float((unsigned)apex_w);
+                    const double uy = (Pc.y - cy0) - (double)__uint_as_float((unsigned)(apex_w >> 32));
+                    const double sgd = dir ? -1.0 : 1.0;
+                    if (ux * d0x + uy * d0y >= sqrt(ux * ux + uy * uy) * cc && sgd * (nx * d0x + ny * d0y) >= cc) res = fmin(res, wd[ring]);
+                    else flag = true;
+                } else flag = true;
+            }
+        }
+        dres[dir] = res;
+    }
+    tests_io += ray_tests;
+    if (flag) return true;
+    double hv = fmax(0.0, fmax(0.0, dres[0]) - c.guard);
+    double lv = -fmax(0.0, fmax(0.0, dres[1]) - c.guard);
+    if (!isfinite(hv)) hv = 0.0;
+    if (!isfinite(lv)) lv = 0.0;
+    hv_out = hv; lv_out = lv;
+    return false;
+}
+
 template <int T, int K>
 __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double2* sP, double* sB, const int* sMisc,
                                                     const unsigned* sHint, const unsigned short* sClr, bool parity_ok, bool closed,
@@ -1583,138 +1756,42 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
     const int M0 = (int)(segO0 - segI0), M1 = (int)(segE - segO0);
     double2* V0 = reinterpret_cast<double2*>(sB);
     double2* V1 = V0 + (M0 + 1);
-    block_sync<T>();   // region B is free
-    for (int q = tid; q <= M0; q += T)
-        V0[q] = (q < M0) ? *reinterpret_cast<const double2*>(gseg + 4 * (segI0 + q)) : *reinterpret_cast<const double2*>(gseg + 4 * (segI0 + M0 - 1) + 2);
-    for (int q = tid; q <= M1; q += T)
-        V1[q] = (q < M1) ? *reinterpret_cast<const double2*>(gseg + 4 * (segO0 + q)) : *reinterpret_cast<const double2*>(gseg + 4 * (segO0 + M1 - 1) + 2);
+    float2* F0 = reinterpret_cast<float2*>(V1 + (M1 + 1));   // FP32 copies relative to the job origin: they only ever SKIP exact work
+    float2* F1 = F0 + (M0 + 1);
     const double2 org = sP[0];
+    block_sync<T>();   // region B is free
+    for (int q = tid; q <= M0; q += T) {
+        const double2 v = (q < M0) ? *reinterpret_cast<const double2*>(gseg + 4 * (segI0 + q)) : *reinterpret_cast<const double2*>(gseg + 4 * (segI0 + M0 - 1) + 2);
+        V0[q] = v; F0[q] = make_float2((float)(v.x - org.x), (float)(v.y - org.y));
+    }
+    for (int q = tid; q <= M1; q += T) {
+        const double2 v = (q < M1) ? *reinterpret_cast<const double2*>(gseg + 4 * (segO0 + q)) : *reinterpret_cast<const double2*>(gseg + 4 * (segO0 + M1 - 1) + 2);
+        V1[q] = v; F1[q] = make_float2((float)(v.x - org.x), (float)(v.y - org.y));
+    }
     const int rf0 = sMisc[8], rf1 = sMisc[9];
     const float mr0 = __int_as_float(sMisc[10]), mr1 = __int_as_float(sMisc[11]);
     block_sync<T>();
+    UpdCtx c;
+    {
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(sP);    // sP is the start of the dynamic shared memory
+        c.oV0 = (int)(reinterpret_cast<const unsigned char*>(V0) - base); c.oV1 = (int)(reinterpret_cast<const unsigned char*>(V1) - base);
+        c.oF0 = (int)(reinterpret_cast<const unsigned char*>(F0) - base); c.oF1 = (int)(reinterpret_cast<const unsigned char*>(F1) - base);
+        c.oHint = (int)(reinterpret_cast<const unsigned char*>(sHint) - base); c.oClr = (int)(reinterpret_cast<const unsigned char*>(sClr) - base);
+    }
+    c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
+    c.ox = org.x; c.oy = org.y; c.guard = guard; c.N = N; c.M0 = M0; c.M1 = M1; c.rf0 = rf0; c.rf1 = rf1; c.mr0 = mr0; c.mr1 = mr1;
+    c.parity_ok = parity_ok; c.closed = closed;
     unsigned flagged = 0u;
-    // one copy of the per-sample code (a runtime loop): the instruction cache matters more than the loop overhead
-#pragma unroll 1
+    // the per-sample code exists once (a real function): the instruction cache matters more than the call, and the
+    // results stay in registers (static j)
+#pragma unroll
     for (int j = 0; j < K; ++j) {
         const int i = tid + j * T;
         loc[j] = 0.0; hic[j] = 0.0;
         if (i >= N) continue;
-        const double2 Pc = sP[i];
-        double nx, ny;
-        normal_at(sP, i, N, closed, nx, ny);
-        const unsigned hw = sHint[i];
-        const unsigned cw = sClr[i];
-        const double cx0 = gcenter[2 * i], cy0 = gcenter[2 * i + 1];
-        const unsigned long long cert_w = gcert[i], apex_w = gapex[i];
-        const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
-        const float pmax = 2e-6f * fmaxf(fabsf((float)(Pc.x - org.x)), fabsf((float)(Pc.y - org.y))) + 1e-5f;
-        bool flag = false;
-        double w[2][2], Rc[2], wd[2];
-        bool ins[2];
-#pragma unroll
-        for (int ring = 0; ring < 2; ++ring) {
-            const int M = ring ? M1 : M0;
-            const double2* V = ring ? V1 : V0;
-            const int rf = ring ? rf1 : rf0;
-            const float m = (ring ? mr1 : mr0) * 1.001f + pmax;      // the FP32 margin the stored clearance was taken with
-            int j0 = (int)((hw >> (13 * ring)) & 0x1fffu);
-            if (j0 >= M) j0 = 0;
-            const unsigned cq = (cw >> (8 * ring)) & 0xffu;
-            const float rc = (cq == 255u ? 3e18f : 0.25f * (float)cq) - disp - 4.f * m;
-            if (!((hw >> (28 + ring)) & 1u) || !(rc > 0.f)) flag = true;
-            Rc[ring] = (double)rc;
-            ins[ring] = parity_ok && (rf & 1) && ((hw >> (26 + ring)) & 1u);
-            double pos = INF, neg = INF;
-            int sp_ = -1, sn_ = -1;
-            int sg = wrap_seg(j0 - kWin, M);
-#pragma unroll 1
-            for (int q = 0; q < 2 * kWin + 1; ++q) {
-                const double2 a = V[sg], b = V[sg + 1];
-                // side of the ray's line each end point lies on: both clearly on one side -> no hit (main.cpp:487-488)
-                const double ax = a.x - Pc.x, ay = a.y - Pc.y, bx = b.x - Pc.x, by = b.y - Pc.y;
-                const double sa = nx * ay - ny * ax, sb = nx * by - ny * bx;
-                const double tol = 1e-6 * (1.0 + fabs(ax) + fabs(ay));
-                if (!((sa > tol && sb > tol) || (sa < -tol && sb < -tol))) {
-                    const double sd[4] = {a.x, a.y, b.x - a.x, b.y - a.y};      // v = b - a as in main.cpp:482
-                    seg_hit(sd, Pc, nx, ny, pos, neg, sg, sp_, sn_, ray_tests);
-                }
-                sg = (sg + 1 == M) ? 0 : sg + 1;
-            }
-            w[ring][0] = pos; w[ring][1] = neg;
-            wd[ring] = -1.0;   // window distance not computed yet
-        }
-        double dres[2];
-#pragma unroll
-        for (int dir = 0; dir < 2; ++dir) {
-            double b = INF;
-#pragma unroll
-            for (int ring = 0; ring < 2; ++ring) {
-                if (w[ring][dir] <= Rc[ring]) b = fmin(b, w[ring][dir]);
-                else if (w[ring][dir] < INF) flag = true;            // a window hit that is not certified nearest
-            }
-            double res = b;
-#pragma unroll
-            for (int ring = 0; ring < 2; ++ring) {
-                if (w[ring][dir] < INF) continue;
-                if (!(b <= Rc[ring])) { flag = true; continue; }    // nothing certified undercuts this ring's far hits
-                if (ins[ring]) continue;                             // parity: it hits, beyond Rc >= b
-                if (wd[ring] < 0.0) {
-                    // exact point-ring distance over the window (minDistanceToSegments_global body, main.cpp:504-509)
-                    const int M = ring ? M1 : M0;
-                    const double2* V = ring ? V1 : V0;
-                    int j0 = (int)((hw >> (13 * ring)) & 0x1fffu);
-                    if (j0 >= M) j0 = 0;
-                    int sg = wrap_seg(j0 - kWin, M);
-                    double best2 = INF;
-#pragma unroll 1
-                    for (int q = 0; q < 2 * kWin + 1; ++q) {
-                        const double2 a = V[sg], bb = V[sg + 1];
-                        const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
-                        best2 = fmin(best2, seg_dist2(sd, Pc));
-                        sg = (sg + 1 == M) ? 0 : sg + 1;
-                    }
-                    wd[ring] = sqrt(best2);
-                }
-                if (wd[ring] <= Rc[ring] && wd[ring] < b) {
-                    // the point distance would undercut: does this ray hit the ring anywhere?  (certificate or flag)
-                    const unsigned w0 = (unsigned)cert_w, w1 = (unsigned)(cert_w >> 32);
-                    const unsigned key = ((unsigned)ring << 2) | ((unsigned)dir << 3);
-                    const unsigned stt = ((w0 & 0xCu) == key) ? (w0 & 3u) : kCertNone;
-                    if (stt == kCertFar) {
-                        const int M = ring ? M1 : M0;
-                        const double2* V = ring ? V1 : V0;
-                        const int f = (int)w1;
-                        bool hit = false;
-                        if (f < M) {
-                            const double2 a = V[f], bb = V[f + 1];
-                            const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
-                            double tp = INF, tn = INF; int s_p = -1, s_n = -1;
-                            seg_hit(sd, Pc, nx, ny, tp, tn, f, s_p, s_n, ray_tests);
-                            hit = (dir ? tn : tp) < INF;
-                        }
-                        if (!hit) flag = true;
-                    } else if (stt == kCertCone) {
-                        double d0x, d0y;
-                        cert_axis(w1, d0x, d0y);
-                        const double cc = (double)(w0 >> 16) * (1.0 / 32767.0) - 1.0 + 2e-6;
-                        const double ux = (Pc.x - cx0) - (double)__uint_as_float((unsigned)apex_w);
-                        const double uy = (Pc.y - cy0) - (double)__uint_as_float((unsigned)(apex_w >> 32));
-                        const double sgd = dir ? -1.0 : 1.0;
-                        if (ux * d0x + uy * d0y >= sqrt(ux * ux + uy * uy) * cc && sgd * (nx * d0x + ny * d0y) >= cc) res = fmin(res, wd[ring]);
-                        else flag = true;
-                    } else flag = true;
-                }
-            }
-            dres[dir] = res;
-        }
-        if (flag) flagged |= (1u << j);
-        else {
-            double hv = fmax(0.0, fmax(0.0, dres[0]) - guard);
-            double lv = -fmax(0.0, fmax(0.0, dres[1]) - guard);
-            if (!isfinite(hv)) hv = 0.0;
-            if (!isfinite(lv)) lv = 0.0;
-            hic[j] = hv; loc[j] = lv;
-        }
+        double hv = 0.0, lv = 0.0;
+        if (corridor_update_sample(c, i, hv, lv, ray_tests)) flagged |= (1u << j);
+        else { hic[j] = hv; loc[j] = lv; }
     }
     return flagged;
 }

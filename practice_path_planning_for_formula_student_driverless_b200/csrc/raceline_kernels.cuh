@@ -1597,7 +1597,8 @@ struct UpdCtx {
     bool parity_ok, closed;
 };
 // one sample of corridor_update: true = FLAGGED (hv/lv untouched), else the corridor bounds hv >= 0 >= lv
-__device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, double& hv_out, double& lv_out, long long& tests_io)
+__device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, double cx0, double cy0, unsigned long long cert_w,
+                                                    unsigned long long apex_w, double& hv_out, double& lv_out, long long& tests_io)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const double2* sP = reinterpret_cast<const double2*>(smem_raw);
@@ -1612,8 +1613,6 @@ __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, doub
     normal_at(sP, i, c.N, c.closed, nx, ny);
     const unsigned hw = reinterpret_cast<const unsigned*>(smem_raw + c.oHint)[i];
     const unsigned cw = reinterpret_cast<const unsigned short*>(smem_raw + c.oClr)[i];
-    const double cx0 = c.gcenter[2 * i], cy0 = c.gcenter[2 * i + 1];
-    const unsigned long long cert_w = c.gcert[i], apex_w = c.gapex[i];
     const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
     const float px = (float)(Pc.x - c.ox), py = (float)(Pc.y - c.oy), fnx = (float)nx, fny = (float)ny;
     const float pmax = 2e-6f * fmaxf(fabsf(px), fabsf(py)) + 1e-5f;
@@ -1784,13 +1783,20 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
     unsigned flagged = 0u;
     // the per-sample code exists once (a real function): the instruction cache matters more than the call, and the
     // results stay in registers (static j)
+    // the sample's global-memory state (centre-line point, certificate words) is fetched one sample ahead
+    double2 cn = make_double2(0.0, 0.0);
+    unsigned long long wn = 0ull, an = 0ull;
+    if (tid < N) { cn = *reinterpret_cast<const double2*>(gcenter + 2 * tid); wn = gcert[tid]; an = gapex[tid]; }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         const int i = tid + j * T;
         loc[j] = 0.0; hic[j] = 0.0;
+        const double2 cc = cn;
+        const unsigned long long wc = wn, ac = an;
+        if (j + 1 < K && i + T < N) { cn = *reinterpret_cast<const double2*>(gcenter + 2 * (i + T)); wn = gcert[i + T]; an = gapex[i + T]; }
         if (i >= N) continue;
         double hv = 0.0, lv = 0.0;
-        if (corridor_update_sample(c, i, hv, lv, ray_tests)) flagged |= (1u << j);
+        if (corridor_update_sample(c, i, cc.x, cc.y, wc, ac, hv, lv, ray_tests)) flagged |= (1u << j);
         else { hic[j] = hv; loc[j] = lv; }
     }
     return flagged;

@@ -220,6 +220,50 @@ int rl_compute_min_time_raceline(rl_ctx* ctx, const double* center_xy, int n,
                                  double* alpha_total, double* alpha_last, double* v, double* ax,
                                  double* lap_time, rl_job_stats* stats);
 
+/* ---- the stage before the path: centre line + width/geometry ------------------- */
+/*
+ * pipeline::make_centerline (main.cpp:1270-1279) = centerline::splineUniformResample (main.cpp:448-474) over
+ * Spline1D::fit / eval (main.cpp:404-446), followed by the per-sample body of pipeline::compute_geom_and_save
+ * (main.cpp:1306-1329): spline position and derivatives, heading, curvature, distancesToRings (main.cpp:513-524),
+ * width and v_kappa -- the columns s,x,y,heading_rad,curvature,dist_to_inner,dist_to_outer,width,v_kappa_mps of
+ * <base>_with_geom.csv (main.cpp:1304).  Batched over tracks; the reference's host code keeps the Delaunay/MST
+ * ordering that produces the mid points and the CSV writer that consumes the rows.
+ *
+ *   track t: ordered mid points  mids_xy[2*mid_off[t] .. 2*mid_off[t+1])   (OM.ordered, at least 3 per track)
+ *            samples[t] = cfg samples (main.cpp:1639), closed[t] = closed_mode; paddingK = closed ? 3 : 0 (main.cpp:1273)
+ *            rings as in rl_batch_desc (edges::ringEdges / polylineEdges of the *_from_mids points)
+ *   rows of track t: closed ? samples : samples + emit_closed_duplicate   (Kmax of main.cpp:1308)
+ *   the first samples[t] rows of x,y are the centre line the solver stages take (center_for_opt, main.cpp:1681-1683)
+ */
+typedef struct rl_geom_desc {
+    int32_t n_tracks;
+    int32_t emit_closed_duplicate; /* cfg emit_closed_duplicate (main.cpp:55) */
+    const int64_t* mid_off;        /* [n_tracks+1]   */
+    const double* mids_xy;         /* [2*mid_off[n_tracks]] */
+    const int32_t* samples;        /* [n_tracks]     */
+    const int32_t* track_closed;   /* [n_tracks]     */
+    const int64_t* seg_off;        /* [2*n_tracks+1] */
+    const double* seg;             /* [4*seg_off[2*n_tracks]] */
+    const rl_params* params;       /* one Config: kappa_eps, a_lat_max, v_cap_mps (main.cpp:1325-1326) */
+} rl_geom_desc;
+
+typedef struct rl_geom_out {       /* rows back to back in track order, off = rl_geom_row_offsets() */
+    double* xy;          /* [2*rows] */
+    double* s_rel;       /* [rows] si - s0 */
+    double* heading;     /* [rows] */
+    double* curvature;   /* [rows] */
+    double* dist_inner;  /* [rows] */
+    double* dist_outer;  /* [rows] */
+    double* width;       /* [rows] */
+    double* v_kappa;     /* [rows] */
+    double* track_L;     /* [n_tracks] CL.L  */
+    double* track_s0;    /* [n_tracks] CL.s0 */
+} rl_geom_out;
+
+int rl_geom_row_offsets(const rl_geom_desc* desc, int64_t* off); /* off has n_tracks+1 entries */
+/* host buffers in, host buffers out (any rl_geom_out pointer may be NULL); at most 4090 mid points per track */
+int rl_centerline_geom_batch(rl_ctx* ctx, const rl_geom_desc* desc, const rl_geom_out* out);
+
 /* ---- measurement helpers (bench / tests; not on the solve path) -------- */
 /*
  * Deterministic synthetic closed tracks: track id

@@ -100,3 +100,35 @@ def read_rlr1(path):
         out.append(r)
     assert pos == raw.size
     return out
+
+
+MAGIC_M = 0x314D4752  # "RGM1": one `ref_harness geom` dump
+
+
+def read_rgm1(path):
+    """Return a dict of numpy arrays for one `ref_harness geom` dump (centre line + width/geometry stage)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    hdr = raw[:64].view(np.int64)
+    assert hdr[0] == MAGIC_M, "not an RGM1 file"
+    n_mid, samples, rows, m_in, m_out, closed, emit = (int(x) for x in hdr[1:8])
+    pos = 64
+
+    def f64(count):
+        nonlocal pos
+        out = raw[pos:pos + 8 * count].view(np.float64).copy()
+        pos += 8 * count
+        return out
+
+    d = {"n_mid": n_mid, "samples": samples, "rows": rows, "m_inner": m_in, "m_outer": m_out, "closed": closed,
+         "emit_closed_duplicate": emit}
+    d["L"] = float(f64(1)[0])
+    d["s0"] = float(f64(1)[0])
+    d["mids_xy"] = f64(2 * n_mid).reshape(n_mid, 2)
+    d["inner_seg"] = f64(4 * m_in).reshape(m_in, 4)
+    d["outer_seg"] = f64(4 * m_out).reshape(m_out, 4)
+    nc = samples + (1 if emit else 0)
+    d["center_xy"] = f64(2 * nc).reshape(nc, 2)
+    for k in ("s_rel", "x", "y", "heading", "curvature", "dist_inner", "dist_outer", "width", "v_kappa"):
+        d[k] = f64(rows)
+    assert pos == raw.size, "trailing bytes in RGM1 file"
+    return d

@@ -25,7 +25,7 @@ _LIB = None
 def build(force=False):
     """Compile liboracle.so (and the _ref/ binaries when /root/reference is present)."""
     so = os.path.join(_HERE, "liboracle.so")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "raceline_oracle.c")):
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("raceline_oracle.c", "geom_oracle.c", "raceline_oracle.h")):
         subprocess.run(["make", "-C", _HERE, "port"], check=True, capture_output=True)
     return so
 
@@ -58,6 +58,11 @@ def lib():
         L.orc_eval_cost_grad.restype = C.c_double
         L.orc_velocity_profile.argtypes = [C.POINTER(RlParams), dp, C.c_int, C.c_double, C.c_int, dp, dp]
         L.orc_velocity_profile.restype = C.c_double
+        L.orc_geom_rows.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.orc_geom_rows.restype = C.c_int
+        L.orc_centerline_geom.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, C.POINTER(RlParams),
+                                          dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_centerline_geom.restype = C.c_int
         L.orc_time_weights.argtypes = [C.POINTER(RlParams), dp, dp, C.c_int, dp]
         L.orc_time_weights.restype = None
         L.orc_corridor.argtypes = [dp, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_double, dp, dp]
@@ -104,6 +109,27 @@ def solve(stage, center_xy, inner_seg, outer_seg, L, closed=True, params=None):
         raise RuntimeError(f"orc_solve failed: {rc}")
     out["stats"] = st
     out["lap_time"] = st.lap_time
+    return out
+
+
+def centerline_geom(mids_xy, samples, inner_seg, outer_seg, closed=True, emit_closed_duplicate=True, params=None):
+    """The stage before the path on the CPU (geom_oracle.c): centre line + width/geometry rows of one track."""
+    mids_xy = _c(mids_xy).reshape(-1, 2)
+    inner_seg = _c(inner_seg).reshape(-1, 4)
+    outer_seg = _c(outer_seg).reshape(-1, 4)
+    params = params if params is not None else default_params()
+    L = lib()
+    rows = L.orc_geom_rows(int(samples), int(bool(closed)), int(bool(emit_closed_duplicate)))
+    out = {k: np.zeros(rows) for k in ("s_rel", "heading", "curvature", "dist_inner", "dist_outer", "width", "v_kappa")}
+    out["xy"] = np.zeros((rows, 2))
+    Lv, s0 = C.c_double(0.0), C.c_double(0.0)
+    rc = L.orc_centerline_geom(_p(mids_xy), mids_xy.shape[0], int(samples), int(bool(closed)), int(bool(emit_closed_duplicate)),
+                               _p(inner_seg), inner_seg.shape[0], _p(outer_seg), outer_seg.shape[0], C.byref(params),
+                               _p(out["xy"]), _p(out["s_rel"]), _p(out["heading"]), _p(out["curvature"]), _p(out["dist_inner"]),
+                               _p(out["dist_outer"]), _p(out["width"]), _p(out["v_kappa"]), C.byref(Lv), C.byref(s0))
+    if rc != rows:
+        raise RuntimeError(f"orc_centerline_geom failed: {rc}")
+    out["L"], out["s0"] = Lv.value, s0.value
     return out
 
 

@@ -46,6 +46,13 @@ int orc_solve(int stage, const double* center_xy, int n,
               double* out_alpha_total, double* out_alpha_last,
               double* out_v, double* out_ax, rl_job_stats* st);
 
+/* geom_oracle.c: the centre-line + width/geometry stage (main.cpp:404-474, 1270-1335) */
+int orc_geom_rows(int samples, int closed, int emit_dup);
+int orc_centerline_geom(const double* mids_xy, int n_mid, int samples, int closed, int emit_dup,
+                        const double* inner_seg, int m_in, const double* outer_seg, int m_out, const rl_params* C,
+                        double* out_xy, double* s_rel, double* heading, double* curvature,
+                        double* d_inner, double* d_outer, double* width, double* v_kappa, double* L_out, double* s0_out);
+
 #ifdef __cplusplus
 }
 #endif

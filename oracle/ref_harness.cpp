@@ -9,6 +9,11 @@
 //       rings, spline) and both solver stages exactly as main() does
 //       (main.cpp:1678-1696) and dumps hot-path inputs + outputs as raw doubles.
 //       If [samples] > 0 the dynamic sample count (main.cpp:1638-1641) is replaced by it.
+//   ref_harness geom <inner.csv> <outer.csv> <out.bin> [samples [open]]
+//       runs the reference front end up to the ordered mid points and the rings, then pipeline::make_centerline
+//       (main.cpp:1270) and the per-sample body of pipeline::compute_geom_and_save (main.cpp:1311-1329) through the
+//       reference's own Spline1D / distancesToRings, dumps inputs + outputs as raw doubles, and checks them against
+//       the *_with_geom.csv the reference itself writes (9 decimals).
 //   ref_harness solve <batch.bin> <out.bin> [first_job] [n_jobs]
 //       solves jobs of a packed batch file (format: oracle/batchfile.py) with
 //       cfg::get() set per job from the job's parameter row; records the
@@ -133,6 +138,100 @@ int run_frontend(int argc, char** argv)
     return 0;
 }
 
+
+// the width/geometry stage, driven through the reference's own functions
+int run_geom(int argc, char** argv)
+{
+    if (argc < 5) { std::fprintf(stderr, "usage: geom inner.csv outer.csv out.bin [samples [open]]\n"); return 1; }
+    const std::string innerPath = argv[2], outerPath = argv[3], outBin = argv[4];
+    const int forced_samples = (argc > 5) ? std::atoi(argv[5]) : 0;
+    auto& C = cfg::get();
+    C.verbose = false;
+    C.debug_dump = false;
+    if (argc > 6 && std::strcmp(argv[6], "open") == 0) C.is_closed_track = false;   // cfg is_closed_track, main.cpp:54
+    char tmpl[] = "/tmp/ref_harness_XXXXXX";
+    if (!mkdtemp(tmpl)) { std::perror("mkdtemp"); return 1; }
+    const std::string base = std::string(tmpl) + "/centerline";
+    std::ostringstream captured;
+    std::streambuf* old = std::cerr.rdbuf(captured.rdbuf());
+    auto inner = io::loadCSV_XY(innerPath);
+    auto outer = io::loadCSV_XY(outerPath);
+    const bool closed_mode = C.is_closed_track;
+    auto tri = pipeline::buildDT(inner, outer);
+    auto MF = pipeline::extract_mids_with_len_filter(tri, base);
+    if (C.use_dynamic_samples) C.samples = pipeline::dynamic_samples_from_mids_count((int)MF.mids.size());
+    if (forced_samples > 0) C.samples = forced_samples;
+    auto OM = pipeline::order_and_align_mids_open_closed(MF.mids, closed_mode);
+    auto RR = pipeline::reconstruct_rings_and_align(OM, MF, tri, base);
+    auto CL = pipeline::make_centerline(OM, closed_mode, base);
+    pipeline::compute_geom_and_save(base, CL.center, CL.spx, CL.spy, CL.s0, CL.L, closed_mode, RR.inner_from_mids, RR.outer_from_mids);
+    std::cerr.rdbuf(old);
+    auto innerE = closed_mode ? edges::ringEdges(RR.inner_from_mids) : edges::polylineEdges(RR.inner_from_mids);
+    auto outerE = closed_mode ? edges::ringEdges(RR.outer_from_mids) : edges::polylineEdges(RR.outer_from_mids);
+
+    // the loop of compute_geom_and_save (main.cpp:1306-1329), values kept in full precision
+    const int Ncenter = (int)CL.center.size();
+    const int Kmax = closed_mode ? C.samples : Ncenter;
+    const int denomN = closed_mode ? C.samples : std::max(1, C.samples);
+    std::vector<double> srel, xs, ys, hd, kp, din, dout, wid, vk;
+    for (int k = 0; k < Kmax; ++k) {
+        double si = CL.s0 + CL.L * (double(k) / double(denomN));
+        double x, xp, xpp, y, yp, ypp;
+        CL.spx.eval_with_deriv(si, x, xp, xpp);
+        CL.spy.eval_with_deriv(si, y, yp, ypp);
+        double heading = std::atan2(yp, xp);
+        double speed2 = xp * xp + yp * yp;
+        double denom = std::pow(std::max(1e-12, speed2), 1.5);
+        double curv = (xp * ypp - yp * xpp) / denom;
+        geom::Vec2 nvec = geom::normalize(geom::Vec2{-yp, xp}, 1e-12);
+        double d_in = 0.0, d_out = 0.0;
+        if (nvec.x != 0 || nvec.y != 0) distancesToRings({x, y}, nvec, innerE, outerE, d_in, d_out);
+        double denom_k = std::max(std::fabs(curv), C.kappa_eps);
+        double v_kappa = std::sqrt(C.a_lat_max / denom_k);
+        if (v_kappa > C.v_cap_mps) v_kappa = C.v_cap_mps;
+        srel.push_back(si - CL.s0); xs.push_back(x); ys.push_back(y); hd.push_back(heading); kp.push_back(curv);
+        din.push_back(d_in); dout.push_back(d_out); wid.push_back(d_in + d_out); vk.push_back(v_kappa);
+    }
+    // pin against what the reference wrote itself
+    {
+        std::ifstream fi(base + "_with_geom.csv");
+        std::string line;
+        std::getline(fi, line);
+        int k = 0;
+        double worst = 0.0;
+        while (std::getline(fi, line) && k < Kmax) {
+            double v[9];
+            if (std::sscanf(line.c_str(), "%lf,%lf,%lf,%lf,%lf,%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8]) != 9) break;
+            const double mine[9] = {srel[k], xs[k], ys[k], hd[k], kp[k], din[k], dout[k], wid[k], vk[k]};
+            for (int c = 0; c < 9; ++c) worst = std::max(worst, std::fabs(v[c] - mine[c]));
+            ++k;
+        }
+        if (k != Kmax || worst > 1.0e-9) { std::fprintf(stderr, "geom: harness loop disagrees with the reference CSV (rows %d/%d, worst %.3e)\n", k, Kmax, worst); return 3; }
+    }
+    FILE* f = std::fopen(outBin.c_str(), "wb");
+    if (!f) { std::perror("fopen"); return 1; }
+    put_i64(f, 0x314D4752);  // "RGM1"
+    put_i64(f, (int64_t)OM.ordered.size());
+    put_i64(f, (int64_t)C.samples);
+    put_i64(f, (int64_t)Kmax);
+    put_i64(f, (int64_t)innerE.size());
+    put_i64(f, (int64_t)outerE.size());
+    put_i64(f, closed_mode ? 1 : 0);
+    put_i64(f, C.emit_closed_duplicate ? 1 : 0);
+    put_f64(f, CL.L);
+    put_f64(f, CL.s0);
+    put_pts(f, OM.ordered);
+    for (auto& e : innerE) { put_f64(f, e.first.x); put_f64(f, e.first.y); put_f64(f, e.second.x); put_f64(f, e.second.y); }
+    for (auto& e : outerE) { put_f64(f, e.first.x); put_f64(f, e.first.y); put_f64(f, e.second.x); put_f64(f, e.second.y); }
+    put_pts(f, CL.center);                       // samples (+1 when the closing duplicate is emitted)
+    put_vec(f, srel); put_vec(f, xs); put_vec(f, ys); put_vec(f, hd); put_vec(f, kp); put_vec(f, din); put_vec(f, dout); put_vec(f, wid); put_vec(f, vk);
+    std::fclose(f);
+    std::string rm = std::string("rm -rf ") + tmpl;
+    if (std::system(rm.c_str()) != 0) {}
+    std::printf("mids=%zu samples=%d rows=%d Min=%zu Mout=%zu L=%.9f s0=%.9f\n", OM.ordered.size(), C.samples, Kmax, innerE.size(), outerE.size(), CL.L, CL.s0);
+    return 0;
+}
+
 template <class T> bool get_arr(FILE* f, std::vector<T>& v, size_t n) { v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
 
 // parameter row layout: the rl_params field order of include/raceline_b200.h (22 doubles, then 6 ints as doubles)
@@ -225,6 +324,7 @@ int main(int argc, char** argv)
 {
     if (argc >= 2 && std::strcmp(argv[1], "frontend") == 0) return run_frontend(argc, argv);
     if (argc >= 2 && std::strcmp(argv[1], "solve") == 0) return run_solve(argc, argv);
-    std::fprintf(stderr, "usage: %s frontend|solve ...\n", argv[0]);
+    if (argc >= 2 && std::strcmp(argv[1], "geom") == 0) return run_geom(argc, argv);
+    std::fprintf(stderr, "usage: %s frontend|solve|geom ...\n", argv[0]);
     return 1;
 }

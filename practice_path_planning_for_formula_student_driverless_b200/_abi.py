@@ -61,5 +61,21 @@ class RlBatchOut(C.Structure):
     ]
 
 
+class RlGeomDesc(C.Structure):
+    _fields_ = [
+        ("n_tracks", _I), ("emit_closed_duplicate", _I), ("mid_off", C.c_void_p), ("mids_xy", C.c_void_p),
+        ("samples", C.c_void_p), ("track_closed", C.c_void_p), ("seg_off", C.c_void_p), ("seg", C.c_void_p),
+        ("params", C.c_void_p),
+    ]
+
+
+class RlGeomOut(C.Structure):
+    _fields_ = [
+        ("xy", C.c_void_p), ("s_rel", C.c_void_p), ("heading", C.c_void_p), ("curvature", C.c_void_p),
+        ("dist_inner", C.c_void_p), ("dist_outer", C.c_void_p), ("width", C.c_void_p), ("v_kappa", C.c_void_p),
+        ("track_L", C.c_void_p), ("track_s0", C.c_void_p),
+    ]
+
+
 PARAM_DOUBLE_FIELDS = [n for n, t in RlParams._fields_ if t is _D]
 PARAM_INT_FIELDS = [n for n, t in RlParams._fields_ if t is _I]

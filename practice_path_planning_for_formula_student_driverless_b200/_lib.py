@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._abi import RlBatchDesc, RlBatchOut, RlJobStats, RlParams
+from ._abi import RlBatchDesc, RlBatchOut, RlGeomDesc, RlGeomOut, RlJobStats, RlParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libraceline_b200.so")
@@ -19,7 +19,8 @@ ABI_SYMBOLS = [
     "rl_set_stream", "rl_last_error", "rl_host_alloc", "rl_host_free", "rl_job_sample_offsets", "rl_solve_batch",
     "rl_batch_create", "rl_batch_upload", "rl_batch_solve", "rl_batch_download", "rl_batch_sync",
     "rl_batch_launches_per_solve", "rl_batch_destroy", "rl_compute_min_curvature_raceline",
-    "rl_compute_min_time_raceline", "rl_synth_tracks", "rl_measure_fp64_peak",
+    "rl_compute_min_time_raceline", "rl_geom_row_offsets", "rl_centerline_geom_batch", "rl_synth_tracks",
+    "rl_measure_fp64_peak",
 ]
 
 
@@ -81,6 +82,10 @@ def lib():
     L.rl_compute_min_curvature_raceline.restype = C.c_int
     L.rl_compute_min_time_raceline.argtypes = single + [dp, dp, dp, C.POINTER(RlJobStats)]
     L.rl_compute_min_time_raceline.restype = C.c_int
+    L.rl_geom_row_offsets.argtypes = [C.POINTER(RlGeomDesc), C.POINTER(C.c_int64)]
+    L.rl_geom_row_offsets.restype = C.c_int
+    L.rl_centerline_geom_batch.argtypes = [vp, C.POINTER(RlGeomDesc), C.POINTER(RlGeomOut)]
+    L.rl_centerline_geom_batch.restype = C.c_int
     L.rl_synth_tracks.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp]
     L.rl_synth_tracks.restype = C.c_int
     L.rl_measure_fp64_peak.argtypes = [vp, dp]

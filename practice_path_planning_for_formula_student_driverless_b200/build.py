@@ -15,8 +15,10 @@ LIB = os.path.join(CSRC, "libraceline_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-SOURCES = ["raceline_inst_256.cu", "raceline_inst_cluster.cu", "raceline_inst_512.cu", "raceline_inst_128.cu", "raceline_inst_64.cu", "raceline_inst_32.cu",
+SOURCES = ["raceline_inst_256.cu", "raceline_inst_cluster.cu", "raceline_geom.cu", "raceline_inst_512.cu", "raceline_inst_128.cu", "raceline_inst_64.cu", "raceline_inst_32.cu",
            "raceline_dispatch.cu", "raceline_api.cu", "synth_tracks.cpp"]
+# the geometry stage reproduces the reference's x86-64 arithmetic bit for bit: no FMA contraction in that unit
+EXTRA_FLAGS = {"raceline_geom.cu": ["-fmad=false"]}
 HEADERS = [os.path.join(CSRC, "raceline_device.h"), os.path.join(CSRC, "raceline_kernels.cuh"), os.path.join(CSRC, "raceline_cluster.cuh"),
            os.path.join(HERE, "..", "include", "raceline_b200.h")]
 
@@ -44,7 +46,7 @@ def build(force=False, verbose=False):
         sp = os.path.join(CSRC, src)
         if not (force or _stale(obj, [sp] + HEADERS)):
             return
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", sp, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", sp, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)

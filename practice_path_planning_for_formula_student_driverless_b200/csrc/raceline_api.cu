@@ -271,6 +271,18 @@ DevBatch dev_view(const rl_batch* b)
     return B;
 }
 
+struct DevFree {
+    std::vector<void*> ptrs;
+    ~DevFree() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> cudaError_t alloc(T** p, size_t n)
+    {
+        *p = nullptr;
+        cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+
 static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
 
 }  // namespace
@@ -640,6 +652,94 @@ int rl_compute_min_time_raceline(rl_ctx* ctx, const double* center_xy, int n, co
 {
     return solve_single(ctx, RL_STAGE_MINTIME, center_xy, n, inner_seg, m_inner, outer_seg, m_outer, veh_width, L, closed, p,
                         raceline_xy, heading, curvature, alpha_total, alpha_last, v, ax, lap_time, stats);
+}
+
+int rl_geom_row_offsets(const rl_geom_desc* d, int64_t* off)
+{
+    if (!d || !off || d->n_tracks < 0 || (d->n_tracks > 0 && (!d->samples || !d->track_closed))) return RL_ERR_ARG;
+    off[0] = 0;
+    for (int t = 0; t < d->n_tracks; ++t) {
+        if (d->samples[t] < 1) return RL_ERR_ARG;
+        off[t + 1] = off[t] + d->samples[t] + ((!d->track_closed[t] && d->emit_closed_duplicate) ? 1 : 0);   // Kmax, main.cpp:1308
+    }
+    return RL_OK;
+}
+
+// pipeline::make_centerline + the per-sample body of pipeline::compute_geom_and_save (main.cpp:1270-1335), batched
+int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out* o)
+{
+    if (!c || !d || !o) return RL_ERR_ARG;
+    if (d->n_tracks < 0) return fail(c, RL_ERR_ARG, "negative track count");
+    if (d->n_tracks == 0) return RL_OK;
+    if (!d->mid_off || !d->mids_xy || !d->samples || !d->track_closed || !d->seg_off || !d->params)
+        return fail(c, RL_ERR_ARG, "null array in geometry descriptor");
+    const int nt = d->n_tracks;
+    if (d->mid_off[0] != 0 || d->seg_off[0] != 0) return fail(c, RL_ERR_ARG, "offset arrays must start at 0");
+    int max_pts = 0;
+    for (int t = 0; t < nt; ++t) {
+        const long long nm = d->mid_off[t + 1] - d->mid_off[t];
+        if (nm < 3) return fail(c, RL_ERR_ARG, "a track needs at least 3 ordered mid points (main.cpp:452)");
+        if (d->seg_off[2 * t + 1] < d->seg_off[2 * t] || d->seg_off[2 * t + 2] < d->seg_off[2 * t + 1]) return fail(c, RL_ERR_ARG, "seg_off not monotone");
+        const long long pts = nm + (d->track_closed[t] ? 6 : 0);
+        if (pts > rl::geom_max_points()) return fail(c, RL_ERR_UNSUPPORTED, "too many mid points for one track");
+        max_pts = std::max(max_pts, (int)pts);
+    }
+    if (d->seg_off[2 * nt] > 0 && !d->seg) return fail(c, RL_ERR_ARG, "null seg");
+    std::vector<long long> row_off((size_t)nt + 1);
+    {
+        std::vector<int64_t> ro((size_t)nt + 1);
+        const int st = rl_geom_row_offsets(d, ro.data());
+        if (st != RL_OK) return fail(c, st, "samples must be >= 1");
+        for (int t = 0; t <= nt; ++t) row_off[t] = ro[t];
+    }
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    const size_t rows = (size_t)row_off[nt], n_mid = (size_t)d->mid_off[nt], n_seg = (size_t)d->seg_off[2 * nt];
+    DevFree mem;
+    long long *d_mid_off, *d_seg_off, *d_row_off;
+    double *d_mids, *d_seg, *d_out, *d_L, *d_s0;
+    int *d_samples, *d_closed;
+    RL_CUDA(c, mem.alloc(&d_mid_off, (size_t)nt + 1));
+    RL_CUDA(c, mem.alloc(&d_seg_off, (size_t)2 * nt + 1));
+    RL_CUDA(c, mem.alloc(&d_row_off, (size_t)nt + 1));
+    RL_CUDA(c, mem.alloc(&d_mids, 2 * n_mid));
+    RL_CUDA(c, mem.alloc(&d_seg, 4 * n_seg + 4));
+    RL_CUDA(c, mem.alloc(&d_samples, (size_t)nt));
+    RL_CUDA(c, mem.alloc(&d_closed, (size_t)nt));
+    RL_CUDA(c, mem.alloc(&d_out, 9 * rows + 16));      // xy (2), s_rel, heading, curvature, dist_inner, dist_outer, width, v_kappa
+    RL_CUDA(c, mem.alloc(&d_L, (size_t)nt));
+    RL_CUDA(c, mem.alloc(&d_s0, (size_t)nt));
+    RL_CUDA(c, cudaMemcpyAsync(d_mid_off, d->mid_off, sizeof(long long) * ((size_t)nt + 1), cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(d_seg_off, d->seg_off, sizeof(long long) * ((size_t)2 * nt + 1), cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(d_row_off, row_off.data(), sizeof(long long) * ((size_t)nt + 1), cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(d_mids, d->mids_xy, sizeof(double) * 2 * n_mid, cudaMemcpyHostToDevice, s));
+    if (n_seg) RL_CUDA(c, cudaMemcpyAsync(d_seg, d->seg, sizeof(double) * 4 * n_seg, cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(d_samples, d->samples, sizeof(int) * (size_t)nt, cudaMemcpyHostToDevice, s));
+    RL_CUDA(c, cudaMemcpyAsync(d_closed, d->track_closed, sizeof(int) * (size_t)nt, cudaMemcpyHostToDevice, s));
+    rl::GeomBatch G;
+    G.mid_off = d_mid_off; G.mids_xy = d_mids; G.samples = d_samples; G.closed = d_closed; G.seg_off = d_seg_off; G.seg = d_seg;
+    G.row_off = d_row_off; G.kappa_eps = d->params->kappa_eps; G.a_lat_max = d->params->a_lat_max; G.v_cap = d->params->v_cap_mps;
+    G.emit_dup = d->emit_closed_duplicate;
+    G.xy = d_out; G.s_rel = d_out + 2 * rows; G.heading = G.s_rel + rows; G.curvature = G.heading + rows;
+    G.dist_inner = G.curvature + rows; G.dist_outer = G.dist_inner + rows; G.width = G.dist_outer + rows; G.v_kappa = G.width + rows;
+    G.track_L = d_L; G.track_s0 = d_s0;
+    const int e = rl::launch_geom(G, nt, max_pts, s);
+    if (e != 0) return cuda_fail(c, (cudaError_t)e, "geometry kernels");
+    if (rows) {
+        if (o->xy) RL_CUDA(c, cudaMemcpyAsync(o->xy, G.xy, 16 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->s_rel) RL_CUDA(c, cudaMemcpyAsync(o->s_rel, G.s_rel, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->heading) RL_CUDA(c, cudaMemcpyAsync(o->heading, G.heading, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->curvature) RL_CUDA(c, cudaMemcpyAsync(o->curvature, G.curvature, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->dist_inner) RL_CUDA(c, cudaMemcpyAsync(o->dist_inner, G.dist_inner, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->dist_outer) RL_CUDA(c, cudaMemcpyAsync(o->dist_outer, G.dist_outer, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->width) RL_CUDA(c, cudaMemcpyAsync(o->width, G.width, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->v_kappa) RL_CUDA(c, cudaMemcpyAsync(o->v_kappa, G.v_kappa, 8 * rows, cudaMemcpyDeviceToHost, s));
+    }
+    if (o->track_L) RL_CUDA(c, cudaMemcpyAsync(o->track_L, d_L, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, s));
+    if (o->track_s0) RL_CUDA(c, cudaMemcpyAsync(o->track_s0, d_s0, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, s));
+    RL_CUDA(c, cudaStreamSynchronize(s));
+    RL_CUDA(c, cudaGetLastError());
+    return RL_OK;
 }
 
 int rl_measure_fp64_peak(rl_ctx* c, double* tflops)

@@ -75,6 +75,27 @@ inline int cluster_size_for_n(long long n, int force = 0)
 int launch_solve_cluster(const DevBatch& B, const int* job_list, int n_list, int cs, int mode, void* stream);
 int configure_solve_cluster();
 
+// ---- the stage before the path (raceline_geom.cu): centre line + width/geometry rows, batched over tracks ----
+struct GeomBatch {
+    const long long* mid_off;   // [n_tracks+1]
+    const double* mids_xy;
+    const int* samples;
+    const int* closed;
+    const long long* seg_off;   // [2*n_tracks+1]
+    const double* seg;
+    const long long* row_off;   // [n_tracks+1]
+    double kappa_eps, a_lat_max, v_cap;
+    int emit_dup;
+    double* xy; double* s_rel; double* heading; double* curvature;
+    double* dist_inner; double* dist_outer; double* width; double* v_kappa;
+    double* track_L; double* track_s0;
+};
+
+size_t geom_centerline_smem(int max_pts);
+int geom_max_points();          // padded mid points one track may have
+int configure_geom();
+int launch_geom(const GeomBatch& G, int n_tracks, int max_pts, void* stream);   // returns a cudaError_t as int
+
 // launches job_list[0..n_list) (indices into B.jobs) with the kernel of class `cls` and mode
 // 0 = closed track, 1 = closed track and every job has N == T*K, 2 = open track.  One CTA per ITEM: item k is the chain
 // job_list[item_off[k] .. item_off[k+1]) of jobs on the same track (item_off has n_items+1 entries, relative to

@@ -34,6 +34,7 @@ int configure_kernels()
     if (!e) e = configure_solve_256();
     if (!e) e = configure_solve_512();
     if (!e) e = configure_solve_cluster();
+    if (!e) e = configure_geom();
     return e;
 }
 

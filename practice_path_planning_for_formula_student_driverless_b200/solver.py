@@ -393,6 +393,72 @@ def solve_batch(tracks: Sequence[Track], configs: Sequence[Config], jobs, ctx: O
     return [pb.result(j) for j in range(pb.n_jobs)]
 
 
+@dataclass
+class CenterlineGeom:
+    """One track's rows of <base>_with_geom.csv (main.cpp:1304) plus CL.L / CL.s0 (main.cpp:1255-1259)."""
+    xy: np.ndarray
+    s: np.ndarray
+    heading: np.ndarray
+    curvature: np.ndarray
+    dist_inner: np.ndarray
+    dist_outer: np.ndarray
+    width: np.ndarray
+    v_kappa: np.ndarray
+    L: float
+    s0: float
+    samples: int
+
+    @property
+    def center_for_opt(self) -> np.ndarray:
+        """The centre line the solver stages take (main.cpp:1681-1683): the first `samples` rows."""
+        return self.xy[:self.samples]
+
+
+def centerline_geom_batch(mids: Sequence[np.ndarray], samples: Sequence[int], inner_rings: Sequence[np.ndarray],
+                          outer_rings: Sequence[np.ndarray], closed=True, cfg: Optional[Config] = None,
+                          ctx: Optional[Context] = None, emit_closed_duplicate=True) -> List[CenterlineGeom]:
+    """pipeline::make_centerline + the per-sample body of pipeline::compute_geom_and_save (main.cpp:1270-1335) for a
+    batch of tracks: ordered mid points in, centre line + heading/curvature/ring distances/width/v_kappa rows out.
+    `inner_rings` / `outer_rings` are segment arrays (ring_edges / polyline_edges of the *_from_mids points)."""
+    from ._abi import RlGeomDesc, RlGeomOut
+    cfg = cfg or Config()
+    ctx = ctx or default_context()
+    nt = len(mids)
+    closed_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(closed, dtype=bool), (nt,)).astype(np.int32))
+    mids = [_f64(m, 2) for m in mids]
+    segs = []
+    for a, b in zip(inner_rings, outer_rings):
+        segs += [_f64(a, 4), _f64(b, 4)]
+    mid_off = np.zeros(nt + 1, dtype=np.int64)
+    mid_off[1:] = np.cumsum([m.shape[0] for m in mids])
+    seg_off = np.zeros(2 * nt + 1, dtype=np.int64)
+    seg_off[1:] = np.cumsum([g.shape[0] for g in segs])
+    mids_xy = np.ascontiguousarray(np.concatenate(mids, axis=0)) if nt else np.zeros((0, 2))
+    seg = np.ascontiguousarray(np.concatenate(segs, axis=0)) if segs else np.zeros((0, 4))
+    smp = np.ascontiguousarray(np.asarray(samples, dtype=np.int32).reshape(nt))
+    p = cfg.to_params()
+    d = RlGeomDesc()
+    d.n_tracks, d.emit_closed_duplicate = nt, int(bool(emit_closed_duplicate))
+    d.mid_off, d.mids_xy, d.samples, d.track_closed = _ptr(mid_off), _ptr(mids_xy), _ptr(smp), _ptr(closed_arr)
+    d.seg_off, d.seg, d.params = _ptr(seg_off), _ptr(seg), C.cast(C.pointer(p), C.c_void_p)
+    off = np.zeros(nt + 1, dtype=np.int64)
+    ctx._check(lib().rl_geom_row_offsets(C.byref(d), off.ctypes.data_as(C.POINTER(C.c_int64))), "rl_geom_row_offsets")
+    rows = int(off[nt])
+    arr = {k: np.zeros(rows) for k in ("s_rel", "heading", "curvature", "dist_inner", "dist_outer", "width", "v_kappa")}
+    xy, Lv, s0 = np.zeros((rows, 2)), np.zeros(nt), np.zeros(nt)
+    o = RlGeomOut()
+    o.xy, o.track_L, o.track_s0 = _ptr(xy), _ptr(Lv), _ptr(s0)
+    for k, a in arr.items():
+        setattr(o, k, _ptr(a))
+    ctx._check(lib().rl_centerline_geom_batch(ctx._h, C.byref(d), C.byref(o)), "rl_centerline_geom_batch")
+    out = []
+    for t in range(nt):
+        a, b = int(off[t]), int(off[t + 1])
+        out.append(CenterlineGeom(xy[a:b], arr["s_rel"][a:b], arr["heading"][a:b], arr["curvature"][a:b], arr["dist_inner"][a:b],
+                                  arr["dist_outer"][a:b], arr["width"][a:b], arr["v_kappa"][a:b], float(Lv[t]), float(s0[t]), int(smp[t])))
+    return out
+
+
 def synth_tracks(n_tracks, n_samples, m_per_ring=None, seed_base=0xB200, first_id=0, threads=0, pool=None):
     """Deterministic synthetic closed tracks; returns packed arrays (center_xy, seg, L)."""
     m = int(round(n_samples / 2.2)) if m_per_ring is None else int(m_per_ring)

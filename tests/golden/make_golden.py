@@ -166,6 +166,30 @@ def open_golden(base):
     return out
 
 
+def geom_golden(name, samples=0, open_track=False):
+    """The centre-line + width/geometry stage through the reference's own functions (`ref_harness geom`, which also
+    checks itself against the *_with_geom.csv the reference writes); pins geom_oracle.c bit for bit."""
+    with tempfile.TemporaryDirectory() as td:
+        o = os.path.join(td, "g.bin")
+        cmd = [os.path.join(ROOT, "oracle", "_ref", "ref_harness"), "geom", f"{REF}/csv/{name}_inner.csv",
+               f"{REF}/csv/{name}_outer.csv", o] + ([str(samples)] if (samples or open_track) else []) + (["open"] if open_track else [])
+        res = subprocess.run(cmd, check=True, capture_output=True, text=True)
+        print(f"  geom: {res.stdout.strip()}")
+        d = batchfile.read_rgm1(o)
+    r = oracle.centerline_geom(d["mids_xy"], d["samples"], d["inner_seg"], d["outer_seg"], bool(d["closed"]),
+                               bool(d["emit_closed_duplicate"]))
+    pairs = [("L", r["L"], d["L"]), ("s0", r["s0"], d["s0"]), ("x", r["xy"][:, 0], d["x"]), ("y", r["xy"][:, 1], d["y"])]
+    pairs += [(k, r[k], d[k]) for k in ("s_rel", "curvature", "dist_inner", "dist_outer", "width", "v_kappa")]
+    for k, a, b in pairs:
+        if not np.array_equal(np.asarray(a), np.asarray(b)):
+            raise SystemExit(f"[geom {name}] port differs from the reference in {k}: max |d| = {np.max(np.abs(np.asarray(a) - np.asarray(b))):.3e}")
+    # heading goes through libm atan2 on both sides here, so it is bitwise too
+    if not np.array_equal(r["heading"], d["heading"]):
+        raise SystemExit(f"[geom {name}] heading differs")
+    assert np.array_equal(d["center_xy"][:d["samples"], 0], d["x"][:d["samples"]])   # centre line == geometry x,y
+    return d
+
+
 def main():
     if not os.path.exists(f"{REF}/src/main.cpp"):
         raise SystemExit("the reference is not mounted; goldens can only be regenerated in the build container")
@@ -189,6 +213,12 @@ def main():
         b = dict(np.load(os.path.join(OUT, name + ".npz")))
         b = {k: (v.item() if v.ndim == 0 else v) for k, v in b.items()}
         np.savez_compressed(os.path.join(OUT, f"open_{name}.npz"), **open_golden(b))
+    print("centre line + width/geometry stage (SURVEY 8f rows 1-2)")
+    for name, smp in (("training_map", 0), ("competition_map1", 0), ("competition_map_testday2", 0), ("competition_map2", 1000)):
+        d = geom_golden(name, smp)
+        np.savez_compressed(os.path.join(OUT, f"geom_{name}" + (f"_n{smp}" if smp else "") + ".npz"), **d)
+    d = geom_golden("competition_map3", 0, open_track=True)      # cfg is_closed_track = false: no padding, polyline edges
+    np.savez_compressed(os.path.join(OUT, "geom_open_competition_map3.npz"), **d)
     print("oracle port == reference, bit for bit, on every golden case")
 
 

@@ -31,6 +31,10 @@ extern "C" {
 /* job stages (one solve of the BASELINE metric = one MINCURV job + one MINTIME job) */
 #define RL_STAGE_MINCURV 1 /* compute_min_curvature_raceline, main.cpp:683 */
 #define RL_STAGE_MINTIME 2 /* compute_min_time_raceline,      main.cpp:905 */
+/* profile of a GIVEN path, no optimisation: heading_curv_from_points_generic (main.cpp:595) with h = L/N, then
+ * velocity_profile_forward_backward (main.cpp:782) -> heading, curvature, v, ax, lap_time; xy = the input path, alpha = 0.
+ * This is what the reference's debug block computes for the centre line and the min-curv path (main.cpp:1464-1477). */
+#define RL_STAGE_EVAL 3
 
 /* per-outer-iteration log depth kept in rl_job_stats (cfg max_outer_iters defaults to 14) */
 #define RL_MAX_OUTER_LOG 32

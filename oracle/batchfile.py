@@ -132,3 +132,32 @@ def read_rgm1(path):
         d[k] = f64(rows)
     assert pos == raw.size, "trailing bytes in RGM1 file"
     return d
+
+
+MAGIC_D = 0x31474452  # "RDG1": one `ref_harness debug` dump
+
+
+def read_rdg1(path):
+    """Return a dict for one `ref_harness debug` dump (the reference's debug comparison, main.cpp:1440-1593)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    hdr = raw[:48].view(np.int64)
+    assert hdr[0] == MAGIC_D, "not an RDG1 file"
+    n, n_mc, rows, m_in, m_out = (int(x) for x in hdr[1:6])
+    pos = 48
+
+    def f64(count):
+        nonlocal pos
+        out = raw[pos:pos + 8 * count].view(np.float64).copy()
+        pos += 8 * count
+        return out
+
+    d = {"n": n, "rows": rows}
+    for k in ("L", "s0", "lap_center", "lap_mincurv", "lap_mintime", "L_mc"):
+        d[k] = float(f64(1)[0])
+    d["center_xy"] = f64(2 * n).reshape(n, 2)
+    d["mc_xy"] = f64(2 * n_mc).reshape(n_mc, 2)
+    d["inner_seg"] = f64(4 * m_in).reshape(m_in, 4)
+    d["outer_seg"] = f64(4 * m_out).reshape(m_out, 4)
+    d["columns"] = f64(20 * rows).reshape(rows, 20)
+    assert pos == raw.size, "trailing bytes in RDG1 file"
+    return d

@@ -396,8 +396,21 @@ int orc_solve(int stage, const double* center_xy, int n,
               double* out_v, double* out_ax, rl_job_stats* st)
 {
     if (st) { memset(st, 0, sizeof(*st)); st->n = n; }
-    if (stage != RL_STAGE_MINCURV && stage != RL_STAGE_MINTIME) return RL_ERR_ARG;
+    if (stage != RL_STAGE_MINCURV && stage != RL_STAGE_MINTIME && stage != RL_STAGE_EVAL) return RL_ERR_ARG;
     if (n == 0) return RL_OK;                                  /* main.cpp:689 / 912 */
+    if (stage == RL_STAGE_EVAL) {
+        /* the debug block's extra laps, main.cpp:1464-1477: heading/curvature of the given points with h = L/N, then the v(s) profile */
+        const double hh = L / (double)n;
+        double* tmp = (double*)malloc(sizeof(double) * 2 * (size_t)n);
+        if (!tmp) return RL_ERR_NOMEM;
+        for (int i = 0; i < n; ++i) { out_alpha_total[i] = 0.0; out_alpha_last[i] = 0.0; }
+        memcpy(out_xy, center_xy, sizeof(double) * 2 * (size_t)n);
+        orc_heading_curv(center_xy, n, hh, closed, out_heading, out_curv);
+        double lap = orc_velocity_profile(C, out_curv, n, hh, closed, out_v ? out_v : tmp, out_ax ? out_ax : tmp + n);
+        if (st) st->lap_time = lap;
+        free(tmp);
+        return RL_OK;
+    }
     const int mt = (stage == RL_STAGE_MINTIME);
     const double h = L / (double)n;                            /* main.cpp:690 / 913 */
 

@@ -14,6 +14,11 @@
 //       (main.cpp:1270) and the per-sample body of pipeline::compute_geom_and_save (main.cpp:1311-1329) through the
 //       reference's own Spline1D / distancesToRings, dumps inputs + outputs as raw doubles, and checks them against
 //       the *_with_geom.csv the reference itself writes (9 decimals).
+//   ref_harness debug <inner.csv> <outer.csv> <out.bin>
+//       runs the two stage wrappers with cfg debug_dump = true exactly as main() does (main.cpp:1684, 1694) and dumps
+//       the 20 columns of the <base>_debug_compare_paths.csv the reference writes (main.cpp:1493-1495), the min-curv
+//       path it re-reads from <base>_raceline.csv, and the centre-line / min-curv laps of main.cpp:1464-1477 recomputed
+//       through the reference's own functions in full precision.
 //   ref_harness solve <batch.bin> <out.bin> [first_job] [n_jobs]
 //       solves jobs of a packed batch file (format: oracle/batchfile.py) with
 //       cfg::get() set per job from the job's parameter row; records the
@@ -232,6 +237,91 @@ int run_geom(int argc, char** argv)
     return 0;
 }
 
+// the debug comparison of pipeline::compute_mintime_and_save
+int run_debug(int argc, char** argv)
+{
+    if (argc < 5) { std::fprintf(stderr, "usage: debug inner.csv outer.csv out.bin\n"); return 1; }
+    const std::string innerPath = argv[2], outerPath = argv[3], outBin = argv[4];
+    auto& C = cfg::get();
+    C.verbose = false;
+    C.debug_dump = true;
+    char tmpl[] = "/tmp/ref_harness_XXXXXX";
+    if (!mkdtemp(tmpl)) { std::perror("mkdtemp"); return 1; }
+    const std::string base = std::string(tmpl) + "/centerline";
+    std::ostringstream captured;
+    std::streambuf* old = std::cerr.rdbuf(captured.rdbuf());
+    auto inner = io::loadCSV_XY(innerPath);
+    auto outer = io::loadCSV_XY(outerPath);
+    const bool closed_mode = C.is_closed_track;
+    auto tri = pipeline::buildDT(inner, outer);
+    auto MF = pipeline::extract_mids_with_len_filter(tri, base);
+    if (C.use_dynamic_samples) C.samples = pipeline::dynamic_samples_from_mids_count((int)MF.mids.size());
+    auto OM = pipeline::order_and_align_mids_open_closed(MF.mids, closed_mode);
+    auto RR = pipeline::reconstruct_rings_and_align(OM, MF, tri, base);
+    auto CL = pipeline::make_centerline(OM, closed_mode, base);
+    std::vector<geom::Vec2> center_for_opt = CL.center;
+    if (closed_mode && center_for_opt.size() >= 2 && geom::almostEq(center_for_opt.front(), center_for_opt.back(), 1e-12))
+        center_for_opt.pop_back();
+    pipeline::compute_raceline_and_save(base, center_for_opt, CL.s0, CL.L, closed_mode, RR.inner_from_mids, RR.outer_from_mids);
+    pipeline::compute_mintime_and_save(base, center_for_opt, CL.s0, CL.L, closed_mode, RR.inner_from_mids, RR.outer_from_mids);
+    std::cerr.rdbuf(old);
+    // the min-curv path as the debug block sees it (main.cpp:1454-1461) and the two extra laps (main.cpp:1464-1477)
+    std::vector<geom::Vec2> mc = io::loadCSV_XY(base + "_raceline.csv");
+    if (!mc.empty() && closed_mode && mc.size() >= 2 && geom::almostEq(mc.front(), mc.back(), 1e-12)) mc.pop_back();
+    const double Hc = center_for_opt.size() > 0 ? (CL.L / std::max(1, (int)center_for_opt.size())) : 1.0;
+    std::vector<double> hd, kp;
+    raceline_min_curv::heading_curv_from_points_generic(center_for_opt, Hc, closed_mode, hd, kp);
+    auto VPc = raceline_min_time::velocity_profile_forward_backward(kp, Hc, closed_mode);
+    double Lmc = 0.0;
+    for (size_t i = 0; i + 1 < mc.size(); ++i) Lmc += std::hypot(mc[i + 1].x - mc[i].x, mc[i + 1].y - mc[i].y);
+    if (closed_mode && mc.size() >= 2) Lmc += std::hypot(mc[0].x - mc.back().x, mc[0].y - mc.back().y);
+    const double Hmc = Lmc / std::max(1, (int)mc.size());
+    raceline_min_curv::heading_curv_from_points_generic(mc, Hmc, closed_mode, hd, kp);
+    auto VPmc = raceline_min_time::velocity_profile_forward_backward(kp, Hmc, closed_mode);
+    // the CSV the reference wrote
+    std::vector<double> cols;
+    int rows = 0;
+    {
+        std::ifstream fi(base + "_debug_compare_paths.csv");
+        std::string line;
+        std::getline(fi, line);
+        while (std::getline(fi, line)) {
+            std::istringstream ls(line);
+            std::string tok;
+            int c = 0;
+            while (std::getline(ls, tok, ',')) { cols.push_back(std::atof(tok.c_str())); ++c; }
+            if (c != 20) { std::fprintf(stderr, "debug csv: %d columns\n", c); return 3; }
+            ++rows;
+        }
+    }
+    // the lap the min-time stage itself reported: "[mintime] Estimated laptime: x s" (main.cpp:1437) -- recompute exactly instead
+    auto innerE = closed_mode ? edges::ringEdges(RR.inner_from_mids) : edges::polylineEdges(RR.inner_from_mids);
+    auto outerE = closed_mode ? edges::ringEdges(RR.outer_from_mids) : edges::polylineEdges(RR.outer_from_mids);
+    std::cerr.rdbuf(captured.rdbuf());
+    auto mt = raceline_min_time::compute_min_time_raceline(center_for_opt, innerE, outerE, C.veh_width_m, CL.L, closed_mode);
+    std::cerr.rdbuf(old);
+    FILE* f = std::fopen(outBin.c_str(), "wb");
+    if (!f) { std::perror("fopen"); return 1; }
+    put_i64(f, 0x31474452);  // "RDG1"
+    put_i64(f, (int64_t)center_for_opt.size());
+    put_i64(f, (int64_t)mc.size());
+    put_i64(f, (int64_t)rows);
+    put_i64(f, (int64_t)innerE.size());
+    put_i64(f, (int64_t)outerE.size());
+    put_f64(f, CL.L); put_f64(f, CL.s0); put_f64(f, VPc.lap_time); put_f64(f, VPmc.lap_time); put_f64(f, mt.lap_time); put_f64(f, Lmc);
+    put_pts(f, center_for_opt);
+    put_pts(f, mc);
+    for (auto& e : innerE) { put_f64(f, e.first.x); put_f64(f, e.first.y); put_f64(f, e.second.x); put_f64(f, e.second.y); }
+    for (auto& e : outerE) { put_f64(f, e.first.x); put_f64(f, e.first.y); put_f64(f, e.second.x); put_f64(f, e.second.y); }
+    put_vec(f, cols);
+    std::fclose(f);
+    std::string rm = std::string("rm -rf ") + tmpl;
+    if (std::system(rm.c_str()) != 0) {}
+    std::printf("N=%zu mc=%zu rows=%d lap_center=%.9f lap_mincurv=%.9f lap_mintime=%.9f\n", center_for_opt.size(), mc.size(), rows,
+                VPc.lap_time, VPmc.lap_time, mt.lap_time);
+    return 0;
+}
+
 template <class T> bool get_arr(FILE* f, std::vector<T>& v, size_t n) { v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
 
 // parameter row layout: the rl_params field order of include/raceline_b200.h (22 doubles, then 6 ints as doubles)
@@ -325,6 +415,7 @@ int main(int argc, char** argv)
     if (argc >= 2 && std::strcmp(argv[1], "frontend") == 0) return run_frontend(argc, argv);
     if (argc >= 2 && std::strcmp(argv[1], "solve") == 0) return run_solve(argc, argv);
     if (argc >= 2 && std::strcmp(argv[1], "geom") == 0) return run_geom(argc, argv);
-    std::fprintf(stderr, "usage: %s frontend|solve|geom ...\n", argv[0]);
+    if (argc >= 2 && std::strcmp(argv[1], "debug") == 0) return run_debug(argc, argv);
+    std::fprintf(stderr, "usage: %s frontend|solve|geom|debug ...\n", argv[0]);
     return 1;
 }

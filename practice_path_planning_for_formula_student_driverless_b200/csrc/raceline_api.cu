@@ -129,7 +129,7 @@ int validate_desc(rl_ctx* c, const rl_batch_desc* d)
         const rl_job& jb = d->jobs[j];
         if (jb.track < 0 || jb.track >= d->n_tracks) return fail(c, RL_ERR_ARG, "job.track out of range");
         if (jb.param < 0 || jb.param >= d->n_params) return fail(c, RL_ERR_ARG, "job.param out of range");
-        if (jb.stage != RL_STAGE_MINCURV && jb.stage != RL_STAGE_MINTIME) return fail(c, RL_ERR_ARG, "job.stage invalid");
+        if (jb.stage != RL_STAGE_MINCURV && jb.stage != RL_STAGE_MINTIME && jb.stage != RL_STAGE_EVAL) return fail(c, RL_ERR_ARG, "job.stage invalid");
     }
     return RL_OK;
 }
@@ -186,8 +186,9 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
             int run = 0, last_t = -1;
             for (size_t q = 0; q < bucket[k].size(); ++q) {
                 const int t = d->jobs[bucket[k][q]].track;
-                if (q == 0 || t != last_t || run >= chain) { b->itemoff.push_back((int)q); ++l.n_items; run = 0; }
-                last_t = t; ++run;
+                const bool eval_job = (d->jobs[bucket[k][q]].stage == RL_STAGE_EVAL);     // no corridor state to share
+                if (q == 0 || t != last_t || run >= chain || eval_job) { b->itemoff.push_back((int)q); ++l.n_items; run = 0; }
+                last_t = eval_job ? -1 : t; ++run;
             }
             b->itemoff.push_back((int)bucket[k].size());
             b->lists.push_back(l);

@@ -524,7 +524,8 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
     const int trk = job.track;
     const long long s0 = B.samp_off[trk];
     const int N = (int)(B.samp_off[trk + 1] - s0);
-    const bool mt = (job.stage == RL_STAGE_MINTIME);
+    const bool ev = (job.stage == RL_STAGE_EVAL);      // profile of the given path only
+    const bool mt = (job.stage == RL_STAGE_MINTIME) || ev;
     const double h = B.track_L[trk] / (double)N;
     {
         const int base = N / (int)cl.CS, rem = N % (int)cl.CS, r = (int)cl.rank;
@@ -595,12 +596,15 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
     long long ray_tests = 0;
     int vrounds = 0, ph = 0, fslot = 0;
     int acc_total = 0, bt_total = 0, ev_total = 0;
-    const int max_outer = C.max_outer_iters;
+    const int max_outer = ev ? 0 : C.max_outer_iters;
 
     double lo[K], hi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { lo[k] = 0.0; hi[k] = 0.0; }
     // initial corridor from the centre line: guard uses the veh_width ARGUMENT (main.cpp:706 / 930)
-    corridor_stream_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, B.seg, segI0, segO0, segE,
-                         C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+    if (!ev)
+        corridor_stream_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, B.seg, segI0, segO0, segE,
+                             C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
 
     double* sC0 = sB + tid;
     double* sCp = sB + NP + tid;

@@ -1248,9 +1248,9 @@ __device__ __noinline__ float cone_scan(const RayTile& tl_in, float ax, float ay
 {
     const RayTile tl = tile_in_smem(tl_in);
     const float e = 2.f * m + 1e-6f;
-    // a cone wider than 30 degrees is never needed (and never wider than 90: only a CONVEX cone keeps
-    // origin + t*direction inside), so everything outside the 30-degree cone is skipped from the start
-    float cbest = 0.8660254f;
+    // a cone wider than 20 degrees is never needed (and never wider than 90: only a CONVEX cone keeps
+    // origin + t*direction inside), so everything outside the 20-degree cone is skipped from the start
+    float cbest = 0.9396926f;
     int sb0 = hint / SU;
     if (sb0 >= tl.nsup) sb0 = 0;
     for (int q = 0; q < tl.nsup; ++q) {
@@ -1843,7 +1843,8 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
     const long long s0 = B.samp_off[trk];
     const int N = (int)(B.samp_off[trk + 1] - s0);
     const long long row0 = B.job_off[jid];
-    const bool mt = (job.stage == RL_STAGE_MINTIME);
+    const bool ev = (job.stage == RL_STAGE_EVAL);      // profile of the given path only: no corridor, no optimisation
+    const bool mt = (job.stage == RL_STAGE_MINTIME) || ev;
     const double h = B.track_L[trk] / (double)N;
     const bool closed = (MODE != kModeOpen);
 
@@ -1902,12 +1903,14 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
     long long ray_tests = 0;
     int vrounds = 0, ph = 0, ex_scans = 0;
     int acc_total = 0, bt_total = 0, ev_total = 0;
-    const int max_outer = C.max_outer_iters;
+    const int max_outer = ev ? 0 : C.max_outer_iters;
 
     double lo[K], hi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { lo[k] = 0.0; hi[k] = 0.0; }
     // initial corridor from the centre line: guard uses the veh_width ARGUMENT (main.cpp:706 / 930)
     constexpr int CAPF = fast_tile_cap(NP);
-    const bool fast_rays = (segO0 - segI0 <= CAPF) && (segE - segO0 <= CAPF) && (CAPF < 8192);
+    const bool fast_rays = !ev && (segO0 - segI0 <= CAPF) && (segE - segO0 <= CAPF) && (CAPF < 8192);
     const bool parity_ok = (C.veh_width_arg * 0.5 + C.safety_margin_m >= 0.0) && (C.veh_width_m * 0.5 + C.safety_margin_m >= 0.0);
     // per-sample existence certificates (see corridor_build_fast) live in the heading and curvature rows until the final geometry pass
     unsigned long long* gcert = reinterpret_cast<unsigned long long*>(B.heading + row0);
@@ -1939,7 +1942,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
         if (!same_track)
             fast_update = (sMisc[8] & 2) && (sMisc[9] & 2) && (segO0 - segI0 > 2 * kWin + 1) && (segE - segO0 > 2 * kWin + 1);
-    } else
+    } else if (!ev)
         corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                    C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
 
@@ -2121,7 +2124,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             for (int i = tid; i < N; i += T) { ncert[i] = gcert[i]; napex[i] = gapex[i]; }
         }
     }
-    prev_trk = trk;
+    prev_trk = ev ? -1 : trk;
     // =================== final geometry (main.cpp:761 / 1046) ===================
     block_sync<T>();
 #pragma unroll

@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from ._abi import (RL_OK, RL_STAGE_MINCURV, RL_STAGE_MINTIME, RlBatchDesc, RlBatchOut, RlJob, RlJobStats,
+from ._abi import (RL_OK, RL_STAGE_EVAL, RL_STAGE_MINCURV, RL_STAGE_MINTIME, RlBatchDesc, RlBatchOut, RlJob, RlJobStats,
                    RlParams)
 from ._lib import lib
 
@@ -254,7 +254,7 @@ class PackedBatch:
     def result(self, j) -> Result:
         a, b = int(self.job_off[j]), int(self.job_off[j + 1])
         st = self.out_stats[j]
-        mt = int(self.jobs_np[j, 2]) == RL_STAGE_MINTIME
+        mt = int(self.jobs_np[j, 2]) in (RL_STAGE_MINTIME, RL_STAGE_EVAL)
         return Result(self.out_xy[a:b], self.out_heading[a:b], self.out_curvature[a:b], self.out_alpha_total[a:b],
                       self.out_alpha_last[a:b], self.out_v[a:b] if mt else None, self.out_ax[a:b] if mt else None,
                       float(st.lap_time), st)
@@ -391,6 +391,89 @@ def solve_batch(tracks: Sequence[Track], configs: Sequence[Config], jobs, ctx: O
     pb = PackedBatch(tracks, [c.to_params(veh_width) for c in configs], jobs)
     ctx.solve_batch(pb)
     return [pb.result(j) for j in range(pb.n_jobs)]
+
+
+def path_length(P, closed=True) -> float:
+    """The `path_length` lambda of the reference's debug block (main.cpp:1445-1450)."""
+    P = _f64(P, 2)
+    if P.shape[0] <= 1:
+        return 0.0
+    d = np.hypot(P[1:, 0] - P[:-1, 0], P[1:, 1] - P[:-1, 1])
+    tot = 0.0
+    for v in d:                      # left-to-right sum like the reference
+        tot += float(v)
+    if closed and P.shape[0] >= 2:
+        tot += float(np.hypot(P[0, 0] - P[-1, 0], P[0, 1] - P[-1, 1]))
+    return tot
+
+
+DEBUG_COLUMNS = ("s", "cx", "cy", "mt_x", "mt_y", "mc_x", "mc_y", "d_mt_signed_m", "d_mc_signed_m", "d_mt_abs_m", "d_mc_abs_m",
+                 "kappa_mt", "v_mt", "ax_mt", "alat_mt", "alat_ratio", "gamma", "a_acc_cap", "a_brk_cap", "a_power_cap")
+
+
+def debug_compare_paths(center, mt: "Result", mc_raceline, L, s0=0.0, closed=True, cfg: Optional["Config"] = None,
+                        ctx: Optional["Context"] = None):
+    """The reference's debug comparison (pipeline::compute_mintime_and_save, main.cpp:1440-1593): the lap of the centre
+    line and of the min-curvature path under the same dynamics (two RL_STAGE_EVAL jobs on the GPU, main.cpp:1464-1477)
+    and the 20 columns of <base>_debug_compare_paths.csv (main.cpp:1493-1495) with their summary statistics.
+    `mc_raceline` is what the reference re-reads from <base>_raceline.csv (closing duplicate dropped), or None."""
+    cfg = cfg or Config()
+    center = _f64(center, 2)
+    N = min(mt.raceline.shape[0], center.shape[0])
+    tracks = [Track(center, np.zeros((0, 4)), np.zeros((0, 4)), L, closed)]
+    jobs = [(0, 0, RL_STAGE_EVAL)]
+    mc = None
+    if mc_raceline is not None and len(mc_raceline):
+        mc = _f64(mc_raceline, 2)
+        tracks.append(Track(mc, np.zeros((0, 4)), np.zeros((0, 4)), path_length(mc, closed), closed))   # L_mc, Hmc (1472-1473)
+        jobs.append((1, 0, RL_STAGE_EVAL))
+    ev = solve_batch(tracks, [cfg], jobs, ctx=ctx)
+    out = {"lap_center": ev[0].lap_time, "lap_mincurv": ev[1].lap_time if mc is not None else -1.0, "lap_mintime": mt.lap_time}
+    # centre-line normals (normals_from_points_generic, main.cpp:581-593)
+    if closed:
+        t = (np.roll(center, -1, axis=0) - np.roll(center, 1, axis=0)) * 0.5
+    else:
+        t = np.empty_like(center)
+        t[1:-1] = (center[2:] - center[:-2]) * 0.5
+        t[0], t[-1] = center[1] - center[0], center[-1] - center[-2]
+    tn = np.hypot(t[:, 0], t[:, 1])
+    t[tn < 1e-15] = (1.0, 0.0)
+    nv = np.stack([-t[:, 1], t[:, 0]], axis=1)
+    ln = np.sqrt(nv[:, 0] * nv[:, 0] + nv[:, 1] * nv[:, 1])
+    nc = np.where((ln < 1e-15)[:, None], 0.0, nv / np.maximum(ln, 1e-300)[:, None])
+    k = np.arange(N)
+    col = {"s": (s0 + L * (k / float(max(1, N)))) - s0, "cx": center[:N, 0], "cy": center[:N, 1],
+           "mt_x": mt.raceline[:N, 0], "mt_y": mt.raceline[:N, 1]}
+    mcx = np.full(N, np.nan)
+    mcy = np.full(N, np.nan)
+    if mc is not None:
+        m = min(N, mc.shape[0])
+        mcx[:m], mcy[:m] = mc[:m, 0], mc[:m, 1]
+    col["mc_x"], col["mc_y"] = mcx, mcy
+    col["d_mt_signed_m"] = (col["mt_x"] - col["cx"]) * nc[:N, 0] + (col["mt_y"] - col["cy"]) * nc[:N, 1]
+    col["d_mc_signed_m"] = (mcx - col["cx"]) * nc[:N, 0] + (mcy - col["cy"]) * nc[:N, 1]
+    col["d_mt_abs_m"], col["d_mc_abs_m"] = np.abs(col["d_mt_signed_m"]), np.abs(col["d_mc_signed_m"])
+    kap, v, ax = mt.curvature[:N], mt.v[:N], mt.ax[:N]
+    alat = v * v * np.abs(kap)
+    col.update({"kappa_mt": kap, "v_mt": v, "ax_mt": ax, "alat_mt": alat,
+                "alat_ratio": np.minimum(1.0, alat / cfg.a_total_max) if cfg.a_total_max > 1e-9 else np.zeros(N)})
+    vk = np.sqrt(cfg.a_lat_max / np.maximum(np.abs(kap), cfg.kappa_eps))
+    col["gamma"] = 1.0 + cfg.w_time_gain * np.clip((vk - v) / np.maximum(1e-6, vk), 0.0, 1.0)       # main.cpp:1525-1527
+    a_res = np.sqrt(np.maximum(0.0, cfg.a_total_max * cfg.a_total_max - alat * alat))               # ax_caps, main.cpp:1530-1539
+    Fd = 0.5 * cfg.rho_air * cfg.Cd * cfg.A_front_m2 * v * v
+    Fr = cfg.mass_kg * 9.81 * cfg.c_rr
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a_pow = np.where((cfg.P_max_W > 0) & (v > 1e-6), cfg.P_max_W / (cfg.mass_kg * v) - (Fd + Fr) / cfg.mass_kg, 1e9)
+    col["a_acc_cap"] = np.maximum(0.0, np.minimum(np.minimum(a_res, cfg.a_long_acc_cap), a_pow))
+    col["a_brk_cap"] = np.maximum(0.0, np.minimum(a_res, cfg.a_long_brake_cap) + (Fd + Fr) / cfg.mass_kg)
+    col["a_power_cap"] = np.maximum(0.0, a_pow)
+    out["columns"] = col
+    a = col["d_mt_abs_m"]
+    out["mt_offset_mean"], out["mt_offset_rms"] = float(a.sum() / max(1, N)), float(np.sqrt((a * a).sum() / max(1, N)))
+    out["mt_offset_max"], out["mt_offset_argmax"] = (float(a.max()), int(a.argmax())) if N else (0.0, 0)
+    if out["lap_mincurv"] > 0.0:
+        out["lap_gain_vs_mincurv_pct"] = (out["lap_mincurv"] - mt.lap_time) / out["lap_mincurv"] * 100.0   # main.cpp:1586-1588
+    return out
 
 
 @dataclass

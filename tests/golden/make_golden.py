@@ -190,6 +190,24 @@ def geom_golden(name, samples=0, open_track=False):
     return d
 
 
+def debug_golden(name):
+    """The reference's debug comparison (`ref_harness debug`): the CSV it writes + the two extra laps; pins the EVAL stage
+    of the C restatement (heading/curvature + v(s) profile of a given path) bit for bit."""
+    with tempfile.TemporaryDirectory() as td:
+        o = os.path.join(td, "d.bin")
+        res = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_harness"), "debug", f"{REF}/csv/{name}_inner.csv",
+                              f"{REF}/csv/{name}_outer.csv", o], check=True, capture_output=True, text=True)
+        print(f"  debug: {res.stdout.strip()}")
+        d = batchfile.read_rdg1(o)
+    from practice_path_planning_for_formula_student_driverless_b200 import RL_STAGE_EVAL
+    e = np.zeros((0, 4))
+    lap_c = oracle.solve(RL_STAGE_EVAL, d["center_xy"], e, e, d["L"], True)["lap_time"]
+    lap_m = oracle.solve(RL_STAGE_EVAL, d["mc_xy"], e, e, d["L_mc"], True)["lap_time"]
+    if lap_c != d["lap_center"] or lap_m != d["lap_mincurv"]:
+        raise SystemExit(f"[debug {name}] EVAL stage of the port differs: {lap_c} vs {d['lap_center']}, {lap_m} vs {d['lap_mincurv']}")
+    return d
+
+
 def main():
     if not os.path.exists(f"{REF}/src/main.cpp"):
         raise SystemExit("the reference is not mounted; goldens can only be regenerated in the build container")
@@ -219,6 +237,9 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"geom_{name}" + (f"_n{smp}" if smp else "") + ".npz"), **d)
     d = geom_golden("competition_map3", 0, open_track=True)      # cfg is_closed_track = false: no padding, polyline edges
     np.savez_compressed(os.path.join(OUT, "geom_open_competition_map3.npz"), **d)
+    print("debug comparison of the min-time stage wrapper (SURVEY 8f row 3)")
+    for name in ("training_map", "competition_map3"):
+        np.savez_compressed(os.path.join(OUT, f"debug_{name}.npz"), **debug_golden(name))
     print("oracle port == reference, bit for bit, on every golden case")
 
 

@@ -302,7 +302,7 @@ def bench_ours(args):
         dist.destroy_process_group()
     dev.close(); ctx.close(); pool.close()
     if out is not None:
-        print(json.dumps(out), flush=True)
+        args.emit(out)
 
 
 def bench_reference(args):
@@ -331,7 +331,29 @@ def bench_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    args.emit(out)
+
+
+class StdoutOnlyJson:
+    """Libraries (NCCL prints its version banner on stdout) must not put anything next to the ONE JSON line the
+    driver parses: file descriptor 1 points at stderr until the result is printed."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
 
 
 def main():
@@ -360,10 +382,12 @@ def main():
         if not args.cpu_baseline_long:
             args.no_cpu_baseline = True      # ~3 core-minutes per solve on the CPU: opt in with --cpu-baseline-long
         args.cpu_tracks_per_core = 1
-    if args.impl == "reference":
-        bench_reference(args)
-    else:
-        bench_ours(args)
+    with StdoutOnlyJson() as out:
+        args.emit = out.emit
+        if args.impl == "reference":
+            bench_reference(args)
+        else:
+            bench_ours(args)
 
 
 if __name__ == "__main__":

@@ -759,6 +759,8 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
         block_sync<T>();
         exchange_path_halo(sP, sHalo, cl, tid);
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
+        // (the reference also rebuilds it after the LAST path update, but nothing reads that corridor: skipped)
+        if (outer + 1 == max_outer) continue;
         corridor_stream_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, B.seg, segI0, segO0, segE,
                              C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
     }

@@ -2094,6 +2094,8 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         for (int k = 0; k < K; ++k) if (k < cnt) sP[start + k] = Pn[k];
         block_sync<T>();
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
+        // (the reference also rebuilds it after the LAST path update, but nothing reads that corridor: skipped)
+        if (outer + 1 == max_outer) continue;
         if (fast_rays) {
             const double guard = C.veh_width_m * 0.5 + C.safety_margin_m;
             double loc[K], hic[K];

@@ -394,101 +394,426 @@ __device__ __forceinline__ double lap_and_ax_c(const Part& pt, const Clu& cl, co
     return t;
 }
 
-// ---- corridor of one chunk, rings streamed through region B in tiles (main.cpp:694-711, 749-756) ----------------
-// Per ring: exact nearest +n / -n hits over all tiles (ray_scan, pruned by this ring's own best hit so far); a ring
-// some ray misses entirely falls back to the exact point-ring distance (dist_scan over all tiles), main.cpp:696.
-// Consecutive mapping (sample il = tid + j*T) inside the search, results handed to the blocked layout through region B.
-template <int K>
-__device__ __forceinline__ void corridor_stream_c(const Part& pt, const PathView& pv, double* sB, uint64_t* mbar, uint32_t& bar_phase,
-                                                  int* sMisc, const double* __restrict__ gseg, long long segI0, long long segO0,
-                                                  long long segE, double guard, double (&lo)[K], double (&hi)[K], long long& ray_tests)
+// ---- corridor of one chunk ------------------------------------------------------------------------------------
+// Two paths, as in solve_kernel (corridor_build_fast / corridor_update), adapted to rings that do not fit shared
+// memory:
+//   corridor_search_c   the SEARCHING path: each ring streamed through region B in tiles (TMA bulk copies, FP32 box
+//                       hierarchy per tile); exact nearest +n / -n hits and the exact point-ring distance over ALL
+//                       tiles (main.cpp:478-512, 694-711), and what later builds live on: the anchor segment of the
+//                       nearest hit, the clearance of everything outside its window, and an existence certificate
+//                       (FAR segment / ring-free CONE) for the ray the point-ring fallback (main.cpp:696) depends on.
+//                       First build: all samples.  Later: only the samples the update path flagged.
+//   corridor_update_c   the UPDATE path: the anchors of a chunk's samples span a short range of each ring, so only
+//                       that range of vertices (FP64 + FP32, 24 B each) is loaded; windows + certificates settle the
+//                       sample exactly like corridor_update_sample does for a whole ring (same code, LOCAL form).
+// Both run per CTA on its own samples with no cluster traffic.
+
+// ray_scan with the nearest hit's SEGMENT per direction (tile-local; untouched when this tile does not improve it).
+// Both rays; pruned by this ring's own best hits so far (pos / neg), so INF afterwards means: no hit on this ring at all.
+__device__ __noinline__ void ray_scan_seg(const RayTile& tl_in, double2 P, double nx, double ny, float px, float py, float m,
+                                          double& pos_io, double& neg_io, int& segp_io, int& segn_io, long long& tests_io)
 {
+    const RayTile tl = tile_in_smem(tl_in);
+    const double INF = dinf();
+    const float FINF = __int_as_float(0x7f800000);
+    const float fnx = (float)nx, fny = (float)ny, anx = fabsf(fnx), any = fabsf(fny);
+    double bp = pos_io, bn = neg_io;
+    int sp = -1, sn = -1, tests = 0;
+    float bpf = (bp < INF) ? __double2float_ru(bp) : FINF, bnf = (bn < INF) ? __double2float_ru(bn) : FINF;
+    for (int sb = 0; sb < tl.nsup; ++sb) {
+        if (!ray_box(tl.supF[sb], px, py, fnx, fny, anx, any, m, bpf, bnf, true, true)) continue;
+        const int b1 = min(tl.nblk, sb * SU + SU);
+        for (int b = sb * SU; b < b1; ++b) {
+            if (!ray_box(tl.boxF[b], px, py, fnx, fny, anx, any, m, bpf, bnf, true, true)) continue;
+            const int s1 = min(tl.nt, b * SB + SB);
+            for (int s = b * SB; s < s1; ++s) {
+                const float4 f = tl.segF[s];
+                const float sa = fnx * (f.y - py) - fny * (f.x - px), sbb = fnx * (f.w - py) - fny * (f.z - px);
+                if (fminf(sa, sbb) > m || fmaxf(sa, sbb) < -m) continue;
+                const double x0 = tl.segD[4 * s], y0 = tl.segD[4 * s + 1], vx = tl.segD[4 * s + 2], vy = tl.segD[4 * s + 3];
+                const double den = nx * (-vy) + ny * vx;                         // main.cpp:483
+                ++tests;
+                if (fabs(den) < 1e-15) continue;                                 // main.cpp:484
+                const double ax = x0 - P.x, ay = y0 - P.y;                      // main.cpp:485
+                const double inv = 1.0 / den;
+                const double t = (ax * (-vy) + ay * vx) * inv;                  // main.cpp:486
+                const double u = (nx * ay - ny * ax) * inv;                     // main.cpp:487
+                if (u >= -1e-12 && u <= 1.0 + 1e-12) {                          // main.cpp:488
+                    if (t > 0.0) { if (t < bp) { bp = t; bpf = __double2float_ru(t); sp = s; } }         // +n ray, main.cpp:497
+                    else if (t < 0.0) { if (-t < bn) { bn = -t; bnf = __double2float_ru(-t); sn = s; } }  // -n ray: t' = -t
+                }
+            }
+        }
+    }
+    pos_io = bp; neg_io = bn; tests_io += tests;
+    if (sp >= 0) segp_io = sp;
+    if (sn >= 0) segn_io = sn;
+}
+
+// crossings (mod 2) of the +x ray from P with the segments of one TILE of a vertex chain; the end vertex of the
+// tile's last segment is the start of the ring's next segment (next_start), shared bit for bit like every other vertex
+__device__ __noinline__ bool inside_ring_tile(const RayTile& tl_in, double2 P, float px, float py, float m, double2 next_start)
+{
+    const RayTile tl = tile_in_smem(tl_in);
+    int cnt = 0;
+    for (int sb = 0; sb < tl.nsup; ++sb) {
+        const float4 sx = tl.supF[sb];
+        if (fabsf(sx.y - py) > sx.w + m || px > sx.x + sx.z + m) continue;
+        const int b1 = min(tl.nblk, sb * SU + SU);
+        for (int b = sb * SU; b < b1; ++b) {
+            const float4 bx = tl.boxF[b];
+            if (fabsf(bx.y - py) > bx.w + m || px > bx.x + bx.z + m) continue;
+            const int s1 = min(tl.nt, b * SB + SB);
+            for (int s = b * SB; s < s1; ++s) {
+                const double ax = tl.segD[4 * s], ay = tl.segD[4 * s + 1];
+                const double bxx = (s + 1 == tl.nt) ? next_start.x : tl.segD[4 * (s + 1)];
+                const double byy = (s + 1 == tl.nt) ? next_start.y : tl.segD[4 * (s + 1) + 1];
+                if ((ay > P.y) != (byy > P.y)) {
+                    const double xc = ax + (P.y - ay) * (bxx - ax) / (byy - ay);
+                    if (xc > P.x) ++cnt;
+                }
+            }
+        }
+    }
+    return (cnt & 1) != 0;
+}
+
+struct AccC {   // one sample's accumulators while the rings stream by (local memory: the sample loops are not unrolled)
+    double nx, ny, pos[2], neg[2], dist[2];
+    int sp[2], sn[2];
+    float clr[2], px, py;
+    unsigned par;     // bit r: odd number of crossings with ring r so far (first build only)
+};
+
+template <int K>
+__device__ __forceinline__ void corridor_search_c(const Part& pt, const PathView& pv, double* sB, uint64_t* mbar, uint32_t& bar_phase,
+                                                  int* sMisc, unsigned* sHint, unsigned short* sClr,
+                                                  const double* __restrict__ gseg, const double* __restrict__ gcenter,
+                                                  unsigned long long* __restrict__ gcert, unsigned long long* __restrict__ gapex,
+                                                  long long segI0, long long segO0, long long segE, double guard, unsigned mask,
+                                                  bool first, bool parity_ok,
+                                                  double (&loc)[K], double (&hic)[K], long long& ray_tests, int& ex_scans)
+{
+    // first: the build from the centre line (every sample): also settles, once per job, whether each ring is a closed
+    // vertex chain and which samples lie inside it (crossing parity) -- a ray from inside a closed ring always hits it
     constexpr int T = kcT, NP = kcT * K;
     constexpr int CAP = fast_tile_cap(NP);
     const int Nl = pv.Nloc, tid = pt.tid;
     const double INF = dinf();
     const double2 org = pv.sP[0];
-    double dpos[K], dneg[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) { dpos[j] = INF; dneg[j] = INF; }
+    AccC acc[K];
+#pragma unroll 1
+    for (int j = 0; j < K; ++j) {
+        const int i = tid + j * T;
+        if (i >= Nl || !((mask >> j) & 1u)) continue;
+        AccC& a = acc[j];
+        normal_c(pv, i, a.nx, a.ny);
+        const double2 Pc = pv.sP[i];
+        a.px = (float)(Pc.x - org.x); a.py = (float)(Pc.y - org.y);
+        for (int r = 0; r < 2; ++r) { a.pos[r] = INF; a.neg[r] = INF; a.dist[r] = INF; a.sp[r] = -1; a.sn[r] = -1; a.clr[r] = 3e18f; }
+        a.par = 0u;
+    }
+    int chain_ok[2] = {1, 1};
+    float mring[2] = {0.f, 0.f};
     for (int ring = 0; ring < 2; ++ring) {
         const long long base = ring ? segO0 : segI0;
         const int mr = (int)(ring ? (segE - segO0) : (segO0 - segI0));
-        if (mr == 0) {   // safe_ray on an empty ring returns 0 (main.cpp:696-697)
-#pragma unroll
-            for (int j = 0; j < K; ++j) { dpos[j] = fmin(dpos[j], 0.0); dneg[j] = fmin(dneg[j], 0.0); }
-            continue;
-        }
-        double pos[K], neg[K], dmin[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) { pos[j] = INF; neg[j] = INF; dmin[j] = INF; }
+        if (mr == 0) continue;   // safe_ray on an empty ring returns 0 (main.cpp:696-697): handled in the combine step
         const int ntiles = (mr + CAP - 1) / CAP;
         RayTile tl;
         float m0 = 0.f;
         for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1) {
-                bool need = false;
-#pragma unroll
-                for (int j = 0; j < K; ++j) need = need || ((tid + j * T < Nl) && (pos[j] == INF || neg[j] == INF));
-                if (!block_or<T>(need)) break;
-            }
             for (int tile = 0; tile < ntiles; ++tile) {
                 const int t0 = tile * CAP, nt = min(CAP, mr - t0);
                 if (pass == 0 || ntiles > 1) {
-                    bool chain;
-                    m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * (base + t0), nt, org.x, org.y, tl, chain);
+                    bool chain, linked;
+                    m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * (base + t0), nt, org.x, org.y, tl, chain, &linked);
+                    mring[ring] = fmaxf(mring[ring], m0);
+                    if (first && pass == 0 && !linked) chain_ok[ring] = 0;
                 }
-#pragma unroll
+                double2 next_start = make_double2(0.0, 0.0);
+                if (first && pass == 0) {
+                    // the vertex after this tile (the ring's first vertex after the last tile) must equal the tile's last end point
+                    const int nxt = (t0 + nt == mr) ? 0 : t0 + nt;
+                    next_start = *reinterpret_cast<const double2*>(gseg + 4 * (base + nxt));
+                    const double2 last_end = *reinterpret_cast<const double2*>(gseg + 4 * (base + t0 + nt - 1) + 2);
+                    if (!(next_start.x == last_end.x && next_start.y == last_end.y)) chain_ok[ring] = 0;
+                }
+#pragma unroll 1
                 for (int j = 0; j < K; ++j) {
-                    const int il = tid + j * T;
-                    if (il >= Nl) continue;
-                    const double2 Pc = pv.sP[il];
-                    const float px = (float)(Pc.x - org.x), py = (float)(Pc.y - org.y);
-                    const float m = m0 + 2e-6f * fmaxf(fabsf(px), fabsf(py));
+                    const int i = tid + j * T;
+                    if (i >= Nl || !((mask >> j) & 1u)) continue;
+                    AccC& a = acc[j];
+                    const double2 Pc = pv.sP[i];
+                    const float m = m0 + 2e-6f * fmaxf(fabsf(a.px), fabsf(a.py));
                     if (pass == 0) {
-                        double nx, ny;
-                        normal_c(pv, il, nx, ny);
-                        double bp = pos[j], bn = neg[j];
-                        ray_scan(tl, Pc, nx, ny, px, py, (float)nx, (float)ny, m, 0, true, true, false, bp, bn, pos[j], neg[j], ray_tests);
-                    } else if (pos[j] == INF || neg[j] == INF) {
-                        const double d = dist_scan(tl, Pc, px, py, m, 0, fmin(dmin[j], fmin(pos[j], neg[j])));
-                        dmin[j] = fmin(dmin[j], d);
+                        // exact nearest hits of both rays on this ring, and their segments (ring-global)
+                        int sp = -1, sn = -1;
+                        ray_scan_seg(tl, Pc, a.nx, a.ny, a.px, a.py, m, a.pos[ring], a.neg[ring], sp, sn, ray_tests);
+                        if (sp >= 0) a.sp[ring] = t0 + sp;
+                        if (sn >= 0) a.sn[ring] = t0 + sn;
+                        if (first && inside_ring_tile(tl, Pc, a.px, a.py, m, next_start)) a.par ^= (1u << ring);
+                    } else {
+                        // everything outside the anchor's window is at least `clr` away; exact point-ring distance
+                        const int anchor = (a.pos[ring] <= a.neg[ring]) ? a.sp[ring] : a.sn[ring];
+                        if (anchor >= 0 && mr <= 8191) a.clr[ring] = fminf(a.clr[ring], clearance_scan(tl, a.px, a.py, m, anchor, t0, mr));
+                        const double d = dist_scan(tl, Pc, a.px, a.py, m, 0, fmin(a.dist[ring], fmin(a.pos[ring], a.neg[ring])));
+                        a.dist[ring] = fmin(a.dist[ring], d);
                     }
                 }
             }
         }
-        // safe_ray + min over the two rings (main.cpp:696-705)
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const double dist = (dmin[j] < INF) ? dmin[j] : 0.0;
-            const double vp = (pos[j] < INF) ? pos[j] : dist;
-            const double vn = (neg[j] < INF) ? neg[j] : dist;
-            dpos[j] = fmin(dpos[j], fmax(0.0, vp));
-            dneg[j] = fmin(dneg[j], fmax(0.0, vn));
+    }
+    if (tid == 0) {   // the FP32 margin later updates must allow for: the largest any tile was built with
+        if (__int_as_float(sMisc[10]) < mring[0]) sMisc[10] = __float_as_int(mring[0]);
+        if (__int_as_float(sMisc[11]) < mring[1]) sMisc[11] = __float_as_int(mring[1]);
+        if (first) { sMisc[8] = chain_ok[0]; sMisc[9] = chain_ok[1]; }     // bit 0: closed vertex chain (every thread computed the same)
+    }
+    const int rfl[2] = {first ? chain_ok[0] : (sMisc[8] & 1), first ? chain_ok[1] : (sMisc[9] & 1)};
+    // ---- combine (main.cpp:696-710), leave the per-sample state, decide which existence certificate a sample needs ----
+    const int M0 = (int)(segO0 - segI0), M1 = (int)(segE - segO0);
+    unsigned need_cone = 0u;   // bit j: sample j needs a CONE certificate; coneKey[j] = ring | dir << 1
+    unsigned coneKey = 0u;     // 2 bits per sample
+#pragma unroll 1
+    for (int j = 0; j < K; ++j) {
+        const int i = tid + j * T;
+        if (i >= Nl || !((mask >> j) & 1u)) continue;
+        AccC& a = acc[j];
+        double dpos = INF, dneg = INF;
+        for (int r = 0; r < 2; ++r) {
+            const int mr = r ? M1 : M0;
+            double vp, vn;
+            if (mr == 0) { vp = 0.0; vn = 0.0; }
+            else {
+                const double dist = (a.dist[r] < INF) ? a.dist[r] : 0.0;
+                vp = (a.pos[r] < INF) ? a.pos[r] : dist;
+                vn = (a.neg[r] < INF) ? a.neg[r] : dist;
+            }
+            dpos = fmin(dpos, fmax(0.0, vp));
+            dneg = fmin(dneg, fmax(0.0, vn));
+        }
+        double hv = fmax(0.0, dpos - guard), lv = -fmax(0.0, dneg - guard);
+        if (!isfinite(hv)) hv = 0.0;
+        if (!isfinite(lv)) lv = 0.0;
+        hic[j] = hv; loc[j] = lv;
+        // state: anchors, clearances (relative to the centre-line sample, 1/4 m units, rounded down)
+        const double2 Pc = pv.sP[i];
+        const double cx0 = gcenter[2 * i], cy0 = gcenter[2 * i + 1];
+        const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
+        // parity bits: taken now (first build) or kept
+        unsigned hw = first ? (((a.par & 1u) && rfl[0] ? 1u : 0u) << 26) | (((a.par & 2u) && rfl[1] ? 1u : 0u) << 27) : (sHint[i] & (3u << 26));
+        unsigned cw = 0u;
+        float rcv[2] = {0.f, 0.f};
+        for (int r = 0; r < 2; ++r) {
+            const int mr = r ? M1 : M0;
+            const int anchor = (a.pos[r] <= a.neg[r]) ? a.sp[r] : a.sn[r];
+            if (anchor >= 0 && mr > 2 * kWin + 1 && mr <= 8191) {
+                const float cval = a.clr[r] - disp;
+                const unsigned cq = (cval >= 63.75f) ? 255u : (cval > 0.f ? (unsigned)(cval * 4.f) : 0u);
+                hw |= ((unsigned)anchor << (13 * r)) | (1u << (28 + r));
+                cw |= cq << (8 * r);
+                rcv[r] = 0.25f * (float)cq - disp - 4.f * (mring[r] * 1.001f + 2e-6f * fmaxf(fabsf(a.px), fabsf(a.py)) + 1e-5f);
+            }
+        }
+        sHint[i] = hw; sClr[i] = (unsigned short)cw;
+        // the certificate the update path will ask for: a ring without a certified near hit in some direction whose
+        // point distance undercuts the other ring's hit there (see corridor_update_sample)
+        for (int dir = 0; dir < 2; ++dir) {
+            for (int r = 0; r < 2; ++r) {
+                const double hit = dir ? a.neg[r] : a.pos[r];
+                if (hit <= (double)rcv[r]) continue;                       // a near hit: no question to answer
+                if (parity_ok && rfl[r] && ((hw >> (26 + r)) & 1u)) continue;  // inside a closed ring: every ray hits it
+                // (asked for only while the point distance undercuts the other ring's hit, but that flips as the path
+                //  moves and a search costs a pass over every tile: the certificate is made now, whichever way it stands)
+                const unsigned key = ((unsigned)r << 2) | ((unsigned)dir << 3);
+                if (hit < INF) {   // it hits far away: remember where
+                    gcert[i] = ((unsigned long long)(unsigned)(dir ? a.sn[r] : a.sp[r]) << 32) | (unsigned long long)(key | kCertFar);
+                } else { need_cone |= (1u << j); coneKey = (coneKey & ~(3u << (2 * j))) | (((unsigned)r | ((unsigned)dir << 1)) << (2 * j)); }
+            }
         }
     }
-    // hi/lo (main.cpp:707-710), handed to the blocked layout through region B
+    // ---- ring-free cones for the rays that miss (cone_scan over every tile of that ring) ----
+    if (block_or<T>(need_cone != 0u)) {
+        for (int ring = 0; ring < 2; ++ring) {
+            bool mine = false;
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) mine = mine || (((need_cone >> j) & 1u) && (int)((coneKey >> (2 * j)) & 1u) == ring);
+            if (!block_or<T>(mine)) continue;
+            const long long base = ring ? segO0 : segI0;
+            const int mr = ring ? M1 : M0;
+            const int ntiles = (mr + CAP - 1) / CAP;
+            float cb[K];
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) cb[j] = -1.f;
+            for (int tile = 0; tile < ntiles; ++tile) {
+                const int t0 = tile * CAP, nt = min(CAP, mr - t0);
+                RayTile tl;
+                bool chain;
+                const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * (base + t0), nt, org.x, org.y, tl, chain);
+#pragma unroll 1
+                for (int j = 0; j < K; ++j) {
+                    const int i = tid + j * T;
+                    if (!((need_cone >> j) & 1u) || (int)((coneKey >> (2 * j)) & 1u) != ring) continue;
+                    const AccC& a = acc[j];
+                    const int dir = (int)((coneKey >> (2 * j + 1)) & 1u);
+                    const double sg = dir ? -1.0 : 1.0;
+                    const int qx = __double2int_rn(sg * a.nx * 32767.0), qy = __double2int_rn(sg * a.ny * 32767.0);
+                    double d0x, d0y;
+                    cert_axis(((unsigned)qx & 0xffffu) | ((unsigned)qy << 16), d0x, d0y);
+                    const double toward = dir ? a.pos[ring] : a.neg[ring];     // this ring's hit on the opposite ray
+                    const double back = (toward < INF) ? fmax(0.0, toward - fmax(0.05, 0.5 * guard)) : 0.0;
+                    const double2 Pc = pv.sP[i];
+                    const double cx0 = gcenter[2 * i], cy0 = gcenter[2 * i + 1];
+                    const float oxf = (float)((Pc.x - cx0) - back * d0x), oyf = (float)((Pc.y - cy0) - back * d0y);
+                    const double axd = cx0 + (double)oxf, ayd = cy0 + (double)oyf;
+                    const float m = m0 + 2e-6f * fmaxf(fabsf(a.px), fabsf(a.py));
+                    cb[j] = fmaxf(cb[j], cone_scan(tl, (float)(axd - org.x), (float)(ayd - org.y), (float)d0x, (float)d0y, m, 0));
+                }
+            }
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) {
+                const int i = tid + j * T;
+                if (!((need_cone >> j) & 1u) || (int)((coneKey >> (2 * j)) & 1u) != ring) continue;
+                const AccC& a = acc[j];
+                const int dir = (int)((coneKey >> (2 * j + 1)) & 1u);
+                const double sg = dir ? -1.0 : 1.0;
+                const unsigned key = ((unsigned)ring << 2) | ((unsigned)dir << 3);
+                const int qx = __double2int_rn(sg * a.nx * 32767.0), qy = __double2int_rn(sg * a.ny * 32767.0);
+                const unsigned nw1 = ((unsigned)qx & 0xffffu) | ((unsigned)qy << 16);
+                double d0x, d0y;
+                cert_axis(nw1, d0x, d0y);
+                const double toward = dir ? a.pos[ring] : a.neg[ring];
+                const double back = (toward < INF) ? fmax(0.0, toward - fmax(0.05, 0.5 * guard)) : 0.0;
+                const double2 Pc = pv.sP[i];
+                const double cx0 = gcenter[2 * i], cy0 = gcenter[2 * i + 1];
+                const float oxf = (float)((Pc.x - cx0) - back * d0x), oyf = (float)((Pc.y - cy0) - back * d0y);
+                unsigned nw0 = key | kCertNoCone;
+                if (cb[j] < 0.9995f) {
+                    const unsigned qc = (unsigned)ceilf((cb[j] + 1.f) * 32767.f + 0.5f);
+                    if (qc < 65535u) nw0 = key | kCertCone | (qc << 16);
+                }
+                gcert[i] = ((unsigned long long)nw1 << 32) | (unsigned long long)nw0;
+                gapex[i] = ((unsigned long long)__float_as_uint(oyf) << 32) | (unsigned long long)__float_as_uint(oxf);
+                ++ex_scans;
+            }
+        }
+    }
+}
+
+// the UPDATE path of one chunk: returns the mask of samples the searching path has to rebuild
+template <int K>
+__device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const PathView& pv, double* sB, int* sMisc,
+                                                      const unsigned* sHint, const unsigned short* sClr, const double2* sHalo,
+                                                      const double* __restrict__ gseg, const double* __restrict__ gcenter,
+                                                      const unsigned long long* __restrict__ gcert, const unsigned long long* __restrict__ gapex,
+                                                      long long segI0, long long segO0, long long segE, double guard, bool parity_ok,
+                                                      double (&loc)[K], double (&hic)[K], long long& ray_tests)
+{
+    constexpr int T = kcT, NP = kcT * K;
+    const int Nl = pv.Nloc, tid = pt.tid;
+    const int M[2] = {(int)(segO0 - segI0), (int)(segE - segO0)};
+#pragma unroll
+    for (int j = 0; j < K; ++j) { loc[j] = 0.0; hic[j] = 0.0; }
+    if (M[0] <= 2 * kWin + 1 || M[1] <= 2 * kWin + 1 || M[0] > 8191 || M[1] > 8191) return 0xffffffffu;
+    // ---- the range of each ring this chunk's windows touch: anchors relative to sample 0's anchor, on the circle ----
+    const unsigned h0 = sHint[0];
+    if (!((h0 >> 28) & 1u) || !((h0 >> 29) & 1u)) return 0xffffffffu;       // (uniform: every thread reads the same word)
     block_sync<T>();
-    double* sLoS = sB;
-    double* sHiS = sB + NP;
+    if (tid == 0) { sMisc[12] = 0; sMisc[13] = 0; sMisc[14] = 0; sMisc[15] = 0; }
+    block_sync<T>();
+    int jref[2], lmin[2] = {0, 0}, lmax[2] = {0, 0};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) jref[r] = (int)((h0 >> (13 * r)) & 0x1fffu);
+#pragma unroll 1
+    for (int j = 0; j < K; ++j) {
+        const int i = tid + j * T;
+        if (i >= Nl) continue;
+        const unsigned hw = sHint[i];
+        for (int r = 0; r < 2; ++r) {
+            if (!((hw >> (28 + r)) & 1u)) continue;                          // no anchor: that sample is flagged anyway
+            int rel = (int)((hw >> (13 * r)) & 0x1fffu) - jref[r];
+            if (rel > M[r] / 2) rel -= M[r];
+            else if (rel < -(M[r] / 2)) rel += M[r];
+            lmin[r] = min(lmin[r], rel); lmax[r] = max(lmax[r], rel);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lmin[r] = min(lmin[r], __shfl_xor_sync(kFull, lmin[r], o)); lmax[r] = max(lmax[r], __shfl_xor_sync(kFull, lmax[r], o)); }
+        if (pt.lane == 0) { atomicMin(&sMisc[12 + 2 * r], lmin[r]); atomicMax(&sMisc[13 + 2 * r], lmax[r]); }
+    }
+    block_sync<T>();
+    int basev[2], nseg[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int rmin = sMisc[12 + 2 * r], rmax = sMisc[13 + 2 * r];
+        nseg[r] = rmax - rmin + 2 * kWin + 1;
+        basev[r] = jref[r] + rmin - kWin;
+        if (nseg[r] >= M[r]) { nseg[r] = M[r]; basev[r] = 0; }
+        basev[r] %= M[r];
+        if (basev[r] < 0) basev[r] += M[r];
+    }
+    if ((size_t)(nseg[0] + nseg[1] + 2) * 24 > (size_t)NP * 32) return 0xffffffffu;     // does not fit region B
+    // ---- load the vertex ranges (and verify that consecutive segments really share their vertex) ----
+    double2* V0 = reinterpret_cast<double2*>(sB);
+    double2* V1 = V0 + (nseg[0] + 1);
+    float2* F0 = reinterpret_cast<float2*>(V1 + (nseg[1] + 1));
+    float2* F1 = F0 + (nseg[0] + 1);
+    const double2 org = pv.sP[0];
+    int linked = 1;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const double* gs = gseg + 4 * (r ? segO0 : segI0);
+        double2* V = r ? V1 : V0;
+        float2* F = r ? F1 : F0;
+        for (int q = tid; q <= nseg[r]; q += T) {
+            int sgl = basev[r] + ((q < nseg[r]) ? q : nseg[r] - 1);
+            if (sgl >= M[r]) sgl -= M[r];
+            const double4 sv = *reinterpret_cast<const double4*>(gs + 4 * (size_t)sgl);
+            double2 v;
+            if (q < nseg[r]) {
+                v = make_double2(sv.x, sv.y);
+                if (q + 1 < nseg[r]) {
+                    int sn = sgl + 1; if (sn >= M[r]) sn -= M[r];
+                    const double2 nx2 = *reinterpret_cast<const double2*>(gs + 4 * (size_t)sn);
+                    linked &= (nx2.x == sv.z && nx2.y == sv.w);
+                }
+            } else v = make_double2(sv.z, sv.w);
+            V[q] = v; F[q] = make_float2((float)(v.x - org.x), (float)(v.y - org.y));
+        }
+    }
+    if (!__syncthreads_and(linked)) return 0xffffffffu;
+    UpdCtx c;
+    {
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(pv.sP);    // start of the dynamic shared memory
+        c.oV0 = (int)(reinterpret_cast<const unsigned char*>(V0) - base); c.oV1 = (int)(reinterpret_cast<const unsigned char*>(V1) - base);
+        c.oF0 = (int)(reinterpret_cast<const unsigned char*>(F0) - base); c.oF1 = (int)(reinterpret_cast<const unsigned char*>(F1) - base);
+        c.oHint = (int)(reinterpret_cast<const unsigned char*>(sHint) - base); c.oClr = (int)(reinterpret_cast<const unsigned char*>(sClr) - base);
+        c.oHalo = (int)(reinterpret_cast<const unsigned char*>(sHalo) - base);
+    }
+    c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
+    c.ox = org.x; c.oy = org.y; c.guard = guard; c.N = Nl; c.M0 = M[0]; c.M1 = M[1]; c.rf0 = sMisc[8] & 1; c.rf1 = sMisc[9] & 1;
+    c.mr0 = __int_as_float(sMisc[10]); c.mr1 = __int_as_float(sMisc[11]);
+    c.parity_ok = parity_ok; c.closed = true;
+    c.base0 = basev[0]; c.base1 = basev[1]; c.len0 = nseg[0]; c.len1 = nseg[1];
+    c.gs0 = gseg + 4 * segI0; c.gs1 = gseg + 4 * segO0;
+    unsigned flagged = 0u;
+    double2 cn = make_double2(0.0, 0.0);
+    unsigned long long wn = 0ull, an = 0ull;
+    if (tid < Nl) { cn = *reinterpret_cast<const double2*>(gcenter + 2 * tid); wn = gcert[tid]; an = gapex[tid]; }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        const int il = tid + j * T;
-        if (il < Nl) {
-            double hv = fmax(0.0, dpos[j] - guard);
-            double lv = -fmax(0.0, dneg[j] - guard);
-            if (!isfinite(hv)) hv = 0.0;
-            if (!isfinite(lv)) lv = 0.0;
-            sHiS[il] = hv; sLoS[il] = lv;
-        }
+        const int i = tid + j * T;
+        const double2 cc = cn;
+        const unsigned long long wc = wn, ac = an;
+        if (j + 1 < K && i + T < Nl) { cn = *reinterpret_cast<const double2*>(gcenter + 2 * (i + T)); wn = gcert[i + T]; an = gapex[i + T]; }
+        if (i >= Nl) continue;
+        double hv = 0.0, lv = 0.0;
+        if (corridor_update_sample<true>(c, i, cc.x, cc.y, wc, ac, hv, lv, ray_tests)) flagged |= (1u << j);
+        else { hic[j] = hv; loc[j] = lv; }
     }
-    block_sync<T>();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        lo[k] = 0.0; hi[k] = 0.0;
-        if (k < pt.cnt) { lo[k] = sLoS[pt.start + k]; hi[k] = sHiS[pt.start + k]; }
-    }
-    block_sync<T>();
+    return flagged;
 }
 
 // ---- the cluster solver kernel -----------------------------------------------------------------------------
@@ -510,6 +835,8 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
     double* sExF = reinterpret_cast<double*>(scr + kcExF);
     double* sExL = reinterpret_cast<double*>(scr + kcExL);
     int* sMisc = reinterpret_cast<int*>(scr + kcMisc);
+    unsigned* sHint = reinterpret_cast<unsigned*>(scr + kcBytes);                                   // anchors + valid bits, per sample
+    unsigned short* sClr = reinterpret_cast<unsigned short*>(scr + kcBytes + (size_t)NP * 4);       // clearances, per sample
 
     Clu cl;
     cl.CS = cl_size(); cl.rank = cl_rank();
@@ -602,9 +929,23 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
 #pragma unroll
     for (int k = 0; k < K; ++k) { lo[k] = 0.0; hi[k] = 0.0; }
     // initial corridor from the centre line: guard uses the veh_width ARGUMENT (main.cpp:706 / 930)
-    if (!ev)
-        corridor_stream_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, B.seg, segI0, segO0, segE,
-                             C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+    const double* gcenter = B.center_xy + 2 * (s0 + cl.n0);
+    unsigned long long* gcert = reinterpret_cast<unsigned long long*>(B.heading + row0);      // certificates: scratch in the chunk's
+    unsigned long long* gapex = reinterpret_cast<unsigned long long*>(B.curvature + row0);    // heading / curvature rows until the end
+    int ex_scans = 0;
+    const bool parity_ok = (C.veh_width_arg * 0.5 + C.safety_margin_m >= 0.0) && (C.veh_width_m * 0.5 + C.safety_margin_m >= 0.0);
+    if (!ev) {
+        for (int i = tid; i < NP; i += T) { sHint[i] = 0u; sClr[i] = 0; }
+        for (int i = tid; i < Nl; i += T) gcert[i] = 0ull;
+        if (tid == 0) { sMisc[8] = 0; sMisc[9] = 0; sMisc[10] = 0; sMisc[11] = 0; }
+        block_sync<T>();
+        double loc[K], hic[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { loc[j] = 0.0; hic[j] = 0.0; }
+        corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                             C.veh_width_arg * 0.5 + C.safety_margin_m, 0xffffffffu, true, parity_ok, loc, hic, ray_tests, ex_scans);
+        corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
+    }
 
     double* sC0 = sB + tid;
     double* sCp = sB + NP + tid;
@@ -761,8 +1102,16 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
         // (the reference also rebuilds it after the LAST path update, but nothing reads that corridor: skipped)
         if (outer + 1 == max_outer) continue;
-        corridor_stream_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, B.seg, segI0, segO0, segE,
-                             C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+        {
+            const double guard = C.veh_width_m * 0.5 + C.safety_margin_m;
+            double loc[K], hic[K];
+            unsigned flagged = corridor_update_c<K>(pt, pv, sB, sMisc, sHint, sClr, sHalo, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                                                    guard, parity_ok, loc, hic, ray_tests);
+            if (block_or<T>(flagged != 0u))   // per CTA: the searching path rebuilds the flagged samples (no cluster traffic inside)
+                corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                                     guard, flagged, false, parity_ok, loc, hic, ray_tests, ex_scans);
+            corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
+        }
     }
 
     // =================== final geometry (main.cpp:761 / 1046) ===================
@@ -802,19 +1151,19 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
 
     // counters (the last cluster barrier also keeps every CTA alive until its neighbours' remote stores are done)
     {
-        double rt = (double)ray_tests, dz = 0.0;
-        cluster_sum2(rt, dz, sRed + ph * kcRedStride, cl, pt.lane, pt.warp);
+        double rt = (double)ray_tests, es = (double)ex_scans;
+        cluster_sum2(rt, es, sRed + ph * kcRedStride, cl, pt.lane, pt.warp);
         ph ^= 1;
         if (tid == 0 && cl.rank == 0) {
             st->outer_done = max_outer; st->accepted = acc_total; st->backtracks = bt_total; st->evals = ev_total;
-            st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap;
+            st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap; st->exist_scans = (int)es;
         }
     }
 }
 
 }  // namespace
 
-inline size_t smem_bytes_cluster(int K) { return (size_t)kcT * K * 48 + kcBytes; }
+inline size_t smem_bytes_cluster(int K) { return (size_t)kcT * K * (48 + 6) + kcBytes; }   // + per-sample corridor state
 
 int launch_solve_cluster(const DevBatch& B, const int* job_list, int n_list, int cs, int mode, void* stream)
 {

@@ -1180,14 +1180,17 @@ __device__ __forceinline__ double window_dist(const RayTile& tl, double2 P, floa
 }
 
 // conservative (rounded down) distance from p to every segment of the ring outside the window of j0
-__device__ __noinline__ float clearance_scan(const RayTile& tl_in, float px, float py, float m, int j0)
+// s_off / m_ring: the tile holds segments [s_off, s_off + nt) of a ring of m_ring segments (a streamed ring); j0 is ring-global
+__device__ __noinline__ float clearance_scan(const RayTile& tl_in, float px, float py, float m, int j0, int s_off = 0, int m_ring = -1)
 {
     const RayTile tl = tile_in_smem(tl_in);
-    const int M = tl.nt;
+    const int M = (m_ring < 0) ? tl.nt : m_ring;
     if (M <= 2 * kWin + 1) return 3e18f;
-    float best = 3e18f;   // distance, not squared
-    int sb0 = (j0 / SB) / SU;
-    if (sb0 >= tl.nsup) sb0 = 0;
+    // clearances are stored in 1/4 m up to 63.75 m: nothing farther away than that can matter, which also lets the
+    // scan skip every distant box from the start (a streamed ring has its near segments in one tile of many)
+    float best = 64.f;    // distance, not squared
+    int sb0 = ((j0 - s_off) / SB) / SU;
+    if (sb0 >= tl.nsup || sb0 < 0) sb0 = 0;
     for (int q = 0; q < tl.nsup; ++q) {
         int sb = sb0 + q;
         if (sb >= tl.nsup) sb -= tl.nsup;
@@ -1201,9 +1204,9 @@ __device__ __noinline__ float clearance_scan(const RayTile& tl_in, float px, flo
             const float4 bx = tl.boxF[b];
             const float ddx = fmaxf(0.f, fabsf(bx.x - px) - bx.z), ddy = fmaxf(0.f, fabsf(bx.y - py) - bx.w);
             if (ddx * ddx + ddy * ddy >= best * best) continue;
-            const int s1 = min(M, b * SB + SB);
+            const int s1 = min(tl.nt, b * SB + SB);
             for (int s = b * SB; s < s1; ++s) {
-                int dj = s - j0; if (dj < 0) dj += M;
+                int dj = s + s_off - j0; if (dj < 0) dj += M;
                 if (dj <= kWin || dj >= M - kWin) continue;              // window segment
                 const float d = sqrtf(seg_dist2_f(tl.segF[s], px, py)) - 4.f * m;
                 best = fminf(best, fmaxf(d, 0.f));
@@ -1430,7 +1433,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                 float Rc = 0.f;
                 if (pass == 0 && !first && ((hw >> (28 + ring)) & 1u)) {
                     const unsigned cq = (cw >> (8 * ring)) & 0xffu;
-                    Rc = (cq == 255u ? 3e18f : 0.25f * (float)cq) - disp - 4.f * m;
+                    Rc = 0.25f * (float)cq - disp - 4.f * m;
                 }
                 double pos_r = INF, neg_r = INF;
                 int seg_p = -1, seg_n = -1;
@@ -1595,8 +1598,15 @@ struct UpdCtx {
     int N, M0, M1, rf0, rf1;
     float mr0, mr1;
     bool parity_ok, closed;
+    // LOCAL form (a chunk of a long track): shared memory holds vertices [base, base + len] of each ring only; the
+    // path has one halo point each side (oHalo); FAR segments outside the range come from global memory (gs0/gs1)
+    int base0, base1, len0, len1, oHalo;
+    const double* gs0; const double* gs1;
 };
+// ring-global segment index -> index into the chunk-local vertex arrays
+__device__ __forceinline__ int loc_idx(int sg, int base, int M) { const int li = sg - base; return (li < 0) ? li + M : li; }
 // one sample of corridor_update: true = FLAGGED (hv/lv untouched), else the corridor bounds hv >= 0 >= lv
+template <bool LOCAL>
 __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, double cx0, double cy0, unsigned long long cert_w,
                                                     unsigned long long apex_w, double& hv_out, double& lv_out, long long& tests_io)
 {
@@ -1610,7 +1620,11 @@ __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, doub
     long long ray_tests = 0;
     const double2 Pc = sP[i];
     double nx, ny;
-    normal_at(sP, i, c.N, c.closed, nx, ny);
+    if (LOCAL) {   // the chunk's neighbours' end points live in the halo slots (closed track)
+        const double2* hl = reinterpret_cast<const double2*>(smem_raw + c.oHalo);
+        const double2 Pm = (i == 0) ? hl[0] : sP[i - 1], Pp = (i == c.N - 1) ? hl[1] : sP[i + 1];
+        normal_from_tangent((Pp.x - Pm.x) * 0.5, (Pp.y - Pm.y) * 0.5, nx, ny);
+    } else normal_at(sP, i, c.N, c.closed, nx, ny);
     const unsigned hw = reinterpret_cast<const unsigned*>(smem_raw + c.oHint)[i];
     const unsigned cw = reinterpret_cast<const unsigned short*>(smem_raw + c.oClr)[i];
     const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
@@ -1629,7 +1643,7 @@ __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, doub
         int j0 = (int)((hw >> (13 * ring)) & 0x1fffu);
         if (j0 >= M) j0 = 0;
         const unsigned cq = (cw >> (8 * ring)) & 0xffu;
-        const float rc = (cq == 255u ? 3e18f : 0.25f * (float)cq) - disp - 4.f * m;
+        const float rc = 0.25f * (float)cq - disp - 4.f * m;
         if (!((hw >> (28 + ring)) & 1u) || !(rc > 0.f)) flag = true;
         Rc[ring] = (double)rc;
         ins[ring] = c.parity_ok && (rf & 1) && ((hw >> (26 + ring)) & 1u);
@@ -1639,12 +1653,16 @@ __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, doub
 #pragma unroll 1
         for (int q = 0; q < 2 * kWin + 1; ++q) {
             // side of the ray's line each end point lies on (FP32, margin m): both clearly on one side -> no hit
-            const float2 fa = F[sg], fb = F[sg + 1];
-            const float sa = fnx * (fa.y - py) - fny * (fa.x - px), sb = fnx * (fb.y - py) - fny * (fb.x - px);
-            if (!(fminf(sa, sb) > m || fmaxf(sa, sb) < -m)) {
-                const double2 a = V[sg], b = V[sg + 1];
-                const double sd[4] = {a.x, a.y, b.x - a.x, b.y - a.y};      // v = b - a as in main.cpp:482
-                seg_hit(sd, Pc, nx, ny, pos, neg, sg, sp_, sn_, ray_tests);
+            const int li = LOCAL ? loc_idx(sg, ring ? c.base1 : c.base0, M) : sg;
+            if (LOCAL && li >= (ring ? c.len1 : c.len0)) flag = true;          // window outside the chunk-local range
+            else {
+                const float2 fa = F[li], fb = F[li + 1];
+                const float sa = fnx * (fa.y - py) - fny * (fa.x - px), sb = fnx * (fb.y - py) - fny * (fb.x - px);
+                if (!(fminf(sa, sb) > m || fmaxf(sa, sb) < -m)) {
+                    const double2 a = V[li], b = V[li + 1];
+                    const double sd[4] = {a.x, a.y, b.x - a.x, b.y - a.y};      // v = b - a as in main.cpp:482
+                    seg_hit(sd, Pc, nx, ny, pos, neg, sg, sp_, sn_, ray_tests);
+                }
             }
             sg = (sg + 1 == M) ? 0 : sg + 1;
         }
@@ -1680,8 +1698,11 @@ __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, doub
                 int sg = sg0;
 #pragma unroll 1
                 for (int q = 0; q < 2 * kWin + 1; ++q) {
-                    const float2 fa = F[sg], fb = F[sg + 1];
-                    dminf = fminf(dminf, seg_dist2_f(make_float4(fa.x, fa.y, fb.x, fb.y), px, py));
+                    const int li = LOCAL ? loc_idx(sg, ring ? c.base1 : c.base0, M) : sg;
+                    if (!(LOCAL && li >= (ring ? c.len1 : c.len0))) {          // (out of range: the hit loop above already flagged)
+                        const float2 fa = F[li], fb = F[li + 1];
+                        dminf = fminf(dminf, seg_dist2_f(make_float4(fa.x, fa.y, fb.x, fb.y), px, py));
+                    }
                     sg = (sg + 1 == M) ? 0 : sg + 1;
                 }
                 const float lim = sqrtf(dminf) + 8.f * m;
@@ -1690,11 +1711,14 @@ __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, doub
                 sg = sg0;
 #pragma unroll 1
                 for (int q = 0; q < 2 * kWin + 1; ++q) {
-                    const float2 fa = F[sg], fb = F[sg + 1];
-                    if (seg_dist2_f(make_float4(fa.x, fa.y, fb.x, fb.y), px, py) <= lim2) {
-                        const double2 a = V[sg], bb = V[sg + 1];
-                        const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
-                        best2 = fmin(best2, seg_dist2(sd, Pc));
+                    const int li = LOCAL ? loc_idx(sg, ring ? c.base1 : c.base0, M) : sg;
+                    if (!(LOCAL && li >= (ring ? c.len1 : c.len0))) {
+                        const float2 fa = F[li], fb = F[li + 1];
+                        if (seg_dist2_f(make_float4(fa.x, fa.y, fb.x, fb.y), px, py) <= lim2) {
+                            const double2 a = V[li], bb = V[li + 1];
+                            const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
+                            best2 = fmin(best2, seg_dist2(sd, Pc));
+                        }
                     }
                     sg = (sg + 1 == M) ? 0 : sg + 1;
                 }
@@ -1711,11 +1735,25 @@ __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, doub
                     const int f = (int)w1;
                     bool hit = false;
                     if (f < M) {
-                        const double2 a = V[f], bb = V[f + 1];
-                        const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
-                        double tp = INF, tn = INF; int s_p = -1, s_n = -1;
-                        seg_hit(sd, Pc, nx, ny, tp, tn, f, s_p, s_n, ray_tests);
-                        hit = (dir ? tn : tp) < INF;
+                        // the segment the ray hit last time; on a long track that hit can be kilometres away and drifts
+                        // along the ring from build to build, so the LOCAL form also tries the neighbours and follows it
+                        const int ntry = LOCAL ? 5 : 1;
+                        for (int q = 0; q < ntry && !hit; ++q) {
+                            int fq = f + ((q + 1) >> 1) * ((q & 1) ? 1 : -1);       // f, f+1, f-1, f+2, f-2
+                            if (fq < 0) fq += M; else if (fq >= M) fq -= M;
+                            double2 a, bb;
+                            const int li = LOCAL ? loc_idx(fq, ring ? c.base1 : c.base0, M) : fq;
+                            if (LOCAL && li >= (ring ? c.len1 : c.len0)) {     // far away: the segment record itself (x0,y0,x1,y1)
+                                const double* g = (ring ? c.gs1 : c.gs0) + 4 * (size_t)fq;
+                                a = make_double2(g[0], g[1]); bb = make_double2(g[2], g[3]);
+                            } else { a = V[li]; bb = V[li + 1]; }
+                            const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
+                            double tp = INF, tn = INF; int s_p = -1, s_n = -1;
+                            seg_hit(sd, Pc, nx, ny, tp, tn, fq, s_p, s_n, ray_tests);
+                            hit = (dir ? tn : tp) < INF;
+                            if (LOCAL && hit && q > 0)
+                                const_cast<unsigned long long*>(c.gcert)[i] = ((unsigned long long)(unsigned)fq << 32) | (unsigned long long)w0;
+                        }
                     }
                     if (!hit) flag = true;
                 } else if (stt == kCertCone) {
@@ -1780,6 +1818,7 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
     c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
     c.ox = org.x; c.oy = org.y; c.guard = guard; c.N = N; c.M0 = M0; c.M1 = M1; c.rf0 = rf0; c.rf1 = rf1; c.mr0 = mr0; c.mr1 = mr1;
     c.parity_ok = parity_ok; c.closed = closed;
+    c.base0 = 0; c.base1 = 0; c.len0 = M0; c.len1 = M1; c.oHalo = 0; c.gs0 = nullptr; c.gs1 = nullptr;
     unsigned flagged = 0u;
     // the per-sample code exists once (a real function): the instruction cache matters more than the call, and the
     // results stay in registers (static j)
@@ -1796,7 +1835,7 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
         if (j + 1 < K && i + T < N) { cn = *reinterpret_cast<const double2*>(gcenter + 2 * (i + T)); wn = gcert[i + T]; an = gapex[i + T]; }
         if (i >= N) continue;
         double hv = 0.0, lv = 0.0;
-        if (corridor_update_sample(c, i, cc.x, cc.y, wc, ac, hv, lv, ray_tests)) flagged |= (1u << j);
+        if (corridor_update_sample<false>(c, i, cc.x, cc.y, wc, ac, hv, lv, ray_tests)) flagged |= (1u << j);
         else { hic[j] = hv; loc[j] = lv; }
     }
     return flagged;

@@ -557,8 +557,10 @@ __device__ __forceinline__ void corridor_search_c(const Part& pt, const PathView
                         // everything outside the anchor's window is at least `clr` away; exact point-ring distance
                         const int anchor = (a.pos[ring] <= a.neg[ring]) ? a.sp[ring] : a.sn[ring];
                         if (anchor >= 0 && mr <= 8191) a.clr[ring] = fminf(a.clr[ring], clearance_scan(tl, a.px, a.py, m, anchor, t0, mr));
-                        const double d = dist_scan(tl, Pc, a.px, a.py, m, 0, fmin(a.dist[ring], fmin(a.pos[ring], a.neg[ring])));
-                        a.dist[ring] = fmin(a.dist[ring], d);
+                        if (a.pos[ring] == INF || a.neg[ring] == INF) {     // only a ring some ray misses needs it (main.cpp:696)
+                            const double d = dist_scan(tl, Pc, a.px, a.py, m, 0, fmin(a.dist[ring], fmin(a.pos[ring], a.neg[ring])));
+                            a.dist[ring] = fmin(a.dist[ring], d);
+                        }
                     }
                 }
             }

@@ -15,7 +15,7 @@
 
 using rl::DevBatch;
 
-constexpr int kMaxChunks = 4;
+constexpr int kMaxChunks = 8;
 
 struct rl_ctx {
     int device = 0;
@@ -156,8 +156,9 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
     b->n_chunks = n_chunks;
     b->chunk_job0.assign((size_t)n_chunks + 1, 0);
     b->chunk_tmax.assign((size_t)n_chunks, -1);
-    int max_chain = 8;
-    if (const char* e = std::getenv("RL_MAX_CHAIN")) max_chain = std::max(1, std::atoi(e));   // tuning / test knob
+    int max_chain = 8, force_chain = 0;
+    if (const char* e = std::getenv("RL_MAX_CHAIN")) max_chain = std::max(1, std::atoi(e));   // tuning knob
+    if (const char* e = std::getenv("RL_FORCE_CHAIN")) force_chain = std::max(0, std::atoi(e)); // test hook: chains of that length whatever the batch size
     for (int c = 0; c <= n_chunks; ++c) b->chunk_job0[c] = (int)(((long long)d->n_jobs * c) / n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
         std::vector<std::vector<int>> bucket(rl::kNumClasses * 3);
@@ -181,7 +182,7 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
         for (int k = 0; k < rl::kNumClasses * 3; ++k) {
             if (bucket[k].empty()) continue;
             const int slots = std::max(1, c_sm(b) * rl::ctas_per_sm(k / 3));
-            const int chain = std::max(1, std::min(max_chain, (int)(bucket[k].size() / (size_t)(6 * slots))));
+            const int chain = force_chain > 0 ? force_chain : std::max(1, std::min(max_chain, (int)(bucket[k].size() / (size_t)(6 * slots))));
             ClassList l = {k / 3, k % 3, (int)b->joblist.size(), (int)bucket[k].size(), c, (int)b->itemoff.size(), 0};
             int run = 0, last_t = -1;
             for (size_t q = 0; q < bucket[k].size(); ++q) {
@@ -196,7 +197,19 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
         }
         for (size_t k = 0; k < cbucket.size(); ++k) {
             if (cbucket[k].empty()) continue;
-            b->lists.push_back({rl::kClusterClassBase + (int)(k / 2), (int)(k % 2), (int)b->joblist.size(), (int)cbucket[k].size(), c, 0, 0});
+            const int cs = (int)(k / 2);
+            const int slots = std::max(1, (c_sm(b) * 2) / cs);      // two CTAs per SM, cs CTAs per cluster
+            const int chain = force_chain > 0 ? force_chain : std::max(1, std::min(max_chain, (int)(cbucket[k].size() / (size_t)(6 * slots))));
+            ClassList l = {rl::kClusterClassBase + cs, (int)(k % 2), (int)b->joblist.size(), (int)cbucket[k].size(), c, (int)b->itemoff.size(), 0};
+            int run = 0, last_t = -1;
+            for (size_t q = 0; q < cbucket[k].size(); ++q) {
+                const int t = d->jobs[cbucket[k][q]].track;
+                const bool eval_job = (d->jobs[cbucket[k][q]].stage == RL_STAGE_EVAL);
+                if (q == 0 || t != last_t || run >= chain || eval_job) { b->itemoff.push_back((int)q); ++l.n_items; run = 0; }
+                last_t = eval_job ? -1 : t; ++run;
+            }
+            b->itemoff.push_back((int)cbucket[k].size());
+            b->lists.push_back(l);
             b->joblist.insert(b->joblist.end(), cbucket[k].begin(), cbucket[k].end());
         }
     }

@@ -821,7 +821,7 @@ __device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const Path
 // ---- the cluster solver kernel -----------------------------------------------------------------------------
 template <int K, int MODE>
 __global__ void __launch_bounds__(kcT, 2)
-solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_list)
+solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __restrict__ item_off, int n_items)
 {
     constexpr int T = kcT, NP = kcT * K;
     constexpr bool EXACT = (MODE == kModeExact);
@@ -845,8 +845,20 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
     cl.left = (cl.rank == 0) ? cl.CS - 1 : cl.rank - 1;
     cl.right = (cl.rank == cl.CS - 1) ? 0 : cl.rank + 1;
     const int cid = (int)(blockIdx.x / cl.CS);
-    if (cid >= n_list) return;   // uniform over the cluster
-    const int jid = job_list[cid];
+    if (cid >= n_items) return;   // uniform over the cluster
+    // one cluster works through one ITEM: a short chain of jobs on the same track (see solve_kernel); the corridor state
+    // of every chunk (anchors, clearances, parity, certificates) carries over to the next job of the chain
+    const int it0 = item_off[cid], it1 = item_off[cid + 1];
+    uint32_t bar_phase = 0;
+    int fslot = 0, prev_trk = -1;
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sFlag[0] = 0; sFlag[1] = 0; sFlag[2] = 0;
+    }
+    cl_sync();   // every CTA of the cluster is running and initialised before any distributed-shared-memory access
+  for (int itj = it0; itj < it1; ++itj) {
+    const int jid = job_list[itj];
     const rl_job job = B.jobs[jid];
     const rl_params& C = B.params[job.param];
     rl_job_stats* st = B.stats + jid;
@@ -882,11 +894,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
     const int tid = pt.tid, cnt = pt.cnt, start = pt.start;
     PathView pv; pv.sP = sP; pv.halo = sHalo; pv.Nloc = Nl;
 
-    uint32_t bar_phase = 0;
     if (tid == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sFlag[0] = 0; sFlag[1] = 0; sFlag[2] = 0;
         if (cl.rank == 0) {
             st->status = RL_OK; st->n = N; st->outer_done = 0; st->accepted = 0; st->backtracks = 0; st->evals = 0;
             st->vpass_rounds = 0; st->exist_scans = 0; st->ray_tests = 0; st->lap_time = 0.0;
@@ -896,7 +904,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
         }
         fence_proxy_async();
     }
-    cl_sync();   // every CTA of the cluster is running and initialised before any distributed-shared-memory access
+    block_sync<T>();
 
     // ---- load this chunk of the centre line (TMA bulk copy) and trade end points with the neighbours ----
     if (tid == 0) {
@@ -923,7 +931,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
     const double inv2h = 1.0 / (2 * h), invh2 = 1.0 / (h * h);          // DiffOps, main.cpp:547
     const double lamJ = C.lambda_smooth * inv2h * inv2h;
     long long ray_tests = 0;
-    int vrounds = 0, ph = 0, fslot = 0;
+    int vrounds = 0, ph = 0;
     int acc_total = 0, bt_total = 0, ev_total = 0;
     const int max_outer = ev ? 0 : C.max_outer_iters;
 
@@ -937,15 +945,25 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
     int ex_scans = 0;
     const bool parity_ok = (C.veh_width_arg * 0.5 + C.safety_margin_m >= 0.0) && (C.veh_width_m * 0.5 + C.safety_margin_m >= 0.0);
     if (!ev) {
-        for (int i = tid; i < NP; i += T) { sHint[i] = 0u; sClr[i] = 0; }
-        for (int i = tid; i < Nl; i += T) gcert[i] = 0ull;
-        if (tid == 0) { sMisc[8] = 0; sMisc[9] = 0; sMisc[10] = 0; sMisc[11] = 0; }
-        block_sync<T>();
+        const double guard0 = C.veh_width_arg * 0.5 + C.safety_margin_m;
+        const bool same_track = (trk == prev_trk);   // the previous job of this chain left its corridor state behind
         double loc[K], hic[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) { loc[j] = 0.0; hic[j] = 0.0; }
-        corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
-                             C.veh_width_arg * 0.5 + C.safety_margin_m, 0xffffffffu, true, parity_ok, loc, hic, ray_tests, ex_scans);
+        if (!same_track) {
+            for (int i = tid; i < NP; i += T) { sHint[i] = 0u; sClr[i] = 0; }
+            for (int i = tid; i < Nl; i += T) gcert[i] = 0ull;
+            if (tid == 0) { sMisc[8] = 0; sMisc[9] = 0; sMisc[10] = 0; sMisc[11] = 0; }
+            block_sync<T>();
+            corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                                 guard0, 0xffffffffu, true, parity_ok, loc, hic, ray_tests, ex_scans);
+        } else {
+            unsigned flagged = corridor_update_c<K>(pt, pv, sB, sMisc, sHint, sClr, sHalo, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                                                    guard0, parity_ok, loc, hic, ray_tests);
+            if (block_or<T>(flagged != 0u))
+                corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                                     guard0, flagged, false, parity_ok, loc, hic, ray_tests, ex_scans);
+        }
         corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
     }
 
@@ -1116,6 +1134,17 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
         }
     }
 
+    // the next job of the chain inherits this chunk's certificates (same thread, same samples: no barrier needed)
+    if (!ev && itj + 1 < it1) {
+        const int njid = job_list[itj + 1];
+        if (B.jobs[njid].track == trk) {
+            const long long nrow0 = B.job_off[njid] + cl.n0;
+            unsigned long long* ncert = reinterpret_cast<unsigned long long*>(B.heading + nrow0);
+            unsigned long long* napex = reinterpret_cast<unsigned long long*>(B.curvature + nrow0);
+            for (int i = tid; i < Nl; i += T) { ncert[i] = gcert[i]; napex[i] = gapex[i]; }
+        }
+    }
+    prev_trk = ev ? -1 : trk;
     // =================== final geometry (main.cpp:761 / 1046) ===================
     block_sync<T>();
     double lap = 0.0;
@@ -1161,17 +1190,19 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, int n_l
             st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap; st->exist_scans = (int)es;
         }
     }
+    cl_sync();   // the next job of the chain reuses the shared-memory regions of every CTA
+  }
 }
 
 }  // namespace
 
 inline size_t smem_bytes_cluster(int K) { return (size_t)kcT * K * (48 + 6) + kcBytes; }   // + per-sample corridor state
 
-int launch_solve_cluster(const DevBatch& B, const int* job_list, int n_list, int cs, int mode, void* stream)
+int launch_solve_cluster(const DevBatch& B, const int* job_list, const int* item_off, int n_items, int cs, int mode, void* stream)
 {
     constexpr int K = 8;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_list * cs));
+    cfg.gridDim = dim3((unsigned)(n_items * cs));
     cfg.blockDim = dim3(kcT);
     cfg.dynamicSmemBytes = smem_bytes_cluster(K);
     cfg.stream = (cudaStream_t)stream;
@@ -1180,8 +1211,8 @@ int launch_solve_cluster(const DevBatch& B, const int* job_list, int n_list, int
     at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaError_t e;
-    if (mode == 1) e = cudaLaunchKernelEx(&cfg, solve_cluster_kernel<K, 1>, B, job_list, n_list);
-    else e = cudaLaunchKernelEx(&cfg, solve_cluster_kernel<K, 0>, B, job_list, n_list);
+    if (mode == 1) e = cudaLaunchKernelEx(&cfg, solve_cluster_kernel<K, 1>, B, job_list, item_off, n_items);
+    else e = cudaLaunchKernelEx(&cfg, solve_cluster_kernel<K, 0>, B, job_list, item_off, n_items);
     return (int)e;
 }
 int configure_solve_cluster()

@@ -72,7 +72,7 @@ inline int cluster_size_for_n(long long n, int force = 0)
     return 0;
 }
 // mode 0 = ragged chunks, 1 = every chunk holds exactly 2048 samples.  Returns a cudaError_t as int.
-int launch_solve_cluster(const DevBatch& B, const int* job_list, int n_list, int cs, int mode, void* stream);
+int launch_solve_cluster(const DevBatch& B, const int* job_list, const int* item_off, int n_items, int cs, int mode, void* stream);
 int configure_solve_cluster();
 
 // ---- the stage before the path (raceline_geom.cu): centre line + width/geometry rows, batched over tracks ----
@@ -99,7 +99,7 @@ int launch_geom(const GeomBatch& G, int n_tracks, int max_pts, void* stream);   
 // launches job_list[0..n_list) (indices into B.jobs) with the kernel of class `cls` and mode
 // 0 = closed track, 1 = closed track and every job has N == T*K, 2 = open track.  One CTA per ITEM: item k is the chain
 // job_list[item_off[k] .. item_off[k+1]) of jobs on the same track (item_off has n_items+1 entries, relative to
-// job_list).  Cluster classes take one job per cluster and ignore the items.  Returns a cudaError_t as int.
+// job_list); a cluster class gives each item to one thread-block cluster.  Returns a cudaError_t as int.
 int launch_solve(const DevBatch& B, const int* job_list, int n_list, const int* item_off, int n_items, int cls, int mode, void* stream);
 // CTAs of class `cls` one SM holds at a time (registers and shared memory)
 inline int ctas_per_sm(int cls) { const int np = kClasses[cls].T * kClasses[cls].K; return np >= 4096 ? 1 : (4096 / np > 16 ? 16 : 4096 / np); }

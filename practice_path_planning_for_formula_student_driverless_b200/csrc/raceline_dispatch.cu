@@ -41,7 +41,7 @@ int configure_kernels()
 int launch_solve(const DevBatch& B, const int* job_list, int n_list, const int* item_off, int n_items, int cls, int mode, void* stream)
 {
     if (n_list <= 0) return 0;
-    if (cls >= kClusterClassBase) return launch_solve_cluster(B, job_list, n_list, cls - kClusterClassBase, mode, stream);
+    if (cls >= kClusterClassBase) return launch_solve_cluster(B, job_list, item_off, n_items, cls - kClusterClassBase, mode, stream);
     switch (kClasses[cls].T) {
         case 32: return launch_solve_32(B, job_list, item_off, n_items, mode, stream);
         case 64: return launch_solve_64(B, job_list, item_off, n_items, mode, stream);

@@ -1,0 +1,91 @@
+"""Job chains: one CTA (or one cluster) works through consecutive jobs on the same track and keeps what the corridor code
+learnt (anchors, clearances, parity bits, certificates), so every job after the first starts with a corridor UPDATE.
+The host only forms chains in large batches; RL_FORCE_CHAIN makes it form them in small ones so that the chained path
+is checked against the oracle and, bit for bit, against the unchained path."""
+import numpy as np
+import pytest
+
+import practice_path_planning_for_formula_student_driverless_b200 as rl
+from conftest import MAPS, TOL_LAP_REL, assert_result_close, load_golden
+from test_gpu_parity import MC, MT, oracle_ref, stalled, track_of
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_bits(a, b):
+    assert np.array_equal(a.raceline, b.raceline) and np.array_equal(a.alpha_total, b.alpha_total)
+    assert np.array_equal(a.curvature, b.curvature) and np.array_equal(a.heading, b.heading)
+    assert a.stats.accepted == b.stats.accepted and a.stats.backtracks == b.stats.backtracks and a.stats.evals == b.stats.evals
+    if a.v is not None and b.v is not None:
+        assert np.array_equal(a.v, b.v) and a.lap_time == b.lap_time
+
+
+def test_chained_shipped_maps(ctx, goldens, monkeypatch):
+    """MC + MT + a second Config per map in one chain of three jobs; the reference goldens and the unchained bits"""
+    tracks = [track_of(goldens[n]) for n in MAPS]
+    cfgs = [rl.Config(), rl.Config(lambda_smooth=3.2e-3, w_time_gain=2.0, veh_width_m=1.2)]
+    jobs = [(t, c, st) for t in range(len(tracks)) for (c, st) in ((0, MC), (0, MT), (1, MT))]
+    plain = rl.solve_batch(tracks, cfgs, jobs, ctx=ctx)
+    monkeypatch.setenv("RL_FORCE_CHAIN", "3")
+    chained = rl.solve_batch(tracks, cfgs, jobs, ctx=ctx)
+    monkeypatch.delenv("RL_FORCE_CHAIN")
+    for (t, c, st), a, b in zip(jobs, chained, plain):
+        _same_bits(a, b)
+        if c == 0:
+            g, pre = goldens[MAPS[t]], ("mc_" if st == MC else "mt_")
+            assert_result_close(a, g, pre, st == MT, tag=(MAPS[t], pre, "chained"))
+            assert a.stats.backtracks == int(g[pre + "bt"].sum())
+    # jobs after the first of a chain did not search the rings again: far fewer exact ray tests
+    assert chained[1].stats.ray_tests < plain[1].stats.ray_tests
+
+
+@pytest.mark.parametrize("n", [40, 300, 1500, 2048])
+def test_chained_synthetic_vs_oracle(ctx, n, monkeypatch):
+    center, seg, L, m = rl.synth_tracks(2, n, seed_base=0xC4A1 + n)
+    center, seg = center.reshape(2, n, 2), seg.reshape(2, 2, m, 4)
+    tracks = [rl.Track(center[i], seg[i, 0], seg[i, 1], L[i]) for i in range(2)]
+    cfgs = [rl.Config(), rl.Config(P_max_W=30000.0, safety_margin_m=0.2)]
+    jobs = [(0, 0, MC), (0, 0, MT), (0, 1, MC), (0, 1, MT), (1, 0, MT), (1, 1, MT)]
+    monkeypatch.setenv("RL_FORCE_CHAIN", "4")
+    res = rl.solve_batch(tracks, cfgs, jobs, ctx=ctx)
+    monkeypatch.delenv("RL_FORCE_CHAIN")
+    for (t, c, st), r in zip(jobs, res):
+        o = oracle_ref(st, tracks[t], cfgs[c].to_params())
+        assert_result_close(r, o, "o_", st == MT, tag=("chain", n, t, c, st))
+        assert r.stats.accepted == o["stats"].accepted, (n, t, c, st)
+        if not stalled(o["stats"]):
+            assert r.stats.backtracks == o["stats"].backtracks, (n, t, c, st)
+        if st == MT:
+            assert abs(r.lap_time - o["lap"]) <= TOL_LAP_REL * o["lap"]
+
+
+def test_chained_open_track(ctx, monkeypatch):
+    g = load_golden("open_competition_map1")
+    tr = rl.Track(g["center_xy"], g["inner_seg"], g["outer_seg"], g["L"], closed=False)
+    monkeypatch.setenv("RL_FORCE_CHAIN", "2")
+    res = rl.solve_batch([tr], [rl.Config()], [(0, 0, MC), (0, 0, MT)], ctx=ctx)
+    monkeypatch.delenv("RL_FORCE_CHAIN")
+    for st, pre, r in ((MC, "mc_", res[0]), (MT, "mt_", res[1])):
+        assert_result_close(r, g, pre, st == MT, tag=("open chained", pre))
+        assert r.stats.accepted == g[pre + "accepted"] and r.stats.backtracks == g[pre + "backtracks"]
+
+
+@pytest.mark.parametrize("cs,n", [(2, 1100), (4, 3000)])
+def test_chained_cluster_vs_oracle(ctx, cs, n, monkeypatch):
+    """the cluster kernel's chains: MC then MT of the same long track in one cluster"""
+    center, seg, L, m = rl.synth_tracks(1, n, seed_base=0xC4B2 + n)
+    tr = rl.Track(center.reshape(n, 2), seg.reshape(2, m, 4)[0], seg.reshape(2, m, 4)[1], L[0])
+    cfg = rl.Config()
+    jobs = [(0, 0, MC), (0, 0, MT)]
+    monkeypatch.setenv("RL_FORCE_CLUSTER", str(cs))
+    plain = rl.solve_batch([tr], [cfg], jobs, ctx=ctx)
+    monkeypatch.setenv("RL_FORCE_CHAIN", "2")
+    chained = rl.solve_batch([tr], [cfg], jobs, ctx=ctx)
+    monkeypatch.delenv("RL_FORCE_CHAIN")
+    monkeypatch.delenv("RL_FORCE_CLUSTER")
+    for (t, c, st), a, b in zip(jobs, chained, plain):
+        _same_bits(a, b)
+        o = oracle_ref(st, tr, cfg.to_params())
+        assert_result_close(a, o, "o_", st == MT, tag=("cluster chain", cs, n, st))
+        assert a.stats.accepted == o["stats"].accepted
+    assert chained[1].stats.ray_tests < plain[1].stats.ray_tests

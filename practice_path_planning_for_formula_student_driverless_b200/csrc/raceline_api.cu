@@ -15,7 +15,7 @@
 
 using rl::DevBatch;
 
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 4;
 
 struct rl_ctx {
     int device = 0;

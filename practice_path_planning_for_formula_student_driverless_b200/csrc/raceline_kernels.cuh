@@ -1523,6 +1523,20 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                         hw &= ~(1u << (28 + ring));
                     }
                     sHint[i] = hw; sClr[i] = cw;
+                    if (first && hs >= 0 && !(parity_ok && chain && ((hw >> (26 + ring)) & 1u))) {
+                        // the certificate the update passes will ask for, made now: the ray WITHOUT a near hit on a ring the
+                        // sample is not inside of.  (On demand it would be made in some later build, for a few samples at a
+                        // time, each time at the price of two tile builds and a round of block barriers.)
+                        const float rc0 = 0.25f * (float)((cw >> (8 * ring)) & 0xffu) - disp - 4.f * m;
+                        const int dirq = (pos_r <= (double)rc0) ? ((neg_r <= (double)rc0) ? -1 : 1) : ((neg_r <= (double)rc0) ? 0 : -1);
+                        if (dirq >= 0) {
+                            ExQuery qy;
+                            qy.P = Pc; qy.nx = nx; qy.ny = ny; qy.px = px; qy.py = py; qy.m = m; qy.j0 = j0; qy.ring = ring; qy.dir = dirq;
+                            qy.i = i; qy.mr = mr; qy.cx0 = cx0; qy.cy0 = cy0; qy.ox = org.x; qy.oy = org.y;
+                            qy.guard = guard; qy.toward = dirq ? pos_r : neg_r; qy.cert = gcert[i]; qy.apex = gapex[i];
+                            far_hit_exists(tl, qy, gcert, gapex, ray_tests, ex_scans);
+                        }
+                    }
                 }
                 // a ring some ray misses entirely: nearest point-segment distance (main.cpp:696)
                 if (!ex_p || !ex_n) {

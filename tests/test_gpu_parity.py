@@ -343,3 +343,42 @@ def test_open_tracks_vs_oracle(ctx, n):
             assert r.stats.backtracks == o["stats"].backtracks, (n, st)
         if st == MT:
             assert abs(r.lap_time - o["lap"]) <= TOL_LAP_REL * max(o["lap"], 1e-9)
+
+
+def test_config_sweep_4096(ctx, goldens):
+    """BASELINE configs[2]: competition_map2 x 8^4 grid over lambda_smooth x mu x P_max_W x w_time_gain (SURVEY 8d ranges;
+    a_total_max = mu * 9.81 set per combo, the reference evaluates it once at construction, main.cpp:102).
+    All 8192 jobs in one batch sharing one copy of the geometry; 64 combos spot-checked against the pinned oracle."""
+    import time
+    g = goldens["competition_map2"]
+    tr = track_of(g)
+    lam = np.logspace(np.log10(4e-4), np.log10(6.4e-3), 8)
+    mu = np.linspace(1.15, 1.6, 8)
+    pmax = np.linspace(20e3, 80e3, 8)
+    wtg = np.linspace(0.0, 3.5, 8)
+    cfgs = [rl.Config(lambda_smooth=float(a), a_total_max=float(b) * 9.81, P_max_W=float(c), w_time_gain=float(d))
+            for a in lam for b in mu for c in pmax for d in wtg]
+    assert len(cfgs) == 4096
+    jobs = [(0, p, st) for p in range(4096) for st in (MC, MT)]
+    pb = rl.PackedBatch([tr], [c.to_params() for c in cfgs], jobs)
+    t0 = time.perf_counter()
+    ctx.solve_batch(pb)
+    dt = time.perf_counter() - t0
+    print(f"4096-combo sweep: {4096 / dt:.0f} solves/s end to end")
+    laps = np.array([pb.out_stats[2 * p + 1].lap_time for p in range(4096)])
+    assert np.all(np.isfinite(laps)) and np.all(laps > 10.0) and np.all(laps < 80.0)
+    assert all(pb.out_stats[j].status == 0 and pb.out_stats[j].outer_done == 14 for j in range(0, 8192, 37))
+    # the grid really is 4096 different problems: (almost) no two combos predict the same lap
+    assert np.unique(np.round(laps, 9)).size > 2000
+    rng = np.random.default_rng(4096)
+    for p in rng.choice(4096, size=64, replace=False):
+        prm = cfgs[p].to_params()
+        for k, st in enumerate((MC, MT)):
+            o = oracle_ref(st, tr, prm)
+            r = pb.result(2 * int(p) + k)
+            assert_result_close(r, o, "o_", st == MT, tag=("sweep4096", int(p), st))
+            assert r.stats.accepted == o["stats"].accepted, (int(p), st)
+            if not stalled(o["stats"]):
+                assert r.stats.backtracks == o["stats"].backtracks, (int(p), st)
+            if st == MT:
+                assert abs(r.lap_time - o["lap"]) <= TOL_LAP_REL * o["lap"]

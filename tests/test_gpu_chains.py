@@ -89,3 +89,29 @@ def test_chained_cluster_vs_oracle(ctx, cs, n, monkeypatch):
         assert_result_close(a, o, "o_", st == MT, tag=("cluster chain", cs, n, st))
         assert a.stats.accepted == o["stats"].accepted
     assert chained[1].stats.ray_tests < plain[1].stats.ray_tests
+
+
+@pytest.mark.parametrize("n,cs", [(700, 0), (1100, 2), (4100, 8)])
+def test_ring_order_does_not_matter(ctx, n, cs, monkeypatch):
+    """rings rotated to another start cone and traversed the other way round (still vertex chains): anchors, windows and
+    chunk-local vertex ranges work on ring indices, the results must not care"""
+    center, seg, L, m = rl.synth_tracks(1, n, seed_base=0xC4C3 + n)
+    seg = seg.reshape(2, m, 4)
+    inner = np.roll(seg[0], -(m // 3), axis=0)                              # another start cone
+    outer = seg[1][::-1][:, [2, 3, 0, 1]].copy()                            # the other way round: segment i = (end, start) reversed
+    tr0 = rl.Track(center.reshape(n, 2), seg[0], seg[1], L[0])
+    tr1 = rl.Track(center.reshape(n, 2), inner, outer, L[0])
+    cfg = rl.Config()
+    if cs:
+        monkeypatch.setenv("RL_FORCE_CLUSTER", str(cs))
+    res = rl.solve_batch([tr0, tr1], [cfg], [(0, 0, MT), (1, 0, MT), (1, 0, MC)], ctx=ctx)
+    if cs:
+        monkeypatch.delenv("RL_FORCE_CLUSTER")
+    o = oracle_ref(MT, tr1, cfg.to_params())
+    assert_result_close(res[1], o, "o_", True, tag=("ring order", n, cs))
+    assert res[1].stats.accepted == o["stats"].accepted and res[1].stats.backtracks == o["stats"].backtracks
+    # same geometry, same answer (the searches take minima over the same set of segments)
+    assert np.max(np.abs(res[0].alpha_total - res[1].alpha_total)) < 1e-9
+    assert abs(res[0].lap_time - res[1].lap_time) <= 1e-9 * res[0].lap_time
+    omc = oracle_ref(MC, tr1, cfg.to_params())
+    assert_result_close(res[2], omc, "o_", False, tag=("ring order mc", n, cs))

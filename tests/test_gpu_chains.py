@@ -115,3 +115,27 @@ def test_ring_order_does_not_matter(ctx, n, cs, monkeypatch):
     assert abs(res[0].lap_time - res[1].lap_time) <= 1e-9 * res[0].lap_time
     omc = oracle_ref(MC, tr1, cfg.to_params())
     assert_result_close(res[2], omc, "o_", False, tag=("ring order mc", n, cs))
+
+
+@pytest.mark.parametrize("n,cs", [(300, 0), (700, 0), (1100, 2)])
+def test_segment_soup_rings(ctx, n, cs, monkeypatch):
+    """rings as an unordered set of segments (no vertex chain): the update path and the parity shortcut do not apply,
+    the searching path answers every build; chained with a second job"""
+    center, seg, L, m = rl.synth_tracks(1, n, seed_base=0xC4D4 + n)
+    seg = seg.reshape(2, m, 4)
+    rng = np.random.default_rng(n)
+    tr = rl.Track(center.reshape(n, 2), seg[0][rng.permutation(m)], seg[1][rng.permutation(m)], L[0])
+    cfg = rl.Config()
+    if cs:
+        monkeypatch.setenv("RL_FORCE_CLUSTER", str(cs))
+    monkeypatch.setenv("RL_FORCE_CHAIN", "2")
+    res = rl.solve_batch([tr], [cfg], [(0, 0, MC), (0, 0, MT)], ctx=ctx)
+    monkeypatch.delenv("RL_FORCE_CHAIN")
+    if cs:
+        monkeypatch.delenv("RL_FORCE_CLUSTER")
+    for st, r in zip((MC, MT), res):
+        o = oracle_ref(st, tr, cfg.to_params())
+        assert_result_close(r, o, "o_", st == MT, tag=("soup", n, cs, st))
+        assert r.stats.accepted == o["stats"].accepted
+        if not stalled(o["stats"]):
+            assert r.stats.backtracks == o["stats"].backtracks

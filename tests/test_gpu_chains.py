@@ -139,3 +139,23 @@ def test_segment_soup_rings(ctx, n, cs, monkeypatch):
         assert r.stats.accepted == o["stats"].accepted
         if not stalled(o["stats"]):
             assert r.stats.backtracks == o["stats"].backtracks
+
+
+@pytest.mark.parametrize("n,m", [(300, 400), (2048, 1400)])
+def test_rings_larger_than_one_tile(ctx, n, m, monkeypatch):
+    """more cones per ring than one shared-memory tile of the job's size class holds: the tiled corridor path of the
+    single-CTA kernel (no per-sample state), also as the second job of a chain"""
+    center, seg, L, mm = rl.synth_tracks(1, n, m_per_ring=m, seed_base=0xC4E5 + n)
+    assert mm == m
+    seg = seg.reshape(2, m, 4)
+    tr = rl.Track(center.reshape(n, 2), seg[0], seg[1], L[0])
+    cfg = rl.Config()
+    monkeypatch.setenv("RL_FORCE_CHAIN", "2")
+    res = rl.solve_batch([tr], [cfg], [(0, 0, MC), (0, 0, MT)], ctx=ctx)
+    monkeypatch.delenv("RL_FORCE_CHAIN")
+    for st, r in zip((MC, MT), res):
+        o = oracle_ref(st, tr, cfg.to_params())
+        assert_result_close(r, o, "o_", st == MT, tag=("tiled", n, m, st))
+        assert r.stats.accepted == o["stats"].accepted
+        if not stalled(o["stats"]):
+            assert r.stats.backtracks == o["stats"].backtracks

@@ -159,3 +159,27 @@ def test_rings_larger_than_one_tile(ctx, n, m, monkeypatch):
         assert r.stats.accepted == o["stats"].accepted
         if not stalled(o["stats"]):
             assert r.stats.backtracks == o["stats"].backtracks
+
+
+@pytest.mark.parametrize("cs", [0, 2])
+def test_negative_guard_disables_parity_shortcut(ctx, cs, monkeypatch):
+    """veh_width/2 + safety_margin < 0 lets the path cross a ring, so 'inside a closed ring => every ray hits it' may not
+    be used (parity_ok); results still follow the reference"""
+    n = 1100 if cs else 600
+    center, seg, L, m = rl.synth_tracks(1, n, seed_base=0xC4F6 + n)
+    seg = seg.reshape(2, m, 4)
+    tr = rl.Track(center.reshape(n, 2), seg[0], seg[1], L[0])
+    cfg = rl.Config(safety_margin_m=-0.9, max_outer_iters=6)
+    if cs:
+        monkeypatch.setenv("RL_FORCE_CLUSTER", str(cs))
+    monkeypatch.setenv("RL_FORCE_CHAIN", "2")
+    res = rl.solve_batch([tr], [cfg], [(0, 0, MC), (0, 0, MT)], ctx=ctx)
+    monkeypatch.delenv("RL_FORCE_CHAIN")
+    if cs:
+        monkeypatch.delenv("RL_FORCE_CLUSTER")
+    for st, r in zip((MC, MT), res):
+        o = oracle_ref(st, tr, cfg.to_params())
+        assert_result_close(r, o, "o_", st == MT, tag=("neg guard", cs, st))
+        assert r.stats.accepted == o["stats"].accepted
+        if not stalled(o["stats"]):
+            assert r.stats.backtracks == o["stats"].backtracks

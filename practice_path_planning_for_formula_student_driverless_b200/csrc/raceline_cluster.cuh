@@ -67,18 +67,28 @@ __device__ __forceinline__ void cl_sync()
 
 // Deterministic cluster-wide sum of two values, bit-identical in every thread of every CTA.  One cluster barrier.
 // sRedPh: [kMaxCS][NW][2] doubles of the current phase.
+__device__ __forceinline__ void packed_warp_sum2(double& a, double& b, int lane)
+{
+    // one butterfly for both values (block_sum2): after the first exchange lanes 0-15 carry a, lanes 16-31 carry b
+    const bool hi_half = (lane & 16) != 0;
+    const double keep = hi_half ? b : a, send = hi_half ? a : b;
+    double v = keep + __shfl_xor_sync(kFull, send, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    a = __shfl_sync(kFull, v, 0);
+    b = __shfl_sync(kFull, v, 16);
+}
 __device__ __forceinline__ void cluster_sum2(double& a, double& b, double* sRedPh, const Clu& cl, int lane, int warp)
 {
-    a = warp_sum(a);
-    b = warp_sum(b);
+    packed_warp_sum2(a, b, lane);
     if (lane < (int)cl.CS) cl_st2(cl_map(sRedPh + 2 * ((int)cl.rank * kcNW + warp), (uint32_t)lane), a, b);
     cl_sync();
     const int ne = (int)cl.CS * kcNW;   // <= 64 pairs
     double sa = 0.0, sb = 0.0;
     if (lane < ne) { const double2 e = *reinterpret_cast<const double2*>(sRedPh + 2 * lane); sa = e.x; sb = e.y; }
     if (lane + 32 < ne) { const double2 e = *reinterpret_cast<const double2*>(sRedPh + 2 * (lane + 32)); sa += e.x; sb += e.y; }
-    a = warp_sum(sa);   // xor butterfly: every lane ends with the same bits
-    b = warp_sum(sb);
+    packed_warp_sum2(sa, sb, lane);   // every lane of every warp of every CTA ends with the same bits
+    a = sa; b = sb;
 }
 
 // cluster-wide OR.  sFlag: int[3] rotating slots (all zero at kernel start); slot advances per call.

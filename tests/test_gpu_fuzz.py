@@ -66,3 +66,30 @@ def test_random_long_tracks_on_the_cluster_path(ctx, block, monkeypatch):
         assert r.stats.accepted == o["stats"].accepted, (block, t, st)
         if not stalled(o["stats"]):
             assert r.stats.backtracks == o["stats"].backtracks, (block, t, st)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("RL_FUZZ_OPEN") != "1", reason="not yet run on a GPU (pool busy when it was written)")
+def test_random_open_tracks(ctx, monkeypatch):
+    """open paths: random arcs of random synthetic tracks with polyline rings, chained"""
+    rng = np.random.default_rng(0xF0D3)
+    tracks, cfgs, jobs = [], [], []
+    for t in range(10):
+        nn = int(rng.integers(60, 900))
+        n = int(rng.integers(20, nn - 8))
+        center, seg, L, m = rl.synth_tracks(1, nn, seed_base=int(rng.integers(1, 1 << 30)))
+        center, seg = center.reshape(nn, 2), seg.reshape(2, m, 4)
+        keep = max(3, int(m * n / nn))
+        tracks.append(rl.Track(center[:n], rl.polyline_edges(seg[0, :keep + 2, :2]), rl.polyline_edges(seg[1, :keep + 2, :2]),
+                               L[0] * n / nn, closed=False))
+        cfgs.append(rl.Config(lambda_smooth=float(10 ** rng.uniform(-3.4, -2.2)), safety_margin_m=float(rng.uniform(0.0, 0.3)),
+                              w_time_gain=float(rng.uniform(0.0, 2.5)), max_outer_iters=int(rng.integers(3, 15))))
+        jobs += [(t, t, MC), (t, t, MT)]
+    monkeypatch.setenv("RL_FORCE_CHAIN", "2")
+    res = rl.solve_batch(tracks, cfgs, jobs, ctx=ctx)
+    monkeypatch.delenv("RL_FORCE_CHAIN")
+    for (t, c, st), r in zip(jobs, res):
+        o = oracle_ref(st, tracks[t], cfgs[c].to_params())
+        assert_result_close(r, o, "o_", st == MT, tag=("fuzz open", t, st))
+        assert r.stats.accepted == o["stats"].accepted, (t, st)
+        if not stalled(o["stats"]):
+            assert r.stats.backtracks == o["stats"].backtracks, (t, st)

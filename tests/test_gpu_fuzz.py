@@ -68,7 +68,6 @@ def test_random_long_tracks_on_the_cluster_path(ctx, block, monkeypatch):
             assert r.stats.backtracks == o["stats"].backtracks, (block, t, st)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("RL_FUZZ_OPEN") != "1", reason="not yet run on a GPU (pool busy when it was written)")
 def test_random_open_tracks(ctx, monkeypatch):
     """open paths: random arcs of random synthetic tracks with polyline rings, chained"""
     rng = np.random.default_rng(0xF0D3)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 1
+#define RL_ABI_VERSION 2
 
 /* job stages (one solve of the BASELINE metric = one MINCURV job + one MINTIME job) */
 #define RL_STAGE_MINCURV 1 /* compute_min_curvature_raceline, main.cpp:683 */
@@ -171,11 +171,25 @@ const char* rl_status_string(int status);
 int rl_device_count(void);
 /* cfg::Config defaults for the fields above (main.cpp:77-113) */
 int rl_default_params(rl_params* p);
-/* one context per device (and per host thread); replaces the process-global cfg::get() (main.cpp:120) */
+/*
+ * One context per device; replaces the process-global cfg::get() (main.cpp:120).
+ * Threading contract: every entry point that takes a context (or a batch made from it) is internally serialised by a
+ * lock inside the context, so host threads MAY share one; calls then run one after the other.  For concurrent solves
+ * use one context per thread (contexts share nothing).  A batch may be destroyed after its context.
+ */
 rl_ctx* rl_create(int device, int* status);
 void rl_destroy(rl_ctx* ctx);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream */
 int rl_set_stream(rl_ctx* ctx, void* cuda_stream);
+/*
+ * Tuning knobs and test hooks of the host plan (0 = automatic):
+ *   "solve_chunks"  pipeline chunks of rl_solve_batch (1..16)
+ *   "max_chain"     longest chain of consecutive jobs on one track that one CTA / cluster works through
+ *   "force_chain"   form chains of exactly this length whatever the batch size (tests)
+ *   "force_cluster" route closed tracks of any length through the cluster kernel with this many CTAs (tests)
+ * Unknown names return RL_ERR_ARG.  The library reads no environment variables.
+ */
+int rl_set_option(rl_ctx* ctx, const char* name, int64_t value);
 const char* rl_last_error(rl_ctx* ctx);
 
 /* page-locked host memory for asynchronous copies (cudaHostAlloc / cudaFreeHost) */
@@ -192,10 +206,17 @@ int rl_solve_batch(rl_ctx* ctx, const rl_batch_desc* desc, const rl_batch_out* o
 
 /* device-resident form: upload once, solve many times, download on demand */
 rl_batch* rl_batch_create(rl_ctx* ctx, const rl_batch_desc* desc, int* status);
-int rl_batch_upload(rl_batch* b, const rl_batch_desc* desc);   /* async H2D of the same shapes   */
+/* async H2D of new VALUES for the shapes the batch was created with: per-track sample / segment counts, closed flags
+ * and every job's (track, stage) must equal those given to rl_batch_create (RL_ERR_ARG otherwise; the plan -- size
+ * classes, output rows, chains -- is frozen at creation); coordinates, L, params and job.param may change */
+int rl_batch_upload(rl_batch* b, const rl_batch_desc* desc);
 int rl_batch_solve(rl_batch* b);                               /* async kernel launches          */
 int rl_batch_download(rl_batch* b, const rl_batch_out* out);   /* async D2H                      */
 int rl_batch_sync(rl_batch* b);                                /* wait; returns first CUDA error */
+/* DEVICE pointers of the batch's output arrays (same layout as rl_batch_out, rows in job order), for device-side
+ * consumers: the final gather of lap times and rasters over NCCL / peer copies reads them in place.  Valid until
+ * the batch is destroyed; written by rl_batch_solve on the context's stream. */
+int rl_batch_device_outputs(rl_batch* b, rl_batch_out* device_pointers);
 int rl_batch_launches_per_solve(const rl_batch* b);            /* kernels one rl_batch_solve launches */
 void rl_batch_destroy(rl_batch* b);
 

@@ -58,19 +58,22 @@ inline rl_params params_from_config(const Cfg& C, double veh_width)
     return p;
 }
 
-// one context per process and device, created on first use (replaces the global cfg::get() coupling, main.cpp:120)
+// One context per process, created on first use (replaces the global cfg::get() coupling, main.cpp:120).  The
+// function-local static is initialised exactly once even when several threads arrive together (C++11), and the C ABI
+// serialises the calls threads make through the shared context (see the threading contract in raceline_b200.h).
 inline rl_ctx* context(int device = 0)
 {
     struct Holder {
         rl_ctx* h = nullptr;
+        explicit Holder(int dev)
+        {
+            int st = RL_OK;
+            h = rl_create(dev, &st);
+            if (!h) throw std::runtime_error(std::string("raceline_b200: rl_create failed: ") + rl_status_string(st));
+        }
         ~Holder() { if (h) rl_destroy(h); }
     };
-    static Holder holder;
-    if (!holder.h) {
-        int st = RL_OK;
-        holder.h = rl_create(device, &st);
-        if (!holder.h) throw std::runtime_error(std::string("raceline_b200: rl_create failed: ") + rl_status_string(st));
-    }
+    static Holder holder(device);   // a throwing constructor leaves it uninitialised: the next call tries again
     return holder.h;
 }
 

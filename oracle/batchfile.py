@@ -12,6 +12,7 @@ import numpy as np
 MAGIC_G = 0x31474C52
 MAGIC_B = 0x31424C52
 MAGIC_R = 0x31524C52
+MAGIC_R2 = 0x32524C52   # RLR1 + per-job backtracks as logged by the reference ("[PG] .. bt=", main.cpp:1019-1022)
 
 # rl_params field order (include/raceline_b200.h); ints are stored as doubles in RLB1
 PARAM_FIELDS = [
@@ -85,16 +86,21 @@ def read_rlr1(path):
     """Return a list of per-job dicts from a `ref_harness solve` result file."""
     raw = np.fromfile(path, dtype=np.uint8)
     hdr = raw[:16].view(np.int64)
-    assert hdr[0] == MAGIC_R, "not an RLR1 file"
+    assert hdr[0] in (MAGIC_R, MAGIC_R2), "not an RLR1/RLR2 file"
+    v2 = hdr[0] == MAGIC_R2
     pos = 16
     out = []
     for _ in range(int(hdr[1])):
         n, stage = (int(x) for x in raw[pos:pos + 16].view(np.int64))
         ms, lap = (float(x) for x in raw[pos + 16:pos + 32].view(np.float64))
         pos += 32
+        bt = -1
+        if v2:
+            bt = int(raw[pos:pos + 8].view(np.int64)[0])
+            pos += 8
         body = raw[pos:pos + 8 * 8 * n].view(np.float64)
         pos += 8 * 8 * n
-        r = {"n": n, "stage": stage, "wall_ms": ms, "lap_time": lap, "xy": body[:2 * n].reshape(n, 2).copy()}
+        r = {"n": n, "stage": stage, "wall_ms": ms, "lap_time": lap, "backtracks": bt, "xy": body[:2 * n].reshape(n, 2).copy()}
         for i, k in enumerate(("heading", "curvature", "alpha_total", "alpha_last", "v", "ax")):
             r[k] = body[(2 + i) * n:(3 + i) * n].copy()
         out.append(r)

@@ -25,9 +25,34 @@ _LIB = None
 def build(force=False):
     """Compile liboracle.so (and the _ref/ binaries when /root/reference is present)."""
     so = os.path.join(_HERE, "liboracle.so")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("raceline_oracle.c", "geom_oracle.c", "raceline_oracle.h")):
+    syn = os.path.join(_HERE, "libsynth_tracks.so")
+    if force or not os.path.exists(so) or not os.path.exists(syn) or os.path.getmtime(so) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("raceline_oracle.c", "geom_oracle.c", "raceline_oracle.h")):
         subprocess.run(["make", "-C", _HERE, "port"], check=True, capture_output=True)
     return so
+
+
+_SYNTH = None
+
+
+def synth_tracks(n_tracks, n_samples, m_per_ring, seed_base=0xB200, first_id=0, threads=0):
+    """The bench workload generator (csrc/synth_tracks.cpp) through oracle/libsynth_tracks.so: the reference arm of
+    bench.py makes its inputs without loading the CUDA library.  Returns (center_xy, seg, L)."""
+    global _SYNTH
+    if _SYNTH is None:
+        build()
+        _SYNTH = C.CDLL(os.path.join(_HERE, "libsynth_tracks.so"))
+        dp = C.POINTER(C.c_double)
+        _SYNTH.rl_synth_tracks.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp]
+        _SYNTH.rl_synth_tracks.restype = C.c_int
+    center = np.empty((n_tracks * n_samples, 2))
+    seg = np.empty((n_tracks * 2 * m_per_ring, 4))
+    L = np.empty(n_tracks)
+    dp = C.POINTER(C.c_double)
+    rc = _SYNTH.rl_synth_tracks(C.c_uint64(seed_base), C.c_int64(first_id), n_tracks, n_samples, m_per_ring, threads,
+                                center.ctypes.data_as(dp), seg.ctypes.data_as(dp), L.ctypes.data_as(dp))
+    if rc != 0:
+        raise RuntimeError(f"rl_synth_tracks failed ({rc})")
+    return center, seg, L
 
 
 def build_ref():

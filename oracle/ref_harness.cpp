@@ -45,6 +45,37 @@ namespace {
 
 struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
 
+// Discards the reference's stderr chatter but keeps count of the Armijo backtracks it reports: the "bt=<int>" field of
+// every "[PG]" line (min-time, main.cpp:1019-1022) and the third integer of "[MCBT] outer it bt" lines (instrumented
+// build only).  Cheaper than accumulating the log: one short line buffer.
+struct BtCountBuf : std::streambuf {
+    std::string line;
+    long long bt = 0, lines = 0;
+    void reset() { line.clear(); bt = 0; lines = 0; }
+    void end_line()
+    {
+        if (line.find("[PG]") != std::string::npos) {
+            const size_t q = line.rfind("bt=");
+            if (q != std::string::npos) { bt += std::atoll(line.c_str() + q + 3); ++lines; }
+        } else {
+            const size_t p = line.find("[MCBT]");
+            long long o, it, b;
+            if (p != std::string::npos && std::sscanf(line.c_str() + p + 6, "%lld %lld %lld", &o, &it, &b) == 3) { bt += b; ++lines; }
+        }
+        line.clear();
+    }
+    int overflow(int c) override
+    {
+        if (c == '\n') end_line(); else if (c != EOF && line.size() < 512) line.push_back((char)c);
+        return c;
+    }
+    std::streamsize xsputn(const char* s, std::streamsize n) override
+    {
+        for (std::streamsize i = 0; i < n; ++i) overflow((unsigned char)s[i]);
+        return n;
+    }
+};
+
 void put_i64(FILE* f, int64_t v) { fwrite(&v, 8, 1, f); }
 void put_f64(FILE* f, double v) { fwrite(&v, 8, 1, f); }
 void put_vec(FILE* f, const std::vector<double>& v) { if (!v.empty()) fwrite(v.data(), 8, v.size(), f); }
@@ -364,11 +395,11 @@ int run_solve(int argc, char** argv)
 
     auto& C = cfg::get();
     C.verbose = false; C.debug_dump = false;
-    NullBuf nb; std::streambuf* old = std::cerr.rdbuf(&nb);
+    BtCountBuf nb; std::streambuf* old = std::cerr.rdbuf(&nb);
 
     FILE* o = std::fopen(argv[3], "wb");
     if (!o) { std::cerr.rdbuf(old); std::perror("out"); return 1; }
-    put_i64(o, 0x31524C52);  // "RLR1"
+    put_i64(o, 0x32524C52);  // "RLR2": RLR1 + the backtracks the reference logged for the job (-1: it logged none)
     put_i64(o, count);
     double total_ms = 0;
     for (int64_t j = first; j < first + count; ++j) {
@@ -387,6 +418,7 @@ int run_solve(int argc, char** argv)
         auto outerE = mk(seg_off[2 * t + 1], seg_off[2 * t + 2]);
         const bool cl = closed[t] != 0;
         std::vector<geom::Vec2> rl; std::vector<double> hd, kp, at, al, v, ax; double lap = 0;
+        nb.reset();
         auto t0 = std::chrono::steady_clock::now();
         if (stage == 1) {
             auto r = raceline_min_curv::compute_min_curvature_raceline(center, innerE, outerE, p[P_VEH_ARG], track_L[t], cl);
@@ -399,7 +431,7 @@ int run_solve(int argc, char** argv)
         }
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         total_ms += ms;
-        put_i64(o, n); put_i64(o, stage); put_f64(o, ms); put_f64(o, lap);
+        put_i64(o, n); put_i64(o, stage); put_f64(o, ms); put_f64(o, lap); put_i64(o, nb.lines > 0 ? nb.bt : -1);
         put_pts(o, rl); put_vec(o, hd); put_vec(o, kp); put_vec(o, at); put_vec(o, al); put_vec(o, v); put_vec(o, ax);
     }
     std::fclose(o);

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-RL_ABI_VERSION = 1
+RL_ABI_VERSION = 2
 RL_STAGE_MINCURV = 1  # compute_min_curvature_raceline, reference src/main.cpp:683
 RL_STAGE_MINTIME = 2  # compute_min_time_raceline, reference src/main.cpp:905
 RL_STAGE_EVAL = 3  # profile of a given path: heading/curvature + v(s) + lap (the debug block's laps, src/main.cpp:1464-1477)

@@ -10,14 +10,15 @@ import os
 from ._abi import RlBatchDesc, RlBatchOut, RlGeomDesc, RlGeomOut, RlJobStats, RlParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libraceline_b200.so")
+# RL_LIB_VARIANT selects a tuning / debug build made by `build.py --suffix` (e.g. "_dbg"); unset = the product library
+LIB_PATH = os.path.join(_HERE, "csrc", "libraceline_b200" + os.environ.get("RL_LIB_VARIANT", "") + ".so")
 _LIB = None
 
 # every symbol include/raceline_b200.h declares
 ABI_SYMBOLS = [
     "rl_abi_version", "rl_status_string", "rl_device_count", "rl_default_params", "rl_create", "rl_destroy",
-    "rl_set_stream", "rl_last_error", "rl_host_alloc", "rl_host_free", "rl_job_sample_offsets", "rl_solve_batch",
-    "rl_batch_create", "rl_batch_upload", "rl_batch_solve", "rl_batch_download", "rl_batch_sync",
+    "rl_set_stream", "rl_set_option", "rl_last_error", "rl_host_alloc", "rl_host_free", "rl_job_sample_offsets", "rl_solve_batch",
+    "rl_batch_create", "rl_batch_upload", "rl_batch_solve", "rl_batch_download", "rl_batch_sync", "rl_batch_device_outputs",
     "rl_batch_launches_per_solve", "rl_batch_destroy", "rl_compute_min_curvature_raceline",
     "rl_compute_min_time_raceline", "rl_geom_row_offsets", "rl_centerline_geom_batch", "rl_synth_tracks",
     "rl_measure_fp64_peak",
@@ -52,6 +53,8 @@ def lib():
     L.rl_destroy.restype = None
     L.rl_set_stream.argtypes = [vp, vp]
     L.rl_set_stream.restype = C.c_int
+    L.rl_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.rl_set_option.restype = C.c_int
     L.rl_last_error.argtypes = [vp]
     L.rl_last_error.restype = C.c_char_p
     L.rl_host_alloc.argtypes = [C.c_size_t]
@@ -70,6 +73,8 @@ def lib():
     L.rl_batch_solve.restype = C.c_int
     L.rl_batch_download.argtypes = [vp, C.POINTER(RlBatchOut)]
     L.rl_batch_download.restype = C.c_int
+    L.rl_batch_device_outputs.argtypes = [vp, C.POINTER(RlBatchOut)]
+    L.rl_batch_device_outputs.restype = C.c_int
     L.rl_batch_sync.argtypes = [vp]
     L.rl_batch_sync.restype = C.c_int
     L.rl_batch_launches_per_solve.argtypes = [vp]

@@ -37,21 +37,26 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every source for sm_100a and link the shared library. Returns its path."""
+def build(force=False, verbose=False, defines=(), suffix=""):
+    """Compile every source for sm_100a and link the shared library. Returns its path.
+
+    `defines` / `suffix` build a tuning or debug VARIANT next to the product library (objects and library carry the
+    suffix, e.g. libraceline_b200_dbg.so built with -DRL_DEBUG_CHECKS); the product build uses neither."""
     nvcc = _nvcc()
-    objs = [os.path.join(CSRC, os.path.splitext(src)[0] + ".o") for src in SOURCES]
+    objs = [os.path.join(CSRC, os.path.splitext(src)[0] + suffix + ".o") for src in SOURCES]
+    lib = os.path.join(CSRC, "libraceline_b200" + suffix + ".so")
+    dflags = ["-D" + d for d in defines]
 
     def compile_one(src, obj):
         sp = os.path.join(CSRC, src)
         if not (force or _stale(obj, [sp] + HEADERS)):
             return
-        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", sp, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + dflags + EXTRA_FLAGS.get(src, []) + ["-c", sp, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError(f"nvcc failed on {src}")
-        with open(os.path.join(CSRC, os.path.splitext(src)[0] + ".ptxas.log"), "w") as f:
+        with open(os.path.join(CSRC, os.path.splitext(src)[0] + suffix + ".ptxas.log"), "w") as f:
             f.write(res.stdout + res.stderr)
         if verbose:
             sys.stderr.write(f"built {obj}\n")
@@ -61,14 +66,20 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=max(1, min(len(SOURCES), os.cpu_count() or 1))) as ex:
         for fut in [ex.submit(compile_one, s, o) for s, o in zip(SOURCES, objs)]:
             fut.result()
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    if force or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--define", "-D", action="append", default=[])
+    ap.add_argument("--suffix", default="")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=True, defines=a.define, suffix=a.suffix))

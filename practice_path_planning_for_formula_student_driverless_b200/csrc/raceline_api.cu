@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -15,11 +16,17 @@
 
 using rl::DevBatch;
 
-constexpr int kMaxChunks = 4;
+constexpr int kMaxChunks = 16;
 
 struct rl_ctx {
     int device = 0;
     int n_sm = 148;
+    // every entry point that touches the context's streams, scratch batch or error string holds this lock: a context
+    // may be shared by host threads (calls are serialised); use one context per thread for concurrency
+    std::recursive_mutex mu;
+    // tuning knobs and test hooks (rl_set_option); 0 = automatic
+    int opt_solve_chunks = 0, opt_max_chain = 0, opt_force_chain = 0, opt_force_cluster = 0;
+    bool pipeline_ready = false;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;   // own_stream or the caller's
     std::string err;
@@ -80,6 +87,14 @@ struct rl_batch {
     int n_chunks = 1;
     std::vector<int> chunk_job0;                // [n_chunks+1] job ranges of the chunks
     std::vector<int> chunk_tmax;                // [n_chunks] highest track index a chunk touches
+    // what the plan was made from (rl_batch_upload must bring the same shapes, see upload_inputs)
+    std::vector<long long> plan_samp_off, plan_seg_off;
+    std::vector<int> plan_closed;
+    std::vector<rl_job> plan_jobs;
+    // row runs [first, count) of the jobs that produce v / ax (MINTIME, EVAL), merged; per chunk [vrun0[c], vrun0[c+1])
+    std::vector<std::pair<long long, long long>> vruns;
+    std::vector<int> vrun0;
+    int device = 0;
     void release()
     {
         d_samp_off.release(); d_seg_off.release(); d_job_off.release(); d_center.release(); d_seg.release();
@@ -156,15 +171,36 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
     b->n_chunks = n_chunks;
     b->chunk_job0.assign((size_t)n_chunks + 1, 0);
     b->chunk_tmax.assign((size_t)n_chunks, -1);
-    int max_chain = 8, force_chain = 0;
-    if (const char* e = std::getenv("RL_MAX_CHAIN")) max_chain = std::max(1, std::atoi(e));   // tuning knob
-    if (const char* e = std::getenv("RL_FORCE_CHAIN")) force_chain = std::max(0, std::atoi(e)); // test hook: chains of that length whatever the batch size
-    for (int c = 0; c <= n_chunks; ++c) b->chunk_job0[c] = (int)(((long long)d->n_jobs * c) / n_chunks);
+    const int max_chain = c->opt_max_chain > 0 ? c->opt_max_chain : 8;   // rl_set_option("max_chain")
+    const int force_chain = std::max(0, c->opt_force_chain);             // test hook: chains of that length whatever the batch size
+    for (int c = 0; c <= n_chunks; ++c) {
+        // a chunk boundary never separates the jobs of one track (they form a chain and share the track's upload)
+        int j = (int)(((long long)d->n_jobs * c) / n_chunks);
+        if (c > 0 && c < n_chunks) {
+            j = std::max(j, b->chunk_job0[c - 1]);
+            for (int moved = 0; moved < max_chain && j > b->chunk_job0[c - 1] && j < d->n_jobs && d->jobs[j].track == d->jobs[j - 1].track; ++moved) ++j;
+        }
+        b->chunk_job0[c] = j;
+    }
+    b->plan_samp_off.assign(d->samp_off, d->samp_off + d->n_tracks + 1);
+    b->plan_seg_off.assign(d->seg_off, d->seg_off + 2 * d->n_tracks + 1);
+    b->plan_closed.assign(d->track_closed, d->track_closed + d->n_tracks);
+    b->plan_jobs.assign(d->jobs, d->jobs + d->n_jobs);
+    b->vruns.clear(); b->vrun0.assign((size_t)n_chunks + 1, 0);
+    for (int c = 0; c < n_chunks; ++c) {
+        b->vrun0[c] = (int)b->vruns.size();
+        for (int j = b->chunk_job0[c]; j < b->chunk_job0[c + 1]; ++j) {
+            if (d->jobs[j].stage == RL_STAGE_MINCURV || b->job_off[j + 1] == b->job_off[j]) continue;
+            if ((int)b->vruns.size() > b->vrun0[c] && b->vruns.back().first + b->vruns.back().second == b->job_off[j])
+                b->vruns.back().second += b->job_off[j + 1] - b->job_off[j];
+            else b->vruns.push_back({b->job_off[j], b->job_off[j + 1] - b->job_off[j]});
+        }
+    }
+    b->vrun0[n_chunks] = (int)b->vruns.size();
     for (int c = 0; c < n_chunks; ++c) {
         std::vector<std::vector<int>> bucket(rl::kNumClasses * 3);
         std::vector<std::vector<int>> cbucket(2 * (rl::kMaxClusterSize + 1));   // [cs][mode] cluster launches
-        int force_cs = 0;
-        if (const char* e = std::getenv("RL_FORCE_CLUSTER")) force_cs = std::atoi(e);   // test hook: cluster kernel on shorter tracks
+        const int force_cs = b->ctx->opt_force_cluster;   // test hook: cluster kernel on shorter tracks
         for (int j = b->chunk_job0[c]; j < b->chunk_job0[c + 1]; ++j) {
             const rl_job& jb = d->jobs[j];
             const int t = jb.track;
@@ -182,7 +218,11 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
         for (int k = 0; k < rl::kNumClasses * 3; ++k) {
             if (bucket[k].empty()) continue;
             const int slots = std::max(1, c_sm(b) * rl::ctas_per_sm(k / 3));
-            const int chain = force_chain > 0 ? force_chain : std::max(1, std::min(max_chain, (int)(bucket[k].size() / (size_t)(6 * slots))));
+            // a chain saves every job after the first the corridor search of its first build: worth more than the
+            // load balance of the tail as soon as the items still fill the device twice
+            int chain = std::max(1, std::min(max_chain, (int)(bucket[k].size() / (size_t)(6 * slots))));
+            if (chain < 2 && bucket[k].size() >= (size_t)(4 * slots)) chain = std::min(2, max_chain);
+            if (force_chain > 0) chain = force_chain;
             ClassList l = {k / 3, k % 3, (int)b->joblist.size(), (int)bucket[k].size(), c, (int)b->itemoff.size(), 0};
             int run = 0, last_t = -1;
             for (size_t q = 0; q < bucket[k].size(); ++q) {
@@ -199,7 +239,9 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
             if (cbucket[k].empty()) continue;
             const int cs = (int)(k / 2);
             const int slots = std::max(1, (c_sm(b) * 2) / cs);      // two CTAs per SM, cs CTAs per cluster
-            const int chain = force_chain > 0 ? force_chain : std::max(1, std::min(max_chain, (int)(cbucket[k].size() / (size_t)(6 * slots))));
+            int chain = std::max(1, std::min(max_chain, (int)(cbucket[k].size() / (size_t)(6 * slots))));
+            if (chain < 2 && cbucket[k].size() >= (size_t)(4 * slots)) chain = std::min(2, max_chain);
+            if (force_chain > 0) chain = force_chain;
             ClassList l = {rl::kClusterClassBase + cs, (int)(k % 2), (int)b->joblist.size(), (int)cbucket[k].size(), c, (int)b->itemoff.size(), 0};
             int run = 0, last_t = -1;
             for (size_t q = 0; q < cbucket[k].size(); ++q) {
@@ -256,10 +298,22 @@ int upload_inputs(rl_batch* b, const rl_batch_desc* d)
 {
     rl_ctx* c = b->ctx;
     cudaStream_t s = c->stream;
-    if (d->n_tracks != b->n_tracks || d->n_params != b->n_params || d->n_jobs != b->n_jobs ||
-        (d->n_tracks && (d->samp_off[d->n_tracks] != b->total_samples || d->seg_off[2 * d->n_tracks] != b->total_segs)))
-        return fail(c, RL_ERR_ARG, "rl_batch_upload: shapes differ from rl_batch_create");
+    // The host plan (size class and mode of every job, output row offsets, chains) was frozen by rl_batch_create and the
+    // kernels size their shared-memory use by it: the descriptor must describe the SAME shapes -- per-track sample and
+    // segment counts, closed flags, and the (track, stage) of every job.  Values (coordinates, L, params, and which
+    // params a job uses) may change.
+    if (d->n_tracks != b->n_tracks || d->n_params != b->n_params || d->n_jobs != b->n_jobs)
+        return fail(c, RL_ERR_ARG, "rl_batch_upload: counts differ from rl_batch_create");
     if (d->n_jobs == 0) return RL_OK;
+    if (std::memcmp(d->samp_off, b->plan_samp_off.data(), sizeof(long long) * ((size_t)d->n_tracks + 1)) != 0 ||
+        std::memcmp(d->seg_off, b->plan_seg_off.data(), sizeof(long long) * ((size_t)2 * d->n_tracks + 1)) != 0)
+        return fail(c, RL_ERR_ARG, "rl_batch_upload: per-track sample / segment counts differ from rl_batch_create");
+    for (int t = 0; t < d->n_tracks; ++t)
+        if ((d->track_closed[t] != 0) != (b->plan_closed[t] != 0))
+            return fail(c, RL_ERR_ARG, "rl_batch_upload: track_closed differs from rl_batch_create");
+    for (int j = 0; j < d->n_jobs; ++j)
+        if (d->jobs[j].track != b->plan_jobs[j].track || d->jobs[j].stage != b->plan_jobs[j].stage)
+            return fail(c, RL_ERR_ARG, "rl_batch_upload: a job's track or stage differs from rl_batch_create");
     RL_CUDA(c, cudaMemcpyAsync(b->d_samp_off.p, d->samp_off, sizeof(long long) * ((size_t)d->n_tracks + 1), cudaMemcpyHostToDevice, s));
     RL_CUDA(c, cudaMemcpyAsync(b->d_seg_off.p, d->seg_off, sizeof(long long) * ((size_t)2 * d->n_tracks + 1), cudaMemcpyHostToDevice, s));
     if (b->total_samples)
@@ -298,6 +352,28 @@ struct DevFree {
 };
 
 static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+
+// D2H of the v / ax rows of chunk `k` (all chunks: k < 0): only the rows of jobs that produce them (MINTIME, EVAL) --
+// the rows of MINCURV jobs are left untouched, as include/raceline_b200.h promises.  Equally long, equally spaced runs
+// (the usual min-curv / min-time interleave of equally long tracks) travel as ONE strided copy.
+int copy_v_rows(rl_ctx* c, const rl_batch* b, int k, double* dst, const double* src, cudaStream_t s)
+{
+    const int r0 = k < 0 ? 0 : b->vrun0[k], r1 = k < 0 ? (int)b->vruns.size() : b->vrun0[k + 1];
+    if (r1 <= r0) return RL_OK;
+    const auto* R = b->vruns.data();
+    bool periodic = (r1 - r0 >= 3);
+    const long long pitch = periodic ? R[r0 + 1].first - R[r0].first : 0;
+    for (int r = r0; periodic && r < r1; ++r)
+        periodic = (R[r].second == R[r0].second) && (R[r].first == R[r0].first + (long long)(r - r0) * pitch);
+    if (periodic) {
+        RL_CUDA(c, cudaMemcpy2DAsync(dst + R[r0].first, (size_t)pitch * 8, src + R[r0].first, (size_t)pitch * 8, (size_t)R[r0].second * 8,
+                                     (size_t)(r1 - r0), cudaMemcpyDeviceToHost, s));
+        return RL_OK;
+    }
+    for (int r = r0; r < r1; ++r)
+        RL_CUDA(c, cudaMemcpyAsync(dst + R[r].first, src + R[r].first, (size_t)R[r].second * 8, cudaMemcpyDeviceToHost, s));
+    return RL_OK;
+}
 
 }  // namespace
 
@@ -375,12 +451,16 @@ void rl_destroy(rl_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->scratch) { rl_batch_destroy(c->scratch); c->scratch = nullptr; }
-    if (c->s_in) {
-        cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
-        cudaEventDestroy(c->ev_start);
-        for (int i = 0; i < kMaxChunks; ++i) { cudaStreamDestroy(c->s_k[i]); cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_k[i]); }
-        for (int i = 0; i < kMaxChunks + 2; ++i) cudaEventDestroy(c->ev_end[i]);
+    // whatever ensure_pipeline managed to create (it may have stopped half way)
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    for (int i = 0; i < kMaxChunks; ++i) {
+        if (c->s_k[i]) cudaStreamDestroy(c->s_k[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     }
+    for (int i = 0; i < kMaxChunks + 2; ++i) if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -389,7 +469,21 @@ void rl_destroy(rl_ctx* c)
 int rl_set_stream(rl_ctx* c, void* cuda_stream)
 {
     if (!c) return RL_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return RL_OK;
+}
+
+int rl_set_option(rl_ctx* c, const char* name, int64_t value)
+{
+    if (!c || !name) return RL_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    const int v = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
+    if (!std::strcmp(name, "solve_chunks")) c->opt_solve_chunks = std::min(v, kMaxChunks);
+    else if (!std::strcmp(name, "max_chain")) c->opt_max_chain = v;
+    else if (!std::strcmp(name, "force_chain")) c->opt_force_chain = v;
+    else if (!std::strcmp(name, "force_cluster")) c->opt_force_cluster = v;
+    else return fail(c, RL_ERR_ARG, std::string("rl_set_option: unknown option ") + name);
     return RL_OK;
 }
 
@@ -419,13 +513,16 @@ rl_batch* rl_batch_create(rl_ctx* c, const rl_batch_desc* d, int* status)
 {
     int st = c ? validate_desc(c, d) : RL_ERR_ARG;
     rl_batch* b = nullptr;
+    std::unique_lock<std::recursive_mutex> lk;
+    if (c) lk = std::unique_lock<std::recursive_mutex>(c->mu);
+    if (st == RL_OK && cudaSetDevice(c->device) != cudaSuccess) st = RL_ERR_CUDA;
     if (st == RL_OK) {
-        cudaSetDevice(c->device);
         b = new (std::nothrow) rl_batch();
         if (!b) st = RL_ERR_NOMEM;
     }
     if (st == RL_OK) {
         b->ctx = c;
+        b->device = c->device;
         st = plan_batch(b, d);
         if (st == RL_OK) st = upload_inputs(b, d);
         if (st == RL_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = RL_ERR_CUDA;
@@ -438,7 +535,10 @@ rl_batch* rl_batch_create(rl_ctx* c, const rl_batch_desc* d, int* status)
 int rl_batch_upload(rl_batch* b, const rl_batch_desc* d)
 {
     if (!b || !d) return RL_ERR_ARG;
-    cudaSetDevice(b->ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(b->ctx->mu);
+    const int st = validate_desc(b->ctx, d);
+    if (st != RL_OK) return st;
+    RL_CUDA(b->ctx, cudaSetDevice(b->device));
     return upload_inputs(b, d);
 }
 
@@ -446,7 +546,8 @@ int rl_batch_solve(rl_batch* b)
 {
     if (!b) return RL_ERR_ARG;
     rl_ctx* c = b->ctx;
-    cudaSetDevice(c->device);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    RL_CUDA(c, cudaSetDevice(c->device));
     const DevBatch B = dev_view(b);
     for (const ClassList& l : b->lists) {
         const int e = rl::launch_solve(B, b->d_joblist.p + l.begin, l.count, b->d_itemoff.p + l.item_begin, l.n_items, l.cls, l.mode, c->stream);
@@ -461,7 +562,8 @@ int rl_batch_download(rl_batch* b, const rl_batch_out* o)
 {
     if (!b || !o) return RL_ERR_ARG;
     rl_ctx* c = b->ctx;
-    cudaSetDevice(c->device);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    RL_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const size_t rows = (size_t)b->rows;
     if (rows) {
@@ -470,18 +572,27 @@ int rl_batch_download(rl_batch* b, const rl_batch_out* o)
         if (o->curvature) RL_CUDA(c, cudaMemcpyAsync(o->curvature, b->d_curv.p, 8 * rows, cudaMemcpyDeviceToHost, s));
         if (o->alpha_total) RL_CUDA(c, cudaMemcpyAsync(o->alpha_total, b->d_atot.p, 8 * rows, cudaMemcpyDeviceToHost, s));
         if (o->alpha_last) RL_CUDA(c, cudaMemcpyAsync(o->alpha_last, b->d_alast.p, 8 * rows, cudaMemcpyDeviceToHost, s));
-        if (o->v) RL_CUDA(c, cudaMemcpyAsync(o->v, b->d_v.p, 8 * rows, cudaMemcpyDeviceToHost, s));
-        if (o->ax) RL_CUDA(c, cudaMemcpyAsync(o->ax, b->d_ax.p, 8 * rows, cudaMemcpyDeviceToHost, s));
+        if (o->v) { const int st = copy_v_rows(c, b, -1, o->v, b->d_v.p, s); if (st != RL_OK) return st; }
+        if (o->ax) { const int st = copy_v_rows(c, b, -1, o->ax, b->d_ax.p, s); if (st != RL_OK) return st; }
     }
     if (o->stats && b->n_jobs)
         RL_CUDA(c, cudaMemcpyAsync(o->stats, b->d_stats.p, sizeof(rl_job_stats) * (size_t)b->n_jobs, cudaMemcpyDeviceToHost, s));
     return RL_OK;
 }
 
+int rl_batch_device_outputs(rl_batch* b, rl_batch_out* dev)
+{
+    if (!b || !dev) return RL_ERR_ARG;
+    dev->xy = b->d_xy.p; dev->heading = b->d_heading.p; dev->curvature = b->d_curv.p; dev->alpha_total = b->d_atot.p;
+    dev->alpha_last = b->d_alast.p; dev->v = b->d_v.p; dev->ax = b->d_ax.p; dev->stats = b->d_stats.p;
+    return RL_OK;
+}
+
 int rl_batch_sync(rl_batch* b)
 {
     if (!b) return RL_ERR_ARG;
-    cudaSetDevice(b->ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(b->ctx->mu);
+    RL_CUDA(b->ctx, cudaSetDevice(b->device));
     RL_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream));
     RL_CUDA(b->ctx, cudaGetLastError());
     return RL_OK;
@@ -490,14 +601,15 @@ int rl_batch_sync(rl_batch* b)
 void rl_batch_destroy(rl_batch* b)
 {
     if (!b) return;
-    cudaSetDevice(b->ctx->device);
+    cudaSetDevice(b->device);   // the batch remembers its device: destroying it after its context is legal
     b->release();
     delete b;
 }
 
 static int ensure_pipeline(rl_ctx* c)
 {
-    if (c->s_in) return RL_OK;
+    if (c->pipeline_ready) return RL_OK;
+    if (c->s_in) return fail(c, RL_ERR_CUDA, "the copy/compute pipeline of this context could not be created earlier");
     RL_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     RL_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     int lo_p = 0, hi_p = 0;   // numerically lowest value = highest priority
@@ -511,32 +623,56 @@ static int ensure_pipeline(rl_ctx* c)
         RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < kMaxChunks + 2; ++i) RL_CUDA(c, cudaEventCreateWithFlags(&c->ev_end[i], cudaEventDisableTiming));
+    c->pipeline_ready = true;   // only now: a half-built pipeline is never used (rl_destroy frees what exists)
     return RL_OK;
 }
 
 // Host buffers in, host buffers out.  The batch is cut into up to kMaxChunks job ranges; chunk k's inputs go up
 // while chunk k-1 computes and chunk k-2's results come down, all bracketed by the context's stream (so events
 // the caller records on it time the whole call).
+// everything rl_solve_batch queues after ev_start; on an error the caller drains the streams before returning
+static int solve_batch_pipeline(rl_ctx* c, rl_batch* b, const rl_batch_desc* d, const rl_batch_out* o);
+
 int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
 {
     if (!c || !o) return RL_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     int st = validate_desc(c, d);
     if (st != RL_OK) return st;
     if (d->n_jobs == 0) return RL_OK;
-    cudaSetDevice(c->device);
+    RL_CUDA(c, cudaSetDevice(c->device));
     if (!c->scratch) {
         c->scratch = new (std::nothrow) rl_batch();
         if (!c->scratch) return fail(c, RL_ERR_NOMEM, "host allocation failed");
         c->scratch->ctx = c;
+        c->scratch->device = c->device;
     }
     rl_batch* b = c->scratch;
     st = ensure_pipeline(c);
     if (st != RL_OK) return st;
-    int want_chunks = std::max(1, std::min(c->n_prio, d->n_jobs / 1024));
-    if (const char* e = std::getenv("RL_SOLVE_CHUNKS")) want_chunks = std::max(1, std::min(kMaxChunks, std::atoi(e)));   // tuning knob
+    // chunks of at least ~2 device fills of chained items each (one item = the jobs of one track), at most kMaxChunks
+    int want_chunks = std::max(1, std::min(kMaxChunks, d->n_jobs / 2048));
+    if (c->opt_solve_chunks > 0) want_chunks = std::min(kMaxChunks, c->opt_solve_chunks);   // rl_set_option("solve_chunks")
     // the small plan arrays travel on the context stream before the pipeline starts
     st = plan_batch(b, d, want_chunks);
-    if (st != RL_OK) return st;
+    if (st == RL_OK) st = solve_batch_pipeline(c, b, d, o);
+    if (st != RL_OK) {
+        // copies into the caller's buffers and reads of the caller's inputs may still be in flight on the pipeline
+        // streams: nothing may outlive this call
+        const std::string keep = c->err;
+        if (c->s_in) cudaStreamSynchronize(c->s_in);
+        if (c->s_out) cudaStreamSynchronize(c->s_out);
+        for (int i = 0; i < kMaxChunks; ++i) if (c->s_k[i]) cudaStreamSynchronize(c->s_k[i]);
+        cudaStreamSynchronize(c->stream);
+        cudaGetLastError();
+        c->err = keep;
+    }
+    return st;
+}
+
+static int solve_batch_pipeline(rl_ctx* c, rl_batch* b, const rl_batch_desc* d, const rl_batch_out* o)
+{
+    int st = RL_OK;
     cudaStream_t s0 = c->stream;
     RL_CUDA(c, cudaMemcpyAsync(b->d_samp_off.p, d->samp_off, sizeof(long long) * ((size_t)d->n_tracks + 1), cudaMemcpyHostToDevice, s0));
     RL_CUDA(c, cudaMemcpyAsync(b->d_seg_off.p, d->seg_off, sizeof(long long) * ((size_t)2 * d->n_tracks + 1), cudaMemcpyHostToDevice, s0));
@@ -572,7 +708,9 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
         }
         RL_CUDA(c, cudaEventRecord(c->ev_in[k], c->s_in));
         // ---- kernels ----
-        cudaStream_t sk = c->s_k[k];
+        // chunk k runs on stream k mod n_prio: within a window of n_prio chunks a later chunk has a lower priority and only
+        // fills what the earlier ones leave idle; chunk k + n_prio queues behind chunk k on the same stream
+        cudaStream_t sk = c->s_k[k % c->n_prio];
         RL_CUDA(c, cudaStreamWaitEvent(sk, c->ev_in[k], 0));
         for (; li < b->lists.size() && b->lists[li].chunk == k; ++li) {
             const ClassList& l = b->lists[li];
@@ -590,8 +728,8 @@ int rl_solve_batch(rl_ctx* c, const rl_batch_desc* d, const rl_batch_out* o)
             if (o->curvature) RL_CUDA(c, cudaMemcpyAsync(o->curvature + r0, b->d_curv.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
             if (o->alpha_total) RL_CUDA(c, cudaMemcpyAsync(o->alpha_total + r0, b->d_atot.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
             if (o->alpha_last) RL_CUDA(c, cudaMemcpyAsync(o->alpha_last + r0, b->d_alast.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
-            if (o->v) RL_CUDA(c, cudaMemcpyAsync(o->v + r0, b->d_v.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
-            if (o->ax) RL_CUDA(c, cudaMemcpyAsync(o->ax + r0, b->d_ax.p + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->v) { st = copy_v_rows(c, b, k, o->v, b->d_v.p, c->s_out); if (st != RL_OK) return st; }
+            if (o->ax) { st = copy_v_rows(c, b, k, o->ax, b->d_ax.p, c->s_out); if (st != RL_OK) return st; }
         }
         if (o->stats && j1 > j0)
             RL_CUDA(c, cudaMemcpyAsync(c->h_stats + j0, b->d_stats.p + j0, sizeof(rl_job_stats) * (size_t)(j1 - j0), cudaMemcpyDeviceToHost, c->s_out));
@@ -616,6 +754,7 @@ static int solve_single(rl_ctx* c, int stage, const double* center_xy, int n, co
                         double* v, double* ax, double* lap_time, rl_job_stats* stats)
 {
     if (!c || !p || n < 0 || m_inner < 0 || m_outer < 0) return RL_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (n > 0 && !center_xy) return RL_ERR_ARG;
     if ((m_inner > 0 && !inner_seg) || (m_outer > 0 && !outer_seg)) return RL_ERR_ARG;
     rl_job_stats local;
@@ -683,6 +822,7 @@ int rl_geom_row_offsets(const rl_geom_desc* d, int64_t* off)
 int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out* o)
 {
     if (!c || !d || !o) return RL_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (d->n_tracks < 0) return fail(c, RL_ERR_ARG, "negative track count");
     if (d->n_tracks == 0) return RL_OK;
     if (!d->mid_off || !d->mids_xy || !d->samples || !d->track_closed || !d->seg_off || !d->params)
@@ -706,7 +846,7 @@ int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out
         if (st != RL_OK) return fail(c, st, "samples must be >= 1");
         for (int t = 0; t <= nt; ++t) row_off[t] = ro[t];
     }
-    cudaSetDevice(c->device);
+    RL_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const size_t rows = (size_t)row_off[nt], n_mid = (size_t)d->mid_off[nt], n_seg = (size_t)d->seg_off[2 * nt];
     DevFree mem;
@@ -759,20 +899,29 @@ int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out
 int rl_measure_fp64_peak(rl_ctx* c, double* tflops)
 {
     if (!c || !tflops) return RL_ERR_ARG;
-    cudaSetDevice(c->device);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    RL_CUDA(c, cudaSetDevice(c->device));
     cudaDeviceProp prop;
     RL_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
     double* d = nullptr;
     RL_CUDA(c, cudaMalloc((void**)&d, sizeof(double) * (size_t)blocks * threads));
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+        if (e0) cudaEventDestroy(e0);
+        cudaFree(d);
+        return cuda_fail(c, cudaGetLastError(), "fp64 probe events");
+    }
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0, c->stream);
         const int e = rl::launch_fp64_peak(d, blocks, threads, iters, c->stream);
         cudaEventRecord(e1, c->stream);
-        if (e != 0 || cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return cuda_fail(c, cudaGetLastError(), "fp64 probe"); }
+        if (e != 0 || cudaEventSynchronize(e1) != cudaSuccess) {
+            const cudaError_t ce = e != 0 ? (cudaError_t)e : cudaGetLastError();
+            cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+            return cuda_fail(c, ce, "fp64 probe");
+        }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         const double fl = 2.0 * 8.0 * (double)iters * (double)blocks * threads;

@@ -179,7 +179,9 @@ __device__ __forceinline__ bool pgd_half_c(const Part& pt, const Clu& cl, const 
     double dec2p = 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const double xn = clamp_box(fma(-c.step2, gh[k], xa[k]), sLo[k * T], sHi[k * T]);
+        double lo, hi;
+        ld_pair<T>(sLo, sHi, k, lo, hi);
+        const double xn = clamp_box(fma(-c.step2, gh[k], xa[k]), lo, hi);
         dec2p = fma(gh[k], xn - xa[k], dec2p);
         xb[k] = xn;
     }
@@ -227,7 +229,9 @@ __device__ __forceinline__ PgdOut pgd_outer_c(const Part& pt, const Clu& cl, con
         double decp = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const double xn = clamp_box(-c.step2 * gh[k], sLo[k * T], sHi[k * T]);
+            double lo, hi;
+            ld_pair<T>(sLo, sHi, k, lo, hi);
+            const double xn = clamp_box(-c.step2 * gh[k], lo, hi);
             decp = fma(gh[k], xn, decp);
             x[k] = xn;
         }
@@ -266,7 +270,9 @@ __device__ __forceinline__ PgdOut pgd_outer_c(const Part& pt, const Clu& cl, con
             double decp = 0.0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double xn = clamp_box(fma(-c.step2, gh[k], a[k]), sLo[k * T], sHi[k * T]);
+                double lo, hi;
+                ld_pair<T>(sLo, sHi, k, lo, hi);
+                const double xn = clamp_box(fma(-c.step2, gh[k], a[k]), lo, hi);
                 decp = fma(gh[k], xn - a[k], decp);
                 x[k] = xn;
             }
@@ -978,8 +984,8 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
     }
 
     double* sC0 = sB + tid;
-    double* sCp = sB + NP + tid;
-    double* sCm = sB + 2 * NP + tid;
+    double* sCp = pair_base_a(sB + NP, NP, tid);
+    double* sCm = pair_base_b(sB + NP, NP, tid);
     double* sSt = sB + 3 * NP + tid;
 
     for (int outer = 0; outer < max_outer; ++outer) {
@@ -1004,10 +1010,10 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         block_sync<T>();
         if (tid == 0) bulk_s2g_issue(B.xy + 2 * row0, sP, (uint32_t)Nl * 16u);
         block_sync<T>();
-        double* sLo = reinterpret_cast<double*>(sP) + tid;
-        double* sHi = sLo + NP;
+        double* sLo = pair_base_a(reinterpret_cast<double*>(sP), NP, tid);
+        double* sHi = pair_base_b(reinterpret_cast<double*>(sP), NP, tid);
 #pragma unroll
-        for (int k = 0; k < K; ++k) { sLo[k * T] = lo[k]; sHi[k * T] = hi[k]; }
+        for (int k = 0; k < K; ++k) st_pair<T>(sLo, sHi, k, lo[k], hi[k]);
         double gam[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) gam[k] = 1.0;
@@ -1067,7 +1073,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
                     if (k == 0) { f0 = c0; fp = cp; fm = cm; }
                     l0 = c0; lp = cp; lm = cm;
                 }
-                sC0[k * T] = c0; sCp[k * T] = cp; sCm[k * T] = cm;
+                sC0[k * T] = c0; st_pair<T>(sCp, sCm, k, cp, cm);
             }
             if (tid == 0) {   // my first sample is the right-hand halo of CTA `left`
                 cl_st2(cl_map(sCoef + 4, cl.left), f0, fp);
@@ -1082,15 +1088,15 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         double cL[3], cR[3];
         {
             const int kl = pt.cntL - 1;
-            const double* b0 = sB + pt.tL; const double* br = sB + pt.tR;
-            cL[0] = b0[kl * T]; cL[1] = b0[NP + kl * T]; cL[2] = b0[2 * NP + kl * T];
-            cR[0] = br[0]; cR[1] = br[NP]; cR[2] = br[2 * NP];
+            cL[0] = sB[pt.tL + kl * T]; cR[0] = sB[pt.tR];
+            ld_pair<T>(pair_base_a(sB + NP, NP, pt.tL), pair_base_b(sB + NP, NP, pt.tL), kl, cL[1], cL[2]);
+            ld_pair<T>(pair_base_a(sB + NP, NP, pt.tR), pair_base_b(sB + NP, NP, pt.tR), 0, cR[1], cR[2]);
             if (tid == 0) { cL[0] = sCoef[0]; cL[1] = sCoef[1]; cL[2] = sCoef[2]; }
             if (tid == T - 1) { cR[0] = sCoef[4]; cR[1] = sCoef[5]; cR[2] = sCoef[6]; }
         }
         if (!EXACT) {
             // the first unused slot mirrors the right neighbour's first sample (position cnt+1 of the window)
-            if (cnt < K) { sC0[cnt * T] = cR[0]; sCp[cnt * T] = cR[1]; sCm[cnt * T] = cR[2]; }
+            if (cnt < K) { sC0[cnt * T] = cR[0]; st_pair<T>(sCp, sCm, cnt, cR[1], cR[2]); }
         }
         // =================== projected gradient with Armijo (main.cpp:723-742 / 996-1026) ===================
         const PgdOut po = pgd_outer_c<K, MODE>(pt, cl, sLo, sHi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,

@@ -374,6 +374,30 @@ __device__ __forceinline__ double lap_and_ax(const Part& pt, const VPar& q, cons
 // Returns gh = grad/2 and accumulates Jz = sum zhat^2, Sd = sum d^2 over the OWNED slots.
 struct Halo { double l0, l1, r0, r1; };
 
+// Shared-memory layout of two per-sample constants that are always read together -- (cp, cm) and (lo, hi) --
+// slot-major [k][t].  Packed (default): the pair shares one 16-byte slot, one LDS.128 instead of two LDS.64.
+// -DRL_NOPACK128 keeps the two planes apart (the layout of round 1, kept for A/B measurements).
+#ifdef RL_NOPACK128
+constexpr bool kPack = false;
+#else
+constexpr bool kPack = true;
+#endif
+// `region` holds 2*NP doubles; base pointers of thread t's column
+__device__ __forceinline__ double* pair_base_a(double* region, int NP, int t) { return kPack ? region + 2 * t : region + t; }
+__device__ __forceinline__ double* pair_base_b(double* region, int NP, int t) { return kPack ? region + 2 * t + 1 : region + NP + t; }
+template <int T>
+__device__ __forceinline__ void ld_pair(const double* a, const double* b, int k, double& x, double& y)
+{
+    if (kPack) { const double2 v = reinterpret_cast<const double2*>(a)[k * T]; x = v.x; y = v.y; }
+    else { x = a[k * T]; y = b[k * T]; }
+}
+template <int T>
+__device__ __forceinline__ void st_pair(double* a, double* b, int k, double x, double y)
+{
+    if (kPack) reinterpret_cast<double2*>(a)[k * T] = make_double2(x, y);
+    else { a[k * T] = x; b[k * T] = y; }
+}
+
 template <int T, int K, int MODE>
 __device__ __forceinline__ void eval_window(const double (&x)[K], const Halo& hh, const Part& pt,
                                             const double* __restrict__ sC0, const double* __restrict__ sCp,
@@ -407,7 +431,7 @@ __device__ __forceinline__ void eval_window(const double (&x)[K], const Halo& hh
         double c0, cp, cm;
         if (p == 0) { c0 = cL[0]; cp = cL[1]; cm = cL[2]; }
         else if (p == K + 1) { c0 = cR[0]; cp = cR[1]; cm = cR[2]; }
-        else { c0 = sC0[(p - 1) * T]; cp = sCp[(p - 1) * T]; cm = sCm[(p - 1) * T]; }
+        else { c0 = sC0[(p - 1) * T]; ld_pair<T>(sCp, sCm, p - 1, cp, cm); }
         const double wm = w[p], wc = w[p + 1], wp = w[p + 2];
         s[p] = cp + cm;
         z[p] = fma(cp, wp, fma(cm, wm, fma(-s[p], wc, c0)));
@@ -530,7 +554,9 @@ __device__ __forceinline__ bool pgd_half(const Part& pt, const double (&xa)[K], 
     double dec2p = 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const double xn = clamp_box(fma(-c.step2, gh[k], xa[k]), sLo[k * T], sHi[k * T]);
+        double lo, hi;
+        ld_pair<T>(sLo, sHi, k, lo, hi);
+        const double xn = clamp_box(fma(-c.step2, gh[k], xa[k]), lo, hi);
         dec2p = fma(gh[k], xn - xa[k], dec2p);
         xb[k] = xn;
     }
@@ -587,7 +613,9 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
         double decp = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const double xn = clamp_box(-c.step2 * gh[k], sLo[k * T], sHi[k * T]);
+            double lo, hi;
+            ld_pair<T>(sLo, sHi, k, lo, hi);
+            const double xn = clamp_box(-c.step2 * gh[k], lo, hi);
             decp = fma(gh[k], xn, decp);
             x[k] = xn;
         }
@@ -627,7 +655,9 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
             double decp = 0.0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double xn = clamp_box(fma(-c.step2, gh[k], a[k]), sLo[k * T], sHi[k * T]);
+                double lo, hi;
+                ld_pair<T>(sLo, sHi, k, lo, hi);
+                const double xn = clamp_box(fma(-c.step2, gh[k], a[k]), lo, hi);
                 decp = fma(gh[k], xn - a[k], decp);
                 x[k] = xn;
             }
@@ -1855,6 +1885,14 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
     return flagged;
 }
 
+// Development build only (-DRL_PHASE_TIMERS): thread 0 accumulates clock64() cycles per phase of the job in the
+// scratch area and leaves them in stats.J0[16..31] (outer iterations use entries 0..13).
+#ifdef RL_PHASE_TIMERS
+#define RL_PH(i) do { if (threadIdx.x == 0) { const long long t__ = clock64(); sPh[i] += t__ - sPh[15]; sPh[15] = t__; } } while (0)
+#else
+#define RL_PH(i) do { } while (0)
+#endif
+
 // ---- the solver kernel ------------------------------------------------------------------------------------
 template <int T, int K, int MODE>
 __global__ void __launch_bounds__(T, (4096 / (T * K)) > 16 ? 16 : ((4096 / (T * K)) < 1 ? 1 : (4096 / (T * K))))
@@ -1873,6 +1911,9 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
     int* sMisc = reinterpret_cast<int*>(scr + kScrMisc);
     unsigned* sHint = reinterpret_cast<unsigned*>(scr + kScrBytes);
     unsigned short* sClr = reinterpret_cast<unsigned short*>(scr + kScrBytes + (size_t)NP * 4);
+#ifdef RL_PHASE_TIMERS
+    long long* sPh = reinterpret_cast<long long*>(scr + kScrMisc + 128);
+#endif
 
     // One CTA works through one ITEM = a short chain of jobs on the SAME track (typically its min-curvature and its
     // min-time stage, or neighbouring Configs of a sweep).  Everything the corridor code learns about the track --
@@ -1918,6 +1959,9 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         else { pt.srcL = (pt.lane + 31) & 31; pt.srcR = (pt.lane + 1) & 31; }
     }
     const int tid = pt.tid, cnt = pt.cnt, start = pt.start;
+#ifdef RL_PHASE_TIMERS
+    if (tid == 0) { for (int i = 0; i < 16; ++i) sPh[i] = 0; sPh[15] = clock64(); }
+#endif
 
     if (tid == 0) {
         st->status = RL_OK; st->n = N; st->outer_done = 0; st->accepted = 0; st->backtracks = 0; st->evals = 0;
@@ -2000,9 +2044,10 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
                                    C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
 
     double* sC0 = sB + tid;
-    double* sCp = sB + NP + tid;
-    double* sCm = sB + 2 * NP + tid;
+    double* sCp = pair_base_a(sB + NP, NP, tid);
+    double* sCm = pair_base_b(sB + NP, NP, tid);
     double* sSt = sB + 3 * NP + tid;
+    RL_PH(0);   // setup + first corridor of the job
 
     for (int outer = 0; outer < max_outer; ++outer) {
         // =================== linearisation (main.cpp:722 / 941-944) ===================
@@ -2027,14 +2072,15 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         block_sync<T>();
         if (tid == 0) bulk_s2g_issue(B.xy + 2 * row0, sP, (uint32_t)N * 16u);   // returns once the smem read is done
         block_sync<T>();
-        double* sLo = reinterpret_cast<double*>(sP) + tid;
-        double* sHi = sLo + NP;
+        double* sLo = pair_base_a(reinterpret_cast<double*>(sP), NP, tid);
+        double* sHi = pair_base_b(reinterpret_cast<double*>(sP), NP, tid);
 #pragma unroll
-        for (int k = 0; k < K; ++k) { sLo[k * T] = lo[k]; sHi[k * T] = hi[k]; }
+        for (int k = 0; k < K; ++k) st_pair<T>(sLo, sHi, k, lo[k], hi[k]);
         double gam[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) gam[k] = 1.0;
         double lap_outer = 0.0;
+        RL_PH(1);   // linearisation + parking the path
         if (mt) {
             // ============ v(s) profile + time weights (main.cpp:944-977) ============
             double kap[K], vv[K], axd[K];
@@ -2076,6 +2122,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             }
             block_sync<T>();
         }
+        RL_PH(2);   // v(s) profile + time weights
         // ---- stencil coefficients into region B (slot-major) ----
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -2092,15 +2139,15 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
                     else if (i == N - 1) { cp = 0.0; cm = -2.0 * c1; }
                 }
             }
-            sC0[k * T] = c0; sCp[k * T] = cp; sCm[k * T] = cm;
+            sC0[k * T] = c0; st_pair<T>(sCp, sCm, k, cp, cm);
         }
         block_sync<T>();
         double cL[3], cR[3];
         {
             const int kl = pt.cntL - 1;
-            const double* b0 = sB + pt.tL; const double* br = sB + pt.tR;
-            cL[0] = b0[kl * T]; cL[1] = b0[NP + kl * T]; cL[2] = b0[2 * NP + kl * T];
-            cR[0] = br[0]; cR[1] = br[NP]; cR[2] = br[2 * NP];
+            cL[0] = sB[pt.tL + kl * T]; cR[0] = sB[pt.tR];
+            ld_pair<T>(pair_base_a(sB + NP, NP, pt.tL), pair_base_b(sB + NP, NP, pt.tL), kl, cL[1], cL[2]);
+            ld_pair<T>(pair_base_a(sB + NP, NP, pt.tR), pair_base_b(sB + NP, NP, pt.tR), 0, cR[1], cR[2]);
         }
         if (OPEN) {   // nothing beyond the two ends of an open track
             if (tid == 0) { cL[0] = 0.0; cL[1] = 0.0; cL[2] = 0.0; }
@@ -2108,8 +2155,9 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         }
         if (!EXACT) {
             // the first unused slot mirrors the right neighbour's first sample (position cnt+1 of the window)
-            if (cnt < K && cnt > 0) { sC0[cnt * T] = cR[0]; sCp[cnt * T] = cR[1]; sCm[cnt * T] = cR[2]; }
+            if (cnt < K && cnt > 0) { sC0[cnt * T] = cR[0]; st_pair<T>(sCp, sCm, cnt, cR[1], cR[2]); }
         }
+        RL_PH(3);   // stencil coefficients
         // =================== projected gradient with Armijo (main.cpp:723-742 / 996-1026) ===================
         const PgdOut po = pgd_outer<T, K, MODE>(pt, sLo, sHi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,
                                                  C.step_init, C.step_min, C.armijo_c, C.max_inner_iters);
@@ -2118,6 +2166,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             st->J0[outer] = po.J0; st->Jend[outer] = po.Jend; st->lap_outer[outer] = lap_outer;
             st->acc_outer[outer] = po.acc; st->bt_outer[outer] = po.bt;
         }
+        RL_PH(4);   // projected-gradient loop
         // ---- bring the path back ----
         block_sync<T>();
         if (tid == 0) {
@@ -2148,6 +2197,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         block_sync<T>();
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
         // (the reference also rebuilds it after the LAST path update, but nothing reads that corridor: skipped)
+        RL_PH(5);   // path back + path update
         if (outer + 1 == max_outer) continue;
         if (fast_rays) {
             const double guard = C.veh_width_m * 0.5 + C.safety_margin_m;
@@ -2160,13 +2210,17 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
 #pragma unroll
                 for (int j = 0; j < K; ++j) { loc[j] = 0.0; hic[j] = 0.0; }
             }
+            RL_PH(6);   // corridor update pass
             if (block_or<T>(flagged != 0u))   // some certificate failed (or none exists yet): the searching path rebuilds those samples
                 corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
                                           segI0, segO0, segE, guard, flagged, loc, hic, ray_tests, ex_scans);
             corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
-        } else
+            RL_PH(7);   // searching path for flagged samples + staging
+        } else {
             corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                        C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+            RL_PH(7);
+        }
     }
 
     // the next job of the chain inherits the certificates (same thread, same samples: no barrier needed)
@@ -2230,6 +2284,10 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap; st->exist_scans = (int)es;
         }
     }
+    RL_PH(8);   // certificates hand-over, final geometry, final v(s) profile, stores
+#ifdef RL_PHASE_TIMERS
+    if (tid == 0) for (int i = 0; i < 9; ++i) st->J0[16 + i] = (double)sPh[i];
+#endif
     block_sync<T>();   // the next job of the chain reuses the shared-memory regions
   }
 }

@@ -37,7 +37,9 @@ def gather_lap_times(local_laps, n_problems: int, device=None):
     import torch
     import torch.distributed as dist
 
-    local = torch.as_tensor(np.asarray(local_laps, dtype=np.float64))
+    # a torch tensor (e.g. DeviceBatch.device_tensor("lap_time"), already on the GPU) is gathered where it lies
+    local = local_laps.to(torch.float64).contiguous() if isinstance(local_laps, torch.Tensor) else \
+        torch.as_tensor(np.asarray(local_laps, dtype=np.float64))
     if device is not None:
         local = local.to(device)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -57,11 +59,40 @@ def gather_lap_times(local_laps, n_problems: int, device=None):
     return np.concatenate(parts) if parts else np.zeros(0)
 
 
+def gather_rasters(local_rows, n_problems: int, rows_per_problem: int):
+    """Final gather of per-sample rasters (e.g. the raceline xy rows) of equally long problems: every rank ends with a
+    tensor of all problems' rows in global problem order.  `local_rows`: torch tensor (local problems * rows_per_problem,
+    ...) on this rank's device; one all_gather over NCCL (NVLink / NVSwitch) or gloo."""
+    import torch
+    import torch.distributed as dist
+
+    local = local_rows.contiguous()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lo, hi = shard_bounds(n_problems, world, rank)
+    assert local.shape[0] == (hi - lo) * rows_per_problem, "local rows do not match this rank's shard"
+    width = max(shard_bounds(n_problems, world, r)[1] - shard_bounds(n_problems, world, r)[0] for r in range(world))
+    tail = tuple(local.shape[1:])
+    pad = torch.zeros((width * rows_per_problem,) + tail, dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world, width * rows_per_problem) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out.view((world * width * rows_per_problem,) + tail), pad)
+    parts = []
+    for r in range(world):
+        a, b = shard_bounds(n_problems, world, r)
+        parts.append(out[r, : (b - a) * rows_per_problem])
+    return torch.cat(parts, dim=0)
+
+
 def best_of_sweep(local_laps, n_problems: int, device=None) -> Tuple[int, float]:
     """arg-min lap over a sharded Config sweep: one all-reduce(min) on (lap, global index) pairs."""
     import torch
     import torch.distributed as dist
 
+    if isinstance(local_laps, torch.Tensor):
+        device = local_laps.device if device is None else device
+        local_laps = local_laps.detach().cpu().numpy()
     laps = np.asarray(local_laps, dtype=np.float64)
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     world, rank = (dist.get_world_size(), dist.get_rank()) if distributed else (1, 0)

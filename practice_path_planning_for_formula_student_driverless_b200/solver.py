@@ -15,6 +15,7 @@ CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -131,10 +132,15 @@ def _ptr(a):
 
 
 class PinnedPool:
-    """Page-locked numpy arrays (rl_host_alloc) so that H2D/D2H copies are asynchronous."""
+    """Page-locked numpy arrays (rl_host_alloc) so that H2D/D2H copies are asynchronous.
+
+    The arrays are views of memory the pool owns: `close()` frees it, so it refuses to run while an array handed out
+    by `empty()` is still referenced (drop the arrays -- and the PackedBatch built on them -- first, or pass
+    force=True at interpreter teardown)."""
 
     def __init__(self):
         self._ptrs = []
+        self._live = []   # weak references to the base arrays handed out
 
     def empty(self, shape, dtype):
         dtype = np.dtype(dtype)
@@ -145,17 +151,25 @@ class PinnedPool:
             raise MemoryError("rl_host_alloc failed")
         self._ptrs.append(p)
         buf = (C.c_char * nbytes).from_address(p)
-        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+        base = np.frombuffer(buf, dtype=dtype, count=n)
+        self._live.append(weakref.ref(base))
+        return base.reshape(shape)
 
     def copy(self, a):
         out = self.empty(a.shape, a.dtype)
         out[...] = a
         return out
 
-    def close(self):
+    def live_arrays(self) -> int:
+        return sum(1 for r in self._live if r() is not None)
+
+    def close(self, force=False):
+        if not force and self.live_arrays():
+            raise RuntimeError(f"PinnedPool.close(): {self.live_arrays()} array(s) of this pool are still referenced; "
+                               "their memory would be freed under them")
         for p in self._ptrs:
             lib().rl_host_free(p)
-        self._ptrs = []
+        self._ptrs, self._live = [], []
 
 
 class PackedBatch:
@@ -269,9 +283,15 @@ class Context:
         if not self._h:
             raise RacelineError(st.value, "rl_create")
         self.device = device
+        self._batches = weakref.WeakSet()   # live DeviceBatch objects: closed with (before) the context
 
     def set_stream(self, cuda_stream: Optional[int]):
         lib().rl_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None)
+
+    def set_option(self, name: str, value: int):
+        """rl_set_option: tuning knobs / test hooks of the host plan ("solve_chunks", "max_chain", "force_chain",
+        "force_cluster"; 0 = automatic)."""
+        self._check(lib().rl_set_option(self._h, name.encode(), int(value)), "rl_set_option")
 
     def _check(self, st, what=""):
         if st != RL_OK:
@@ -289,6 +309,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for b in list(self._batches):
+                b.close()
             lib().rl_destroy(self._h)
             self._h = None
 
@@ -297,6 +319,15 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class _CudaView:
+    """A device array described through __cuda_array_interface__ (what torch.as_tensor needs to wrap it in place)."""
+
+    def __init__(self, ptr, shape, strides=None, typestr="<f8", owner=None):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                         "strides": tuple(strides) if strides else None}
+        self._owner = owner
 
 
 class DeviceBatch:
@@ -308,6 +339,7 @@ class DeviceBatch:
         self._h = lib().rl_batch_create(ctx._h, C.byref(batch.desc), C.byref(st))
         if not self._h:
             ctx._check(st.value, "rl_batch_create")
+        ctx._batches.add(self)
 
     def upload(self):
         self.ctx._check(lib().rl_batch_upload(self._h, C.byref(self.host.desc)), "rl_batch_upload")
@@ -324,6 +356,24 @@ class DeviceBatch:
     @property
     def launches_per_solve(self):
         return lib().rl_batch_launches_per_solve(self._h)
+
+    def device_tensor(self, name: str):
+        """The batch's DEVICE output array `name` as a torch tensor that shares its memory (no copy): "xy" (rows, 2),
+        "heading" / "curvature" / "alpha_total" / "alpha_last" / "v" / "ax" (rows,), or "lap_time" (n_jobs,) -- a strided
+        view of the per-job counters.  For device-side consumers such as the final gather over NCCL (sharding.py)."""
+        import torch
+        dev = RlBatchOut()
+        self.ctx._check(lib().rl_batch_device_outputs(self._h, C.byref(dev)), "rl_batch_device_outputs")
+        rows, nj = self.host.rows, self.host.n_jobs
+        if name == "lap_time":
+            view = _CudaView(dev.stats + RlJobStats.lap_time.offset, (nj,), (C.sizeof(RlJobStats),), owner=self)
+        elif name == "xy":
+            view = _CudaView(dev.xy, (rows, 2), owner=self)
+        elif name in ("heading", "curvature", "alpha_total", "alpha_last", "v", "ax"):
+            view = _CudaView(getattr(dev, name), (rows,), owner=self)
+        else:
+            raise KeyError(name)
+        return torch.as_tensor(view, device=torch.device("cuda", self.ctx.device))
 
     def close(self):
         if self._h:

@@ -132,3 +132,55 @@ def test_final_gather_over_gloo_world_size_2():
     for _, allv, best in got:
         assert np.array_equal(allv, expect)
         assert best[0] == int(np.argmin(expect)) and best[1] == expect.min()
+
+
+def test_library_reads_no_environment_variables():
+    """Tuning knobs / test hooks go through rl_set_option; the C ABI never calls getenv."""
+    csrc = os.path.join(ROOT, "practice_path_planning_for_formula_student_driverless_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
+            assert "getenv" not in open(os.path.join(csrc, f)).read(), f
+
+
+def test_reference_arm_generator_equals_the_product_generator():
+    """bench.py --impl reference makes its tracks with oracle/libsynth_tracks.so (the same source file compiled without
+    CUDA) so that the CUDA library is not loaded in that arm: same seed, same bits."""
+    from oracle import oracle
+    c0, s0, L0, m = rl.synth_tracks(3, 300, 136, seed_base=0xB200, first_id=5)
+    c1, s1, L1 = oracle.synth_tracks(3, 300, 136, seed_base=0xB200, first_id=5)
+    assert np.array_equal(c0, c1) and np.array_equal(s0, s1) and np.array_equal(L0, L1)
+
+
+def test_ref_harness_solve_reports_the_logged_backtracks(tmp_path):
+    """RLR2 result files carry the backtracks the reference logs ('[PG] .. bt=' lines, min-time only): bench.py's
+    `parity.bt_equal` rests on them."""
+    from conftest import load_golden
+    from oracle import batchfile, oracle
+    exe = oracle.ref_binary("ref_harness")
+    if not exe:
+        pytest.skip("oracle/_ref/ref_harness not built (needs /root/reference at build time)")
+    import subprocess
+    g = load_golden("training_map")
+    n, mi, mo = g["center_xy"].shape[0], g["inner_seg"].shape[0], g["outer_seg"].shape[0]
+    p = oracle.default_params()
+    row = np.array([float(getattr(p, k)) for k in batchfile.PARAM_FIELDS])
+    bf, out = str(tmp_path / "b.bin"), str(tmp_path / "r.bin")
+    batchfile.write_rlb1(bf, [0, n], [0, mi, mi + mo], [g["L"]], [1], g["center_xy"], np.concatenate([g["inner_seg"], g["outer_seg"]]),
+                         row[None, :], [[0, 0, 1], [0, 0, 2]])
+    subprocess.run([exe, "solve", bf, out], check=True, capture_output=True)
+    res = batchfile.read_rlr1(out)
+    assert res[0]["backtracks"] == -1                       # the reference logs nothing for min-curv
+    assert res[1]["backtracks"] == int(g["mt_bt"].sum())
+    assert np.array_equal(res[1]["alpha_total"], g["mt_alpha_total"]) and res[1]["lap_time"] == g["mt_lap_time"]
+
+
+def test_pinned_pool_refuses_to_free_memory_under_live_arrays():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("pinned allocations need a CUDA driver")
+    pool = rl.PinnedPool()
+    a = pool.empty((4, 2), np.float64)
+    with pytest.raises(RuntimeError):
+        pool.close()
+    del a
+    pool.close()

@@ -1,6 +1,6 @@
 """GPU parity tests of the long-track path: one thread-block cluster per job (raceline_cluster.cuh).
 
-The cluster kernel serves N in (4096, 16384] (BASELINE configs[4] is N = 16,384).  RL_FORCE_CLUSTER=<cs> routes
+The cluster kernel serves N in (4096, 16384] (BASELINE configs[4] is N = 16,384).  the "force_cluster" option (rl_set_option) routes
 shorter closed tracks through it as well, so that every cluster size and the ragged / exact-fit chunkings can be
 checked against the pinned oracle at sizes the CPU finishes in seconds.  Same tolerances as test_gpu_parity.py.
 """
@@ -35,14 +35,14 @@ def _check(r, tr, st, cfg, tag):
 
 
 @pytest.mark.parametrize("cs,n", [(2, 1024), (2, 1100), (2, 4096), (4, 2500), (4, 3000), (8, 4100)])
-def test_forced_cluster_vs_oracle(ctx, cs, n, monkeypatch):
+def test_forced_cluster_vs_oracle(ctx, cs, n):
     """every cluster size, ragged and exact-fit chunks, on tracks the single-CTA kernels could also solve"""
-    monkeypatch.setenv("RL_FORCE_CLUSTER", str(cs))
+    ctx.set_option("force_cluster", cs)
     tracks = _tracks(2, n, 0xC100 + n)
     cfg = rl.Config()
     jobs = [(0, 0, MC), (0, 0, MT), (1, 0, MT)]
     res = rl.solve_batch(tracks, [cfg], jobs, ctx=ctx)
-    monkeypatch.delenv("RL_FORCE_CLUSTER")
+    ctx.set_option("force_cluster", 0)
     for (t, _, st), r in zip(jobs, res):
         _check(r, tracks[t], st, cfg, ("cluster", cs, n, t, st))
     # and the same bits as the single-CTA kernel on the same problem where that kernel exists
@@ -55,9 +55,9 @@ def test_forced_cluster_vs_oracle(ctx, cs, n, monkeypatch):
                 assert abs(a.lap_time - b.lap_time) <= 1e-9 * b.lap_time
 
 
-def test_forced_cluster_config_variants(ctx, monkeypatch):
+def test_forced_cluster_config_variants(ctx):
     """inverse-speed weights (a third cluster-wide reduction), heavy backtracking and early stops on the cluster path"""
-    monkeypatch.setenv("RL_FORCE_CLUSTER", "2")
+    ctx.set_option("force_cluster", 2)
     tracks = _tracks(1, 1300, 0xC177)
     cfgs = [rl.Config(time_weight_use_inv_v=True, inv_v_gain=0.4), rl.Config(step_init=40.0),
             rl.Config(step_init=40.0, step_min=10.0, max_outer_iters=2), rl.Config(max_vpass_iters=1, P_max_W=20000.0)]

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("block", range(8))
-def test_random_tracks_and_configs(ctx, block, monkeypatch):
+def test_random_tracks_and_configs(ctx, block):
     rng = np.random.default_rng(0xF022 + block)
     tracks, cfgs, jobs = [], [], []
     for t in range(12):
@@ -26,9 +26,9 @@ def test_random_tracks_and_configs(ctx, block, monkeypatch):
                               P_max_W=float(rng.uniform(15e3, 90e3)), step_init=float(rng.choice([0.3, 0.65, 1.5, 6.0])),
                               max_outer_iters=int(rng.integers(3, 15)), time_weight_use_inv_v=bool(rng.integers(0, 2))))
         jobs += [(t, t, MC), (t, t, MT)]
-    monkeypatch.setenv("RL_FORCE_CHAIN", "2")
+    ctx.set_option("force_chain", 2)
     res = rl.solve_batch(tracks, cfgs, jobs, ctx=ctx)
-    monkeypatch.delenv("RL_FORCE_CHAIN")
+    ctx.set_option("force_chain", 0)
     for (t, c, st), r in zip(jobs, res):
         prm = cfgs[c].to_params()
         o = oracle_ref(st, tracks[t], prm)
@@ -41,7 +41,7 @@ def test_random_tracks_and_configs(ctx, block, monkeypatch):
 
 
 @pytest.mark.parametrize("block", range(2))
-def test_random_long_tracks_on_the_cluster_path(ctx, block, monkeypatch):
+def test_random_long_tracks_on_the_cluster_path(ctx, block):
     """the same sweep through the cluster kernel (2 CTAs per job), chained"""
     rng = np.random.default_rng(0xF0C2 + block)
     tracks, cfgs, jobs = [], [], []
@@ -55,11 +55,11 @@ def test_random_long_tracks_on_the_cluster_path(ctx, block, monkeypatch):
                               veh_width_m=float(rng.uniform(0.8, 1.4)), w_time_gain=float(rng.uniform(0.0, 2.5)),
                               max_outer_iters=int(rng.integers(3, 9))))
         jobs += [(t, t, MC), (t, t, MT)]
-    monkeypatch.setenv("RL_FORCE_CLUSTER", "2")
-    monkeypatch.setenv("RL_FORCE_CHAIN", "2")
+    ctx.set_option("force_cluster", 2)
+    ctx.set_option("force_chain", 2)
     res = rl.solve_batch(tracks, cfgs, jobs, ctx=ctx)
-    monkeypatch.delenv("RL_FORCE_CHAIN")
-    monkeypatch.delenv("RL_FORCE_CLUSTER")
+    ctx.set_option("force_chain", 0)
+    ctx.set_option("force_cluster", 0)
     for (t, c, st), r in zip(jobs, res):
         o = oracle_ref(st, tracks[t], cfgs[c].to_params())
         assert_result_close(r, o, "o_", st == MT, tag=("fuzz cluster", block, t, st))
@@ -68,7 +68,7 @@ def test_random_long_tracks_on_the_cluster_path(ctx, block, monkeypatch):
             assert r.stats.backtracks == o["stats"].backtracks, (block, t, st)
 
 
-def test_random_open_tracks(ctx, monkeypatch):
+def test_random_open_tracks(ctx):
     """open paths: random arcs of random synthetic tracks with polyline rings, chained"""
     rng = np.random.default_rng(0xF0D3)
     tracks, cfgs, jobs = [], [], []
@@ -83,9 +83,9 @@ def test_random_open_tracks(ctx, monkeypatch):
         cfgs.append(rl.Config(lambda_smooth=float(10 ** rng.uniform(-3.4, -2.2)), safety_margin_m=float(rng.uniform(0.0, 0.3)),
                               w_time_gain=float(rng.uniform(0.0, 2.5)), max_outer_iters=int(rng.integers(3, 15))))
         jobs += [(t, t, MC), (t, t, MT)]
-    monkeypatch.setenv("RL_FORCE_CHAIN", "2")
+    ctx.set_option("force_chain", 2)
     res = rl.solve_batch(tracks, cfgs, jobs, ctx=ctx)
-    monkeypatch.delenv("RL_FORCE_CHAIN")
+    ctx.set_option("force_chain", 0)
     for (t, c, st), r in zip(jobs, res):
         o = oracle_ref(st, tracks[t], cfgs[c].to_params())
         assert_result_close(r, o, "o_", st == MT, tag=("fuzz open", t, st))

@@ -298,6 +298,9 @@ int rl_centerline_geom_batch(rl_ctx* ctx, const rl_geom_desc* desc, const rl_geo
  */
 int rl_synth_tracks(uint64_t seed_base, int64_t first_id, int n_tracks, int n_samples,
                     int m_per_ring, int n_threads, double* center_xy, double* seg, double* track_L);
+/* device time (CUDA events on the context's stream) of the kernels of the last rl_centerline_geom_batch call on this
+ * context, in milliseconds, copies excluded; -1 before the first call */
+double rl_last_kernel_ms(rl_ctx* ctx);
 /* measured DFMA throughput of this device in TFLOP/s (2 flop per FMA); the FP64 roofline denominator */
 int rl_measure_fp64_peak(rl_ctx* ctx, double* tflops);
 

@@ -26,7 +26,7 @@ def build(force=False):
     """Compile liboracle.so (and the _ref/ binaries when /root/reference is present)."""
     so = os.path.join(_HERE, "liboracle.so")
     syn = os.path.join(_HERE, "libsynth_tracks.so")
-    if force or not os.path.exists(so) or not os.path.exists(syn) or os.path.getmtime(so) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("raceline_oracle.c", "geom_oracle.c", "raceline_oracle.h")):
+    if force or not os.path.exists(so) or not os.path.exists(syn) or not os.path.exists(os.path.join(_HERE, "liboracle_fma.so")) or os.path.getmtime(so) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("raceline_oracle.c", "geom_oracle.c", "raceline_oracle.h")):
         subprocess.run(["make", "-C", _HERE, "port"], check=True, capture_output=True)
     return so
 
@@ -116,8 +116,24 @@ def default_params() -> RlParams:
     return p
 
 
-def solve(stage, center_xy, inner_seg, outer_seg, L, closed=True, params=None):
-    """Run one stage on the CPU.  Returns a dict with the reference Result fields + 'stats'."""
+_FMA = None
+
+
+def _fma_lib():
+    """liboracle_fma.so: the same C restatement compiled with FMA contraction (a rounding-sensitivity yardstick)."""
+    global _FMA
+    if _FMA is None:
+        build()
+        F = C.CDLL(os.path.join(_HERE, "liboracle_fma.so"))
+        F.orc_solve.argtypes = lib().orc_solve.argtypes
+        F.orc_solve.restype = C.c_int
+        _FMA = F
+    return _FMA
+
+
+def solve(stage, center_xy, inner_seg, outer_seg, L, closed=True, params=None, rounding="reference"):
+    """Run one stage on the CPU.  Returns a dict with the reference Result fields + 'stats'.
+    rounding="fma": the FMA-contracted build (NOT the reference's bits; see _fma_lib)."""
     center_xy = _c(center_xy).reshape(-1, 2)
     inner_seg = _c(inner_seg).reshape(-1, 4)
     outer_seg = _c(outer_seg).reshape(-1, 4)
@@ -126,7 +142,7 @@ def solve(stage, center_xy, inner_seg, outer_seg, L, closed=True, params=None):
     out = {k: np.zeros(n) for k in ("heading", "curvature", "alpha_total", "alpha_last", "v", "ax")}
     out["xy"] = np.zeros((n, 2))
     st = RlJobStats()
-    rc = lib().orc_solve(int(stage), _p(center_xy), n, _p(inner_seg), inner_seg.shape[0], _p(outer_seg),
+    rc = (lib() if rounding == "reference" else _fma_lib()).orc_solve(int(stage), _p(center_xy), n, _p(inner_seg), inner_seg.shape[0], _p(outer_seg),
                          outer_seg.shape[0], float(L), int(bool(closed)), C.byref(params), _p(out["xy"]),
                          _p(out["heading"]), _p(out["curvature"]), _p(out["alpha_total"]), _p(out["alpha_last"]),
                          _p(out["v"]), _p(out["ax"]), C.byref(st))

@@ -27,6 +27,9 @@ struct rl_ctx {
     // tuning knobs and test hooks (rl_set_option); 0 = automatic
     int opt_solve_chunks = 0, opt_max_chain = 0, opt_force_chain = 0, opt_force_cluster = 0;
     bool pipeline_ready = false;
+    struct GeomBufs* geom = nullptr;   // device buffers of rl_centerline_geom_batch, kept between calls (grow only)
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // timing events around the kernels of the last geometry call
+    float last_kernel_ms = -1.f;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;   // own_stream or the caller's
     std::string err;
@@ -65,6 +68,17 @@ struct DevArr {
 struct ClassList { int cls; int mode; int begin; int count; int chunk; int item_begin; int n_items; };
 
 }  // namespace
+
+struct GeomBufs {
+    DevArr<long long> mid_off, seg_off, row_off;
+    DevArr<double> mids, seg, out, L, s0;
+    DevArr<int> samples, closed;
+    void release()
+    {
+        mid_off.release(); seg_off.release(); row_off.release(); mids.release(); seg.release(); out.release();
+        L.release(); s0.release(); samples.release(); closed.release();
+    }
+};
 
 struct rl_batch {
     rl_ctx* ctx = nullptr;
@@ -174,8 +188,12 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
     const int max_chain = c->opt_max_chain > 0 ? c->opt_max_chain : 8;   // rl_set_option("max_chain")
     const int force_chain = std::max(0, c->opt_force_chain);             // test hook: chains of that length whatever the batch size
     for (int c = 0; c <= n_chunks; ++c) {
+        // The first chunk's upload and the last chunk's download are the only copies no kernel hides: with enough
+        // chunks those two are a quarter of the size of the others.
         // a chunk boundary never separates the jobs of one track (they form a chain and share the track's upload)
-        int j = (int)(((long long)d->n_jobs * c) / n_chunks);
+        long long num = c, den = n_chunks;
+        if (n_chunks >= 6) { den = 4ll * n_chunks - 6; num = (c == 0) ? 0 : (c == n_chunks ? den : 4ll * c - 3); }
+        int j = (int)(((long long)d->n_jobs * num) / den);
         if (c > 0 && c < n_chunks) {
             j = std::max(j, b->chunk_job0[c - 1]);
             for (int moved = 0; moved < max_chain && j > b->chunk_job0[c - 1] && j < d->n_jobs && d->jobs[j].track == d->jobs[j - 1].track; ++moved) ++j;
@@ -462,6 +480,9 @@ void rl_destroy(rl_ctx* c)
     }
     for (int i = 0; i < kMaxChunks + 2; ++i) if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
     if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->geom) { c->geom->release(); delete c->geom; }
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -685,7 +706,17 @@ static int solve_batch_pipeline(rl_ctx* c, rl_batch* b, const rl_batch_desc* d, 
     RL_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_start, 0));
     for (int i = 0; i < kMaxChunks; ++i) RL_CUDA(c, cudaStreamWaitEvent(c->s_k[i], c->ev_start, 0));
 
-    if (o->stats && (size_t)d->n_jobs > c->h_stats_cap) {
+    // the per-job counters go straight into the caller's array when it is page-locked (rl_host_alloc); a D2H copy into
+    // PAGEABLE memory would block the host until it has run and serialise the pipeline, so those land in a pinned
+    // staging area first and are copied over at the end
+    rl_job_stats* stats_dst = o->stats;
+    if (o->stats) {
+        cudaPointerAttributes pa;
+        const bool pinned = cudaPointerGetAttributes(&pa, o->stats) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!pinned) stats_dst = nullptr;
+    }
+    if (o->stats && !stats_dst && (size_t)d->n_jobs > c->h_stats_cap) {
         if (c->h_stats) cudaFreeHost(c->h_stats);
         c->h_stats = nullptr; c->h_stats_cap = 0;
         const size_t want = (size_t)d->n_jobs + (size_t)d->n_jobs / 8 + 16;
@@ -732,7 +763,7 @@ static int solve_batch_pipeline(rl_ctx* c, rl_batch* b, const rl_batch_desc* d, 
             if (o->ax) { st = copy_v_rows(c, b, k, o->ax, b->d_ax.p, c->s_out); if (st != RL_OK) return st; }
         }
         if (o->stats && j1 > j0)
-            RL_CUDA(c, cudaMemcpyAsync(c->h_stats + j0, b->d_stats.p + j0, sizeof(rl_job_stats) * (size_t)(j1 - j0), cudaMemcpyDeviceToHost, c->s_out));
+            RL_CUDA(c, cudaMemcpyAsync((stats_dst ? stats_dst : c->h_stats) + j0, b->d_stats.p + j0, sizeof(rl_job_stats) * (size_t)(j1 - j0), cudaMemcpyDeviceToHost, c->s_out));
     }
     // join everything back into the context stream
     for (int i = 0; i < kMaxChunks + 2; ++i) {
@@ -742,7 +773,7 @@ static int solve_batch_pipeline(rl_ctx* c, rl_batch* b, const rl_batch_desc* d, 
     }
     st = rl_batch_sync(b);
     if (st != RL_OK) return st;
-    if (o->stats) std::memcpy(o->stats, c->h_stats, sizeof(rl_job_stats) * (size_t)d->n_jobs);
+    if (o->stats && !stats_dst) std::memcpy(o->stats, c->h_stats, sizeof(rl_job_stats) * (size_t)d->n_jobs);
     for (auto& sk : b->skipped)
         if (sk.second != RL_OK) return fail(c, sk.second, "a job's shape is not covered by the kernels (N too large)");
     return RL_OK;
@@ -849,20 +880,28 @@ int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out
     RL_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const size_t rows = (size_t)row_off[nt], n_mid = (size_t)d->mid_off[nt], n_seg = (size_t)d->seg_off[2 * nt];
-    DevFree mem;
-    long long *d_mid_off, *d_seg_off, *d_row_off;
-    double *d_mids, *d_seg, *d_out, *d_L, *d_s0;
-    int *d_samples, *d_closed;
-    RL_CUDA(c, mem.alloc(&d_mid_off, (size_t)nt + 1));
-    RL_CUDA(c, mem.alloc(&d_seg_off, (size_t)2 * nt + 1));
-    RL_CUDA(c, mem.alloc(&d_row_off, (size_t)nt + 1));
-    RL_CUDA(c, mem.alloc(&d_mids, 2 * n_mid));
-    RL_CUDA(c, mem.alloc(&d_seg, 4 * n_seg + 4));
-    RL_CUDA(c, mem.alloc(&d_samples, (size_t)nt));
-    RL_CUDA(c, mem.alloc(&d_closed, (size_t)nt));
-    RL_CUDA(c, mem.alloc(&d_out, 9 * rows + 16));      // xy (2), s_rel, heading, curvature, dist_inner, dist_outer, width, v_kappa
-    RL_CUDA(c, mem.alloc(&d_L, (size_t)nt));
-    RL_CUDA(c, mem.alloc(&d_s0, (size_t)nt));
+    if (!c->geom) {
+        c->geom = new (std::nothrow) GeomBufs();
+        if (!c->geom) return fail(c, RL_ERR_NOMEM, "host allocation failed");
+    }
+    if (!c->ev_t0) {
+        RL_CUDA(c, cudaEventCreate(&c->ev_t0));
+        RL_CUDA(c, cudaEventCreate(&c->ev_t1));
+    }
+    GeomBufs& gb = *c->geom;     // no allocation in the steady state: the buffers only ever grow
+    RL_CUDA(c, gb.mid_off.ensure((size_t)nt + 1));
+    RL_CUDA(c, gb.seg_off.ensure((size_t)2 * nt + 1));
+    RL_CUDA(c, gb.row_off.ensure((size_t)nt + 1));
+    RL_CUDA(c, gb.mids.ensure(2 * n_mid + 2));
+    RL_CUDA(c, gb.seg.ensure(4 * n_seg + 4));
+    RL_CUDA(c, gb.samples.ensure((size_t)nt));
+    RL_CUDA(c, gb.closed.ensure((size_t)nt));
+    RL_CUDA(c, gb.out.ensure(9 * rows + 16));      // xy (2), s_rel, heading, curvature, dist_inner, dist_outer, width, v_kappa
+    RL_CUDA(c, gb.L.ensure((size_t)nt));
+    RL_CUDA(c, gb.s0.ensure((size_t)nt));
+    long long *d_mid_off = gb.mid_off.p, *d_seg_off = gb.seg_off.p, *d_row_off = gb.row_off.p;
+    double *d_mids = gb.mids.p, *d_seg = gb.seg.p, *d_out = gb.out.p, *d_L = gb.L.p, *d_s0 = gb.s0.p;
+    int *d_samples = gb.samples.p, *d_closed = gb.closed.p;
     RL_CUDA(c, cudaMemcpyAsync(d_mid_off, d->mid_off, sizeof(long long) * ((size_t)nt + 1), cudaMemcpyHostToDevice, s));
     RL_CUDA(c, cudaMemcpyAsync(d_seg_off, d->seg_off, sizeof(long long) * ((size_t)2 * nt + 1), cudaMemcpyHostToDevice, s));
     RL_CUDA(c, cudaMemcpyAsync(d_row_off, row_off.data(), sizeof(long long) * ((size_t)nt + 1), cudaMemcpyHostToDevice, s));
@@ -877,8 +916,10 @@ int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out
     G.xy = d_out; G.s_rel = d_out + 2 * rows; G.heading = G.s_rel + rows; G.curvature = G.heading + rows;
     G.dist_inner = G.curvature + rows; G.dist_outer = G.dist_inner + rows; G.width = G.dist_outer + rows; G.v_kappa = G.width + rows;
     G.track_L = d_L; G.track_s0 = d_s0;
+    RL_CUDA(c, cudaEventRecord(c->ev_t0, s));
     const int e = rl::launch_geom(G, nt, max_pts, s);
     if (e != 0) return cuda_fail(c, (cudaError_t)e, "geometry kernels");
+    RL_CUDA(c, cudaEventRecord(c->ev_t1, s));
     if (rows) {
         if (o->xy) RL_CUDA(c, cudaMemcpyAsync(o->xy, G.xy, 16 * rows, cudaMemcpyDeviceToHost, s));
         if (o->s_rel) RL_CUDA(c, cudaMemcpyAsync(o->s_rel, G.s_rel, 8 * rows, cudaMemcpyDeviceToHost, s));
@@ -893,7 +934,16 @@ int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out
     if (o->track_s0) RL_CUDA(c, cudaMemcpyAsync(o->track_s0, d_s0, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, s));
     RL_CUDA(c, cudaStreamSynchronize(s));
     RL_CUDA(c, cudaGetLastError());
+    c->last_kernel_ms = -1.f;
+    cudaEventElapsedTime(&c->last_kernel_ms, c->ev_t0, c->ev_t1);
     return RL_OK;
+}
+
+double rl_last_kernel_ms(rl_ctx* c)
+{
+    if (!c) return -1.0;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    return (double)c->last_kernel_ms;
 }
 
 int rl_measure_fp64_peak(rl_ctx* c, double* tflops)

@@ -176,15 +176,7 @@ __device__ __forceinline__ bool pgd_half_c(const Part& pt, const Clu& cl, const 
     double Jz = 0.0, Sd = 0.0;
     eval_window<T, K, MODE>(xa, ha, pt, c.sC0, c.sCp, c.sCm, cL, cR, c.lamJ, Jz, Sd, gh);
     double Jn = fma(c.lamJ, Sd, Jz);
-    double dec2p = 0.0;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        double lo, hi;
-        ld_pair<T>(sLo, sHi, k, lo, hi);
-        const double xn = clamp_box(fma(-c.step2, gh[k], xa[k]), lo, hi);
-        dec2p = fma(gh[k], xn - xa[k], dec2p);
-        xb[k] = xn;
-    }
+    const double dec2p = project_trial<T, K>(xa, gh, c.step2, sLo, sHi, xb);
     hb = halo_send_c<K, MODE>(xb, pt, cl, c.sExF + c.ph * kcExStride, c.sExL + c.ph * kcExStride);
     double dec = c.decp;
     cluster_sum2(Jn, dec, c.sRed + c.ph * kcRedStride, cl, pt.lane, pt.warp);

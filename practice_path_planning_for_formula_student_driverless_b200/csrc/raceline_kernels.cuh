@@ -129,8 +129,12 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* sred, i
         if ((lane & 15) == 0) sred[2 * warp + (lane >> 4)] = v;
         __syncthreads();
         double2 e[NW];
+        // all partial pairs are requested before the first add: `volatile` keeps the compiler from recycling two
+        // registers through NW/2 dependent load -> add round trips (one LDS latency each)
+        const uint32_t sa = smem_u32(sred);
 #pragma unroll
-        for (int w = 0; w < NW; ++w) e[w] = reinterpret_cast<const double2*>(sred)[w];
+        for (int w = 0; w < NW; ++w)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e[w].x), "=d"(e[w].y) : "r"(sa + 16u * w));
 #pragma unroll
         for (int n = NW / 2; n > 0; n >>= 1) {
 #pragma unroll
@@ -505,8 +509,11 @@ __device__ __forceinline__ Halo halo_send(const double (&x)[K], const Part& pt, 
     h.r0 = __shfl_sync(kFull, F0, pt.srcR);
     h.r1 = __shfl_sync(kFull, F1, pt.srcR);
     if (T > 32) {
-        if (pt.lane == 0) { sExF[2 * pt.warp] = F0; sExF[2 * pt.warp + 1] = F1; }
-        if (pt.lane == 31) { sExL[2 * pt.warp] = L0; sExL[2 * pt.warp + 1] = L1; }
+        // predicated stores: no divergent branch (BSSY / BSYNC and its branch-resolving bubble) in the hot loop
+        asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %0, 0;\n@p st.shared.v2.f64 [%1], {%2, %3};\n}" ::"r"(pt.lane),
+                     "r"(smem_u32(sExF + 2 * pt.warp)), "d"(F0), "d"(F1) : "memory");
+        asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %0, 31;\n@p st.shared.v2.f64 [%1], {%2, %3};\n}" ::"r"(pt.lane),
+                     "r"(smem_u32(sExL + 2 * pt.warp)), "d"(L0), "d"(L1) : "memory");
     }
     return h;
 }
@@ -530,6 +537,24 @@ __device__ __forceinline__ double clamp_box(double a, double lo, double hi)
     return (a < hi) ? a : hi;
 }
 
+// Projection of the next trial onto the box (main.cpp:731): xb = min(hi, max(lo, xa - step*grad)); returns
+// sum gh * (xb - xa) (main.cpp:733 for the NEXT Armijo test, in units of grad/2).
+template <int T, int K>
+__device__ __forceinline__ double project_trial(const double (&xa)[K], const double (&gh)[K], double step2,
+                                                const double* sLo, const double* sHi, double (&xb)[K])
+{
+    double dec2p = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double lo, hi;
+        ld_pair<T>(sLo, sHi, k, lo, hi);
+        const double xn = clamp_box(fma(-step2, gh[k], xa[k]), lo, hi);
+        dec2p = fma(gh[k], xn - xa[k], dec2p);
+        xb[k] = xn;
+    }
+    return dec2p;
+}
+
 // State shared by the two halves of the ping-pong loop below.
 template <int K>
 struct PgdCtx {
@@ -551,15 +576,7 @@ __device__ __forceinline__ bool pgd_half(const Part& pt, const double (&xa)[K], 
     double Jz = 0.0, Sd = 0.0;
     eval_window<T, K, MODE>(xa, ha, pt, c.sC0, c.sCp, c.sCm, cL, cR, c.lamJ, Jz, Sd, gh);
     double Jn = fma(c.lamJ, Sd, Jz);
-    double dec2p = 0.0;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        double lo, hi;
-        ld_pair<T>(sLo, sHi, k, lo, hi);
-        const double xn = clamp_box(fma(-c.step2, gh[k], xa[k]), lo, hi);
-        dec2p = fma(gh[k], xn - xa[k], dec2p);
-        xb[k] = xn;
-    }
+    const double dec2p = project_trial<T, K>(xa, gh, c.step2, sLo, sHi, xb);
     hb = halo_send<T, K, MODE>(xb, pt, c.sExF + c.ph * 32, c.sExL + c.ph * 32);
     double dec = c.decp;
     block_sum2<T>(Jn, dec, c.sRed + c.ph * 32, pt.lane, pt.warp);
@@ -673,6 +690,8 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
     o.Jend = c.J;
     return o;
 }
+
+
 
 // ---- corridor, general path (rings of any size, streamed through shared memory in tiles) ------------------
 // (main.cpp:694-711, 749-756): rays +-n against both rings, exact nearest hit

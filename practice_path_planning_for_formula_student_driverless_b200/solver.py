@@ -199,7 +199,7 @@ class PackedBatch:
             self.seg[self.seg_off[2 * t + 1]:self.seg_off[2 * t + 2]] = _f64(tr.outer_seg, 4)
             self.track_L[t] = float(tr.L)
             self.track_closed[t] = int(bool(tr.closed))
-        self._finish(params, jobs, alloc)
+        self._finish(params, jobs, alloc, pool)
 
     @classmethod
     def from_arrays(cls, samp_off, seg_off, center_xy, seg, track_L, track_closed, params, jobs, pool=None):
@@ -213,10 +213,10 @@ class PackedBatch:
         self.seg = _f64(seg, 4)
         self.track_L = _f64(track_L)
         self.track_closed = np.ascontiguousarray(track_closed, dtype=np.int32)
-        self._finish(params, jobs, alloc)
+        self._finish(params, jobs, alloc, pool)
         return self
 
-    def _finish(self, params, jobs, alloc):
+    def _finish(self, params, jobs, alloc, pool=None):
         jobs = np.asarray(jobs, dtype=np.int64).reshape(-1, 3)
         self.n_jobs = jobs.shape[0]
         self.params = (RlParams * max(1, self.n_params))(*params)
@@ -248,7 +248,13 @@ class PackedBatch:
         self.out_alpha_last = alloc(rows, np.float64)
         self.out_v = alloc(rows, np.float64)
         self.out_ax = alloc(rows, np.float64)
-        self.out_stats = (RlJobStats * max(1, self.n_jobs))()
+        if pool is not None:      # page-locked, so that the library copies the counters straight into it
+            raw = pool.empty(max(1, self.n_jobs) * C.sizeof(RlJobStats), np.uint8)
+            raw[:] = 0
+            self._stats_raw = raw
+            self.out_stats = (RlJobStats * max(1, self.n_jobs)).from_buffer(raw)
+        else:
+            self.out_stats = (RlJobStats * max(1, self.n_jobs))()
         self.out = RlBatchOut()
         self.out.xy, self.out.heading, self.out.curvature = _ptr(self.out_xy), _ptr(self.out_heading), _ptr(self.out_curvature)
         self.out.alpha_total, self.out.alpha_last = _ptr(self.out_alpha_total), _ptr(self.out_alpha_last)
@@ -301,6 +307,10 @@ class Context:
         """Host buffers in, host buffers out (rl_solve_batch)."""
         self._check(lib().rl_solve_batch(self._h, C.byref(batch.desc), C.byref(batch.out)), "rl_solve_batch")
         return batch
+
+    def last_kernel_ms(self) -> float:
+        """Device time of the kernels of the last centerline_geom_batch call on this context (copies excluded)."""
+        return float(lib().rl_last_kernel_ms(self._h))
 
     def fp64_peak_tflops(self) -> float:
         v = C.c_double(0)
@@ -549,10 +559,12 @@ class CenterlineGeom:
 
 def centerline_geom_batch(mids: Sequence[np.ndarray], samples: Sequence[int], inner_rings: Sequence[np.ndarray],
                           outer_rings: Sequence[np.ndarray], closed=True, cfg: Optional[Config] = None,
-                          ctx: Optional[Context] = None, emit_closed_duplicate=True) -> List[CenterlineGeom]:
+                          ctx: Optional[Context] = None, emit_closed_duplicate=True,
+                          pool: Optional[PinnedPool] = None) -> List[CenterlineGeom]:
     """pipeline::make_centerline + the per-sample body of pipeline::compute_geom_and_save (main.cpp:1270-1335) for a
     batch of tracks: ordered mid points in, centre line + heading/curvature/ring distances/width/v_kappa rows out.
-    `inner_rings` / `outer_rings` are segment arrays (ring_edges / polyline_edges of the *_from_mids points)."""
+    `inner_rings` / `outer_rings` are segment arrays (ring_edges / polyline_edges of the *_from_mids points).
+    With a PinnedPool the packed inputs and the output rows are page-locked (copies at PCIe speed)."""
     from ._abi import RlGeomDesc, RlGeomOut
     cfg = cfg or Config()
     ctx = ctx or default_context()
@@ -568,6 +580,9 @@ def centerline_geom_batch(mids: Sequence[np.ndarray], samples: Sequence[int], in
     seg_off[1:] = np.cumsum([g.shape[0] for g in segs])
     mids_xy = np.ascontiguousarray(np.concatenate(mids, axis=0)) if nt else np.zeros((0, 2))
     seg = np.ascontiguousarray(np.concatenate(segs, axis=0)) if segs else np.zeros((0, 4))
+    zeros = (lambda shape: pool.empty(shape, np.float64)) if pool else (lambda shape: np.zeros(shape))
+    if pool:
+        mids_xy, seg = pool.copy(mids_xy), pool.copy(seg)
     smp = np.ascontiguousarray(np.asarray(samples, dtype=np.int32).reshape(nt))
     p = cfg.to_params()
     d = RlGeomDesc()
@@ -577,8 +592,8 @@ def centerline_geom_batch(mids: Sequence[np.ndarray], samples: Sequence[int], in
     off = np.zeros(nt + 1, dtype=np.int64)
     ctx._check(lib().rl_geom_row_offsets(C.byref(d), off.ctypes.data_as(C.POINTER(C.c_int64))), "rl_geom_row_offsets")
     rows = int(off[nt])
-    arr = {k: np.zeros(rows) for k in ("s_rel", "heading", "curvature", "dist_inner", "dist_outer", "width", "v_kappa")}
-    xy, Lv, s0 = np.zeros((rows, 2)), np.zeros(nt), np.zeros(nt)
+    arr = {k: zeros(rows) for k in ("s_rel", "heading", "curvature", "dist_inner", "dist_outer", "width", "v_kappa")}
+    xy, Lv, s0 = zeros((rows, 2)), np.zeros(nt), np.zeros(nt)
     o = RlGeomOut()
     o.xy, o.track_L, o.track_s0 = _ptr(xy), _ptr(Lv), _ptr(s0)
     for k, a in arr.items():

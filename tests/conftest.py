@@ -33,12 +33,26 @@ def goldens():
     return {m: load_golden(m) for m in MAPS}
 
 
+_CTX = []
+
+
 @pytest.fixture(scope="session")
 def ctx():
     import practice_path_planning_for_formula_student_driverless_b200 as rl
     c = rl.Context(0)
+    _CTX.append(c)
     yield c
+    _CTX.clear()
     c.close()
+
+
+@pytest.fixture(autouse=True)
+def _plan_options_back_to_automatic():
+    """Tests steer the host plan through rl_set_option on the shared context; none of that may leak into the next test."""
+    yield
+    for c in _CTX:
+        for name in ("solve_chunks", "max_chain", "force_chain", "force_cluster"):
+            c.set_option(name, 0)
 
 
 def angle_diff(a, b):

@@ -249,18 +249,27 @@ def test_rigid_motion_and_mirror_invariance(ctx, goldens):
     assert abs(res[0].lap_time - res[2].lap_time) < TOL_LAP_REL * res[0].lap_time
 
 
-def test_dropin_binary_matches_reference_binary(tmp_path, goldens):
+@pytest.mark.parametrize("name,shuffled", [("competition_map3", False), ("competition_map1", True), ("competition_map2", True),
+                                           ("competition_map3", True), ("competition_map_testday1", True),
+                                           ("competition_map_testday2", True)])
+def test_dropin_binary_matches_reference_binary(tmp_path, goldens, name, shuffled):
     """The reference's own main() with ONLY its two solver calls redirected to the CUDA library
     (oracle/_ref/fsd_path_b200, see oracle/Makefile `dropin`) against the unmodified reference binary:
-    same cone files in, same CSV columns out (s,x,y,heading_rad,curvature,alpha_last,v_mps,ax_mps2; main.cpp:1364, 1420)."""
+    same cone files in, same CSV columns out (s,x,y,heading_rad,curvature,alpha_last,v_mps,ax_mps2; main.cpp:1364, 1420).
+    `shuffled`: the cones in random order, like the reference's own csv/*_shuffled.csv sets (its front end --
+    Delaunay, MST ordering -- has to put them back in order before the solver stages run)."""
     import os
     import subprocess
     ref, ours = oracle.ref_binary("fsd_path"), oracle.ref_binary("fsd_path_b200")
     if not (ref and ours):
         pytest.skip("oracle/_ref binaries not built (they are built where /root/reference is mounted)")
-    g = goldens["competition_map3"]
-    np.savetxt(tmp_path / "inner.csv", g["inner_seg"][:, :2], delimiter=",", fmt="%.17g")
-    np.savetxt(tmp_path / "outer.csv", g["outer_seg"][:, :2], delimiter=",", fmt="%.17g")
+    g = goldens[name]
+    rng = np.random.default_rng(len(name) * 131 + 7)
+    inner, outer = g["inner_seg"][:, :2], g["outer_seg"][:, :2]
+    if shuffled:
+        inner, outer = inner[rng.permutation(len(inner))], outer[rng.permutation(len(outer))]
+    np.savetxt(tmp_path / "inner.csv", inner, delimiter=",", fmt="%.17g")
+    np.savetxt(tmp_path / "outer.csv", outer, delimiter=",", fmt="%.17g")
     outs = {}
     for tag, exe in (("ref", ref), ("b200", ours)):
         d = tmp_path / tag

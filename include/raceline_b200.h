@@ -187,6 +187,7 @@ int rl_set_stream(rl_ctx* ctx, void* cuda_stream);
  *   "max_chain"     longest chain of consecutive jobs on one track that one CTA / cluster works through
  *   "force_chain"   form chains of exactly this length whatever the batch size (tests)
  *   "force_cluster" route closed tracks of any length through the cluster kernel with this many CTAs (tests)
+ *   "debug_inject"  debug-checks build only, see rl_debug_check_failures
  * Unknown names return RL_ERR_ARG.  The library reads no environment variables.
  */
 int rl_set_option(rl_ctx* ctx, const char* name, int64_t value);
@@ -298,6 +299,14 @@ int rl_centerline_geom_batch(rl_ctx* ctx, const rl_geom_desc* desc, const rl_geo
  */
 int rl_synth_tracks(uint64_t seed_base, int64_t first_id, int n_tracks, int n_samples,
                     int m_per_ring, int n_threads, double* center_xy, double* seg, double* track_L);
+/*
+ * Debug-checks build only (library compiled with -DRL_DEBUG_CHECKS; RL_ERR_UNSUPPORTED otherwise): the kernels verify
+ * the hand-over protocol of their shared-memory regions, guard zones between the regions and the bounds of the views
+ * they carve out (csrc/raceline_kernels.cuh).  out[0] = failed checks since the context was created, out[1] = the
+ * first one (check code | CTA index << 32).  The option "debug_inject" = 1 makes one warp skip a hand-over so that a
+ * test can see the checker fire.
+ */
+int rl_debug_check_failures(rl_ctx* ctx, uint64_t* out2);
 /* device time (CUDA events on the context's stream) of the kernels of the last rl_centerline_geom_batch call on this
  * context, in milliseconds, copies excluded; -1 before the first call */
 double rl_last_kernel_ms(rl_ctx* ctx);

@@ -7,14 +7,14 @@ fails loudly if it has not been built -- there is no CPU fallback).
 from ._abi import (RL_ABI_VERSION, RL_ERR_ARG, RL_ERR_CUDA, RL_ERR_NODEVICE, RL_ERR_NOMEM, RL_ERR_UNSUPPORTED,
                    RL_MAX_OUTER_LOG, RL_OK, RL_STAGE_EVAL, RL_STAGE_MINCURV, RL_STAGE_MINTIME, RlBatchDesc, RlBatchOut, RlJob,
                    RlJobStats, RlParams)
-from .solver import (CenterlineGeom, Config, Context, DeviceBatch, PackedBatch, PinnedPool, RacelineError, Result, Track,
+from .solver import (CenterlineGeom, Config, Context, DeviceBatch, PackedBatch, PackedGeom, PinnedPool, RacelineError, Result, Track,
                      centerline_geom_batch, compute_min_curvature_raceline, debug_compare_paths, path_length, compute_min_time_raceline, default_context,
                      polyline_edges, ring_edges, solve_batch, synth_tracks)
 
 __all__ = [
     "RL_ABI_VERSION", "RL_OK", "RL_ERR_ARG", "RL_ERR_CUDA", "RL_ERR_UNSUPPORTED", "RL_ERR_NOMEM", "RL_ERR_NODEVICE",
     "RL_STAGE_MINCURV", "RL_STAGE_MINTIME", "RL_STAGE_EVAL", "RL_MAX_OUTER_LOG", "RlParams", "RlJob", "RlJobStats", "RlBatchDesc",
-    "RlBatchOut", "Config", "Context", "DeviceBatch", "PackedBatch", "PinnedPool", "RacelineError", "Result", "Track",
+    "RlBatchOut", "Config", "Context", "DeviceBatch", "PackedBatch", "PackedGeom", "PinnedPool", "RacelineError", "Result", "Track",
     "compute_min_curvature_raceline", "compute_min_time_raceline", "default_context", "polyline_edges", "ring_edges",
     "solve_batch", "synth_tracks", "CenterlineGeom", "centerline_geom_batch", "debug_compare_paths", "path_length",
 ]

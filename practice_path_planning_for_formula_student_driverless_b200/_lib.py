@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "rl_set_stream", "rl_set_option", "rl_last_error", "rl_host_alloc", "rl_host_free", "rl_job_sample_offsets", "rl_solve_batch",
     "rl_batch_create", "rl_batch_upload", "rl_batch_solve", "rl_batch_download", "rl_batch_sync", "rl_batch_device_outputs",
     "rl_batch_launches_per_solve", "rl_batch_destroy", "rl_compute_min_curvature_raceline",
-    "rl_compute_min_time_raceline", "rl_geom_row_offsets", "rl_centerline_geom_batch", "rl_synth_tracks", "rl_last_kernel_ms",
+    "rl_compute_min_time_raceline", "rl_geom_row_offsets", "rl_centerline_geom_batch", "rl_synth_tracks", "rl_last_kernel_ms", "rl_debug_check_failures",
     "rl_measure_fp64_peak",
 ]
 
@@ -93,6 +93,8 @@ def lib():
     L.rl_centerline_geom_batch.restype = C.c_int
     L.rl_synth_tracks.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp]
     L.rl_synth_tracks.restype = C.c_int
+    L.rl_debug_check_failures.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.rl_debug_check_failures.restype = C.c_int
     L.rl_last_kernel_ms.argtypes = [vp]
     L.rl_last_kernel_ms.restype = C.c_double
     L.rl_measure_fp64_peak.argtypes = [vp, dp]

@@ -30,6 +30,7 @@ struct rl_ctx {
     struct GeomBufs* geom = nullptr;   // device buffers of rl_centerline_geom_batch, kept between calls (grow only)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // timing events around the kernels of the last geometry call
     float last_kernel_ms = -1.f;
+    unsigned long long* d_dbg = nullptr;   // debug-checks build: [0] failures, [1] first failure, [2] fault injection switch
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;   // own_stream or the caller's
     std::string err;
@@ -226,7 +227,7 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
             const long long n = d->samp_off[t + 1] - d->samp_off[t];
             if (n == 0) { b->skipped.push_back({j, RL_OK}); continue; }   // empty Result, main.cpp:689 / 912
             const int cls = rl::class_for_n((int)n);
-            const int cs = (d->track_closed[t] && (cls < 0 || force_cs > 0)) ? rl::cluster_size_for_n(n, force_cs) : 0;
+            const int cs = (d->track_closed[t] && (cls < 0 || force_cs > 0)) ? rl::cluster_size_for_n(n, force_cs, rl::cluster_max_size()) : 0;
             if (cs > 0) { cbucket[2 * cs + (n == 2048ll * cs ? 1 : 0)].push_back(j); continue; }
             if (cls < 0) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
             const bool exact = (n == (long long)rl::kClasses[cls].T * rl::kClasses[cls].K);
@@ -354,6 +355,7 @@ DevBatch dev_view(const rl_batch* b)
     B.track_L = b->d_L.p; B.track_closed = b->d_closed.p; B.params = b->d_params.p; B.jobs = b->d_jobs.p;
     B.job_off = b->d_job_off.p; B.xy = b->d_xy.p; B.heading = b->d_heading.p; B.curvature = b->d_curv.p;
     B.alpha_total = b->d_atot.p; B.alpha_last = b->d_alast.p; B.v = b->d_v.p; B.ax = b->d_ax.p; B.stats = b->d_stats.p;
+    B.dbg = b->ctx ? b->ctx->d_dbg : nullptr;
     return B;
 }
 
@@ -458,6 +460,10 @@ rl_ctx* rl_create(int device, int* status)
         if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) st = RL_ERR_CUDA;
         c->stream = c->own_stream;
         if (st == RL_OK && rl::configure_kernels() != 0) st = RL_ERR_CUDA;
+#ifdef RL_DEBUG_CHECKS
+        if (st == RL_OK && (cudaMalloc((void**)&c->d_dbg, 3 * sizeof(unsigned long long)) != cudaSuccess ||
+                            cudaMemset(c->d_dbg, 0, 3 * sizeof(unsigned long long)) != cudaSuccess)) st = RL_ERR_CUDA;
+#endif
         if (st != RL_OK) { if (c->own_stream) cudaStreamDestroy(c->own_stream); delete c; c = nullptr; }
     }
     if (status) *status = st;
@@ -481,6 +487,7 @@ void rl_destroy(rl_ctx* c)
     for (int i = 0; i < kMaxChunks + 2; ++i) if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->geom) { c->geom->release(); delete c->geom; }
+    if (c->d_dbg) cudaFree(c->d_dbg);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -504,6 +511,13 @@ int rl_set_option(rl_ctx* c, const char* name, int64_t value)
     else if (!std::strcmp(name, "max_chain")) c->opt_max_chain = v;
     else if (!std::strcmp(name, "force_chain")) c->opt_force_chain = v;
     else if (!std::strcmp(name, "force_cluster")) c->opt_force_cluster = v;
+    else if (!std::strcmp(name, "debug_inject")) {
+        // debug-checks build only: make one warp skip a phase hand-over so that tests can see the checker fire
+        if (!c->d_dbg) return fail(c, RL_ERR_UNSUPPORTED, "rl_set_option: debug_inject needs the -DRL_DEBUG_CHECKS build");
+        const unsigned long long inj = (unsigned long long)v;
+        RL_CUDA(c, cudaSetDevice(c->device));
+        RL_CUDA(c, cudaMemcpy(c->d_dbg + 2, &inj, sizeof(inj), cudaMemcpyHostToDevice));
+    }
     else return fail(c, RL_ERR_ARG, std::string("rl_set_option: unknown option ") + name);
     return RL_OK;
 }
@@ -936,6 +950,19 @@ int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out
     RL_CUDA(c, cudaGetLastError());
     c->last_kernel_ms = -1.f;
     cudaEventElapsedTime(&c->last_kernel_ms, c->ev_t0, c->ev_t1);
+    return RL_OK;
+}
+
+int rl_debug_check_failures(rl_ctx* c, uint64_t* out2)
+{
+    if (!c || !out2) return RL_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (!c->d_dbg) return RL_ERR_UNSUPPORTED;    // the product build carries no checks
+    RL_CUDA(c, cudaSetDevice(c->device));
+    RL_CUDA(c, cudaDeviceSynchronize());
+    unsigned long long h[2] = {0, 0};
+    RL_CUDA(c, cudaMemcpy(h, c->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    out2[0] = h[0]; out2[1] = h[1];
     return RL_OK;
 }
 

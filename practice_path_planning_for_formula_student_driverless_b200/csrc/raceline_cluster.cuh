@@ -24,7 +24,7 @@
 namespace rl {
 namespace {
 
-constexpr int kMaxCS = 8;        // portable cluster size limit
+constexpr int kMaxCS = 16;       // 2, 4, 8 are portable cluster sizes; 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed
 constexpr int kcT = 256;         // threads per CTA of the cluster kernel
 constexpr int kcNW = kcT / 32;
 // scratch layout (bytes)
@@ -36,8 +36,9 @@ constexpr int kcRed = 128;                            // [2][kMaxCS][NW][2] doub
 constexpr int kcExF = kcRed + 2 * kMaxCS * kcNW * 16; // [2][NW+1][2] doubles; slot NW = right neighbour CTA's first two samples
 constexpr int kcExL = kcExF + 2 * (kcNW + 1) * 16;    // [2][NW+1][2] doubles; slot NW = left neighbour CTA's last two samples
 constexpr int kcMisc = kcExL + 2 * (kcNW + 1) * 16;   // a few ints
-constexpr int kcBytes = 3072;
-static_assert(kcMisc + 64 <= kcBytes, "cluster scratch layout");
+constexpr int kcEbar = kcMisc + 64;                   // uint64[2]: the two mbarriers of the per-evaluation exchange (even / odd)
+constexpr int kcBytes = 4992;
+static_assert(kcEbar + 16 <= kcBytes && kcEbar % 8 == 0, "cluster scratch layout");
 
 struct Clu {
     uint32_t CS, rank, left, right;
@@ -78,17 +79,64 @@ __device__ __forceinline__ void packed_warp_sum2(double& a, double& b, int lane)
     a = __shfl_sync(kFull, v, 0);
     b = __shfl_sync(kFull, v, 16);
 }
+// sum of the `ne` (<= kMaxCS*NW = 128) partial pairs every CTA holds after an exchange; every lane of every warp of every
+// CTA adds the same pairs in the same order and ends with the same bits
+__device__ __forceinline__ void gather_pairs(const double* sRedPh, int ne, int lane, double& a, double& b)
+{
+    double sa = 0.0, sb = 0.0;
+    if (lane < ne) { const double2 e = *reinterpret_cast<const double2*>(sRedPh + 2 * lane); sa = e.x; sb = e.y; }
+#pragma unroll
+    for (int j = 1; j < (kMaxCS * kcNW) / 32; ++j)
+        if (lane + 32 * j < ne) { const double2 e = *reinterpret_cast<const double2*>(sRedPh + 2 * (lane + 32 * j)); sa += e.x; sb += e.y; }
+    packed_warp_sum2(sa, sb, lane);
+    a = sa; b = sb;
+}
 __device__ __forceinline__ void cluster_sum2(double& a, double& b, double* sRedPh, const Clu& cl, int lane, int warp)
 {
     packed_warp_sum2(a, b, lane);
     if (lane < (int)cl.CS) cl_st2(cl_map(sRedPh + 2 * ((int)cl.rank * kcNW + warp), (uint32_t)lane), a, b);
     cl_sync();
-    const int ne = (int)cl.CS * kcNW;   // <= 64 pairs
-    double sa = 0.0, sb = 0.0;
-    if (lane < ne) { const double2 e = *reinterpret_cast<const double2*>(sRedPh + 2 * lane); sa = e.x; sb = e.y; }
-    if (lane + 32 < ne) { const double2 e = *reinterpret_cast<const double2*>(sRedPh + 2 * (lane + 32)); sa += e.x; sb += e.y; }
-    packed_warp_sum2(sa, sb, lane);   // every lane of every warp of every CTA ends with the same bits
-    a = sa; b = sb;
+    gather_pairs(sRedPh, (int)cl.CS * kcNW, lane, a, b);
+}
+
+// ---- the per-evaluation exchange without a cluster barrier -------------------------------------------------------
+// barrier.cluster makes all CS*256 threads wait for the slowest CTA AND pays a cluster-scope fence (28 % of the stall
+// samples of round 1's kernel).  An evaluation only needs DATA: the CS*NW partial pairs and the two alpha halos of the
+// neighbour CTAs.  So every producer sends its 16 bytes with st.async, which writes into the consumer CTA's shared memory
+// and completes the bytes on the consumer's own mbarrier in one instruction; a consumer waits on its own mbarrier
+// only -- until ITS data is there, not until everybody is done.  Per evaluation and CTA the barrier expects
+// (CS*NW + 2)*16 bytes plus one arrival per local warp (the warps' local warp-edge halos go through plain st.shared).
+// Two barriers alternate (even / odd evaluation): a neighbour that is one evaluation ahead signals the OTHER barrier,
+// and it cannot be two ahead because it needs this CTA's data of the evaluation in between; its bytes may land before
+// this CTA has posted its expect_tx (the tx-count goes negative for a moment, which an mbarrier allows; the phase cannot
+// complete meanwhile because no local warp has arrived yet).
+__device__ __forceinline__ void st_async2(uint32_t remote_addr, double x, double y, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "d"(x), "d"(y),
+                 "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_local(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // cluster-wide OR.  sFlag: int[3] rotating slots (all zero at kernel start); slot advances per call.
@@ -161,6 +209,8 @@ struct PgdCtxC {
     double* sRed; double* sExF; double* sExL;
     double lamJ, armijo_c, step2, J, decp;
     int ph;
+    uint64_t* ebar;     // the two exchange mbarriers of this CTA
+    uint32_t* epar;     // their wait parities (bit b: barrier b), kept by the kernel across outer iterations and jobs
 };
 constexpr int kcRedStride = kMaxCS * kcNW * 2;   // doubles per phase
 constexpr int kcExStride = (kcNW + 1) * 2;
@@ -177,10 +227,44 @@ __device__ __forceinline__ bool pgd_half_c(const Part& pt, const Clu& cl, const 
     eval_window<T, K, MODE>(xa, ha, pt, c.sC0, c.sCp, c.sCm, cL, cR, c.lamJ, Jz, Sd, gh);
     double Jn = fma(c.lamJ, Sd, Jz);
     const double dec2p = project_trial<T, K>(xa, gh, c.step2, sLo, sHi, xb);
-    hb = halo_send_c<K, MODE>(xb, pt, cl, c.sExF + c.ph * kcExStride, c.sExL + c.ph * kcExStride);
     double dec = c.decp;
+#ifdef RL_CLUSTER_BARRIER_EXCHANGE      // round 1's exchange (one barrier.cluster per evaluation), kept for A/B measurements
+    hb = halo_send_c<K, MODE>(xb, pt, cl, c.sExF + c.ph * kcExStride, c.sExL + c.ph * kcExStride);
     cluster_sum2(Jn, dec, c.sRed + c.ph * kcRedStride, cl, pt.lane, pt.warp);
     halo_recv_c(hb, pt, c.sExF + c.ph * kcExStride, c.sExL + c.ph * kcExStride);
+#else
+    {
+        // ---- exchange of this evaluation: halos of the next trial + partial sums, signalled through mbarrier c.ph ----
+        double* sExF = c.sExF + c.ph * kcExStride; double* sExL = c.sExL + c.ph * kcExStride; double* sRedPh = c.sRed + c.ph * kcRedStride;
+        uint64_t* bar = c.ebar + c.ph;
+        double F0, F1, L0, L1;
+        edge_values<K, MODE>(xb, pt.cnt, F0, F1, L0, L1);
+        hb.l0 = __shfl_sync(kFull, L0, pt.srcL);
+        hb.l1 = __shfl_sync(kFull, L1, pt.srcL);
+        hb.r0 = __shfl_sync(kFull, F0, pt.srcR);
+        hb.r1 = __shfl_sync(kFull, F1, pt.srcR);
+        if (pt.lane == 0) {
+            if (pt.warp == 0) st_async2(cl_map(sExF + 2 * kcNW, cl.left), F0, F1, cl_map(bar, cl.left));     // I am the right neighbour of CTA `left`
+            else { sExF[2 * pt.warp] = F0; sExF[2 * pt.warp + 1] = F1; }
+        }
+        if (pt.lane == 31) {
+            if (pt.warp == kcNW - 1) st_async2(cl_map(sExL + 2 * kcNW, cl.right), L0, L1, cl_map(bar, cl.right));
+            else { sExL[2 * pt.warp] = L0; sExL[2 * pt.warp + 1] = L1; }
+        }
+        packed_warp_sum2(Jn, dec, pt.lane);
+        if (pt.lane < (int)cl.CS)
+            st_async2(cl_map(sRedPh + 2 * ((int)cl.rank * kcNW + pt.warp), (uint32_t)pt.lane), Jn, dec, cl_map(bar, (uint32_t)pt.lane));
+        __syncwarp();
+        if (pt.lane == 0) {
+            if (pt.warp == 0) mbar_arrive_expect_local(bar, (uint32_t)((int)cl.CS * kcNW + 2) * 16u);
+            else mbar_arrive_local(bar);
+        }
+        mbar_wait_cluster(bar, (*c.epar >> c.ph) & 1u);
+        *c.epar ^= (1u << c.ph);
+        gather_pairs(sRedPh, (int)cl.CS * kcNW, pt.lane, Jn, dec);
+        halo_recv_c(hb, pt, sExF, sExL);
+    }
+#endif
     c.ph ^= 1;
     dec *= 2.0;                                    // gh is grad/2 (main.cpp:733)
     if (Jn <= c.J + c.armijo_c * dec) {            // Armijo accept, main.cpp:734
@@ -198,13 +282,15 @@ __device__ __forceinline__ PgdOut pgd_outer_c(const Part& pt, const Clu& cl, con
                                               const double (&cL)[3], const double (&cR)[3],
                                               const double* sC0, const double* sCp, const double* sCm, double* sSt,
                                               double* sRed, double* sExF, double* sExL, int& ph,
-                                              double lamJ, double step_init, double step_min, double armijo_c, int max_inner)
+                                              double lamJ, double step_init, double step_min, double armijo_c, int max_inner,
+                                              uint64_t* ebar, uint32_t& epar)
 {
     constexpr int T = kcT;
     PgdOut o; o.acc = 0; o.bt = 0; o.ev = 0;
     PgdCtxC<K> c;
     c.sC0 = sC0; c.sCp = sCp; c.sCm = sCm; c.sSt = sSt; c.sRed = sRed; c.sExF = sExF; c.sExL = sExL;
     c.lamJ = lamJ; c.armijo_c = armijo_c; c.ph = ph;
+    c.ebar = ebar; c.epar = &epar;
     c.step2 = 2.0 * step_init;
     double x[K], y[K];
     Halo hx, hy;
@@ -859,8 +945,12 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
     const int it0 = item_off[cid], it1 = item_off[cid + 1];
     uint32_t bar_phase = 0;
     int fslot = 0, prev_trk = -1;
+    uint64_t* ebar = reinterpret_cast<uint64_t*>(scr + kcEbar);   // per-evaluation exchange barriers: one arrival per local warp + tx bytes
+    uint32_t epar = 0;
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
+        mbar_init(ebar, kcNW);
+        mbar_init(ebar + 1, kcNW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sFlag[0] = 0; sFlag[1] = 0; sFlag[2] = 0;
     }
@@ -1092,7 +1182,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         }
         // =================== projected gradient with Armijo (main.cpp:723-742 / 996-1026) ===================
         const PgdOut po = pgd_outer_c<K, MODE>(pt, cl, sLo, sHi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,
-                                               C.step_init, C.step_min, C.armijo_c, C.max_inner_iters);
+                                               C.step_init, C.step_min, C.armijo_c, C.max_inner_iters, ebar, epar);
         acc_total += po.acc; bt_total += po.bt; ev_total += po.ev;
         if (tid == 0 && cl.rank == 0 && outer < RL_MAX_OUTER_LOG) {
             st->J0[outer] = po.J0; st->Jend[outer] = po.Jend; st->lap_outer[outer] = lap_outer;
@@ -1218,17 +1308,36 @@ int launch_solve_cluster(const DevBatch& B, const int* job_list, const int* item
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (cs > cluster_max_size()) return (int)cudaErrorInvalidConfiguration;
     cudaError_t e;
     if (mode == 1) e = cudaLaunchKernelEx(&cfg, solve_cluster_kernel<K, 1>, B, job_list, item_off, n_items);
     else e = cudaLaunchKernelEx(&cfg, solve_cluster_kernel<K, 0>, B, job_list, item_off, n_items);
     return (int)e;
 }
+namespace { int g_cluster_max = 8; }
+// largest cluster the device schedules for this kernel: 16 (non-portable size, tracks up to 32,768 samples) when the
+// occupancy query says at least one such cluster fits, else the portable 8
+int cluster_max_size() { return g_cluster_max; }
 int configure_solve_cluster()
 {
     const int smem = (int)smem_bytes_cluster(8);
     cudaError_t e = cudaFuncSetAttribute(solve_cluster_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    return (int)e;
+    if (e != cudaSuccess) return (int)e;
+    g_cluster_max = 8;
+    if (cudaFuncSetAttribute(solve_cluster_kernel<8, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(solve_cluster_kernel<8, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16); cfg.blockDim = dim3(kcT); cfg.dynamicSmemBytes = (size_t)smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, solve_cluster_kernel<8, 0>, &cfg) == cudaSuccess && n >= 1) g_cluster_max = 16;
+    }
+    cudaGetLastError();
+    return 0;
 }
 
 }  // namespace rl

@@ -26,6 +26,7 @@ struct DevBatch {
     double* v;
     double* ax;
     rl_job_stats* stats;         // [n_jobs]
+    unsigned long long* dbg;     // debug-checks build only (else null): [0] failures, [1] first failure (code | CTA << 32), [2] fault injection
 };
 
 // Size classes: one CTA of T threads solves one (track, config, stage) job, K samples per thread.
@@ -49,22 +50,28 @@ inline int class_for_n(int n)
 inline size_t smem_bytes_for_class(int T, int K)
 {
     const size_t np = (size_t)T * K;
-    return np * 16      /* path points, double2            */
-           + np * 8 * 4 /* region B: PGD coefficients+stash / ray tile+corridor staging */
-           + 2048       /* barriers, reduction + halo exchange scratch */
-           + np * 6;    /* per-sample corridor state: anchor segments + parity bits (4 B), clearances (2 B) */
+    size_t b = np * 16      /* path points, double2            */
+               + np * 8 * 4 /* region B: PGD coefficients+stash / ray tile+corridor staging */
+               + 2048       /* barriers, reduction + halo exchange scratch */
+               + np * 6;    /* per-sample corridor state: anchor segments + parity bits (4 B), clearances (2 B) */
+#ifdef RL_DEBUG_CHECKS
+    b += 4 * 64 + 2048;     /* four guard zones + the per-thread phase counters (raceline_kernels.cuh) */
+#endif
+    return b;
 }
 
 // Long tracks (N > 4096): one thread-block cluster of `cs` CTAs (256 threads x 8 samples) per job, see
 // raceline_cluster.cuh.  Every CTA of the cluster needs between 512 and 2048 samples.  Returns 0 when no cluster
-// size fits.  `force` > 0 (test hook RL_FORCE_CLUSTER) asks for exactly that size.
-constexpr int kMaxClusterSize = 8;
+// size up to `max_cs` fits.  `force` > 0 (test hook RL_FORCE_CLUSTER) asks for exactly that size.
+constexpr int kMaxClusterSize = 16;
+int cluster_max_size();                  // 16 when the device schedules 16-CTA (non-portable) clusters of the kernel, else 8
 constexpr int kClusterClassBase = 100;   // ClassList.cls = kClusterClassBase + cs for cluster launches
-inline int cluster_size_for_n(long long n, int force = 0)
+inline int cluster_size_for_n(long long n, int force = 0, int max_cs = 8)
 {
-    const int sizes[3] = {2, 4, 8};
-    for (int i = 0; i < 3; ++i) {
+    const int sizes[4] = {2, 4, 8, 16};
+    for (int i = 0; i < 4; ++i) {
         const int cs = sizes[i];
+        if (cs > max_cs) break;
         if (force > 0 && cs != force) continue;
         if (force <= 0 && cs == 2) continue;   // N <= 4096 belongs to the single-CTA kernels
         if (n >= 512ll * cs && n <= 2048ll * cs) return cs;

@@ -47,6 +47,55 @@ constexpr int kScrMisc = kScrExL + 512; // a few ints
 constexpr int kScrBytes = 2048;         // followed by the per-sample corridor hint words [T*K]
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- debug-checks build (-DRL_DEBUG_CHECKS, library variant "_dbg"; compute-sanitizer is not available on the pool) ----
+// Region B of the shared memory changes owner five times per outer iteration (stencil coefficients + stash | ring tile |
+// both rings' vertices | corridor staging | v(s) exchange arrays) and the path area once (path | box bounds); what
+// keeps the owners apart are hand-placed block barriers.  The debug build checks that protocol and the layout:
+//   * phase hand-over: every thread counts the region-B phases it has FINISHED in sDone[tid]; entering a phase (after the
+//     barrier that is supposed to free the region) it checks that the thread with its lane in every warp has finished as
+//     many phases as itself.  A missing or misplaced barrier lets a fast warp enter while a slow one still reads: caught
+//     whenever the timing produces it, reported with the phase code.
+//   * guard zones of 64 bytes with a known pattern between / after the shared-memory regions, verified at every job end;
+//   * bounds asserts where a phase carves its views out of a region.
+// Failures are counted in global memory (rl_debug_check_failures); the solve goes on.
+#ifdef RL_DEBUG_CHECKS
+constexpr int kDbgGap = 64;
+constexpr int kDbgScr = 2048;                 // sDone[T <= 512] behind the ordinary scratch
+constexpr unsigned kDbgCanary = 0xC0FFEE11u;
+enum { kDbgPhCoef = 1, kDbgPhVsweep = 2, kDbgPhVerts = 3, kDbgPhStage = 4, kDbgPhTile = 5, kDbgPhLap = 6 };
+__device__ __noinline__ void dbg_fail(int* sMisc, int code)
+{
+    unsigned long long* g = *reinterpret_cast<unsigned long long**>(sMisc + 24);
+    if (g) { atomicAdd(g, 1ull); atomicCAS(g + 1, 0ull, (unsigned long long)(unsigned)code | ((unsigned long long)blockIdx.x << 32)); }
+}
+__device__ __forceinline__ int* dbg_done(int* sMisc) { return sMisc + (2048 - kScrMisc) / 4; }
+template <int T>
+__device__ __forceinline__ void dbg_enter(int* sMisc, int phase)
+{
+    const int* sDone = dbg_done(sMisc);
+    const int mine = sDone[threadIdx.x], lane = threadIdx.x & 31;
+    bool ok = true;
+#pragma unroll 1
+    for (int w = 0; w < T / 32; ++w) ok = ok && (sDone[w * 32 + lane] >= mine);
+    if (!ok) dbg_fail(sMisc, 1000 + phase);
+}
+__device__ __forceinline__ void dbg_leave(int* sMisc, int phase)
+{
+    int* sDone = dbg_done(sMisc);
+    if (sMisc[27] == phase && sMisc[26] > 0 && threadIdx.x < 32) return;   // fault injection (tests): warp 0 "forgets" to hand this phase over
+    sDone[threadIdx.x] = sDone[threadIdx.x] + 1;
+}
+#define RL_DBG_ENTER(T, sMisc, ph) dbg_enter<T>(sMisc, ph)
+#define RL_DBG_LEAVE(sMisc, ph) dbg_leave(sMisc, ph)
+#define RL_DBG_ASSERT(sMisc, cond, code) do { if (!(cond)) dbg_fail(sMisc, code); } while (0)
+#else
+constexpr int kDbgGap = 0;
+constexpr int kDbgScr = 0;
+#define RL_DBG_ENTER(T, sMisc, ph) do { } while (0)
+#define RL_DBG_LEAVE(sMisc, ph) do { } while (0)
+#define RL_DBG_ASSERT(sMisc, cond, code) do { } while (0)
+#endif
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
 // ---- TMA 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) completed through an mbarrier -------------
@@ -1066,8 +1115,9 @@ __device__ __noinline__ bool inside_ring(const RayTile& tl_in, double2 P, float 
 template <int T, int K>
 __device__ __forceinline__ float ring_tile_build(const Part& pt, double* sB, uint64_t* mbar, uint32_t& bar_phase, int* sMisc,
                                                  const double* __restrict__ gseg, int mr, double ox, double oy,
-                                                 RayTile& tl, bool& closed, bool* linked = nullptr)
+                                                 RayTile& tl, bool& closed, bool* linked = nullptr, bool dbg = false)
 {
+    (void)dbg;
     constexpr int NP = T * K;
     constexpr int CAP = fast_tile_cap(NP);
     const int tid = pt.tid;
@@ -1078,6 +1128,7 @@ __device__ __forceinline__ float ring_tile_build(const Part& pt, double* sB, uin
     tl.segD = segD; tl.segF = segF; tl.boxF = boxF; tl.supF = supF;
     tl.nt = mr; tl.nblk = (mr + SB - 1) / SB; tl.nsup = (tl.nblk + SU - 1) / SU;
     block_sync<T>();
+    if (dbg) { RL_DBG_ENTER(T, sMisc, kDbgPhTile); RL_DBG_ASSERT(sMisc, mr <= CAP, 2001); }
     if (tid == 0) {
         sMisc[0] = 0;
         fence_proxy_async();
@@ -1453,7 +1504,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
             }
             RayTile tl;
             bool chain, linked;   // the ring's segments form a closed chain / consecutive segments share their vertex
-            const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, chain, &linked);
+            const float m0 = ring_tile_build<T, K>(pt, sB, mbar, bar_phase, sMisc, gseg + 4 * base, mr, org.x, org.y, tl, chain, &linked, true);
             if (first && tid == 0) {   // per-ring constants for corridor_update
                 sMisc[8 + ring] = (chain ? 1 : 0) | (linked ? 2 : 0);
                 sMisc[10 + ring] = __float_as_int(m0);
@@ -1594,6 +1645,7 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
                     if (!ex_n) dfn[j] = fmin(dfn[j], dist_r);
                 }
             }
+            RL_DBG_LEAVE(sMisc, kDbgPhTile);     // this thread is done with the ring tile in region B
         }
         if (pass == 0) {
             // a pending "exists, value >= lb" that could undercut the minimum found: redo that sample in full
@@ -1622,10 +1674,12 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
 // corridor bounds from the consecutive mapping (sample tid + j*T) to the blocked layout, through region B
 template <int T, int K>
 __device__ __forceinline__ void corridor_stage_out(const Part& pt, double* sB, const double (&loc)[K], const double (&hic)[K],
-                                                   double (&lo)[K], double (&hi)[K])
+                                                   double (&lo)[K], double (&hi)[K], int* dbgMisc = nullptr)
 {
     constexpr int NP = T * K;
+    (void)dbgMisc;
     block_sync<T>();
+    if (dbgMisc) RL_DBG_ENTER(T, dbgMisc, kDbgPhStage);
     double* sLoS = sB;
     double* sHiS = sB + NP;
 #pragma unroll
@@ -1639,6 +1693,7 @@ __device__ __forceinline__ void corridor_stage_out(const Part& pt, double* sB, c
         lo[k] = 0.0; hi[k] = 0.0;
         if (k < pt.cnt) { lo[k] = sLoS[pt.start + k]; hi[k] = sHiS[pt.start + k]; }
     }
+    if (dbgMisc) RL_DBG_LEAVE(dbgMisc, kDbgPhStage);
     block_sync<T>();
 }
 
@@ -1860,6 +1915,8 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
     float2* F1 = F0 + (M0 + 1);
     const double2 org = sP[0];
     block_sync<T>();   // region B is free
+    RL_DBG_ENTER(T, const_cast<int*>(sMisc), kDbgPhVerts);
+    RL_DBG_ASSERT(const_cast<int*>(sMisc), (size_t)(M0 + M1 + 2) * 24 <= (size_t)T * K * 32, 2002);
     for (int q = tid; q <= M0; q += T) {
         const double2 v = (q < M0) ? *reinterpret_cast<const double2*>(gseg + 4 * (segI0 + q)) : *reinterpret_cast<const double2*>(gseg + 4 * (segI0 + M0 - 1) + 2);
         V0[q] = v; F0[q] = make_float2((float)(v.x - org.x), (float)(v.y - org.y));
@@ -1901,6 +1958,7 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
         if (corridor_update_sample<false>(c, i, cc.x, cc.y, wc, ac, hv, lv, ray_tests)) flagged |= (1u << j);
         else { hic[j] = hv; loc[j] = lv; }
     }
+    RL_DBG_LEAVE(const_cast<int*>(sMisc), kDbgPhVerts);
     return flagged;
 }
 
@@ -1921,15 +1979,29 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
     constexpr bool EXACT = (MODE == kModeExact), OPEN = (MODE == kModeOpen);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* sP = reinterpret_cast<double2*>(smem_raw);
-    double* sB = reinterpret_cast<double*>(smem_raw + (size_t)NP * 16);
-    unsigned char* scr = smem_raw + (size_t)NP * 16 + (size_t)NP * 32;
+    double* sB = reinterpret_cast<double*>(smem_raw + (size_t)NP * 16 + kDbgGap);
+    unsigned char* scr = smem_raw + (size_t)NP * 16 + (size_t)NP * 32 + 2 * kDbgGap;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(scr + kScrBar);
     double* sRed = reinterpret_cast<double*>(scr + kScrRed);
     double* sExF = reinterpret_cast<double*>(scr + kScrExF);
     double* sExL = reinterpret_cast<double*>(scr + kScrExL);
     int* sMisc = reinterpret_cast<int*>(scr + kScrMisc);
-    unsigned* sHint = reinterpret_cast<unsigned*>(scr + kScrBytes);
-    unsigned short* sClr = reinterpret_cast<unsigned short*>(scr + kScrBytes + (size_t)NP * 4);
+    unsigned* sHint = reinterpret_cast<unsigned*>(scr + kScrBytes + kDbgScr + kDbgGap);
+    unsigned short* sClr = reinterpret_cast<unsigned short*>(scr + kScrBytes + kDbgScr + kDbgGap + (size_t)NP * 4);
+#ifdef RL_DEBUG_CHECKS
+    // guard zones: after the path area, after region B, after the scratch (+ sDone), after the per-sample corridor state
+    unsigned* const guard[4] = {reinterpret_cast<unsigned*>(smem_raw + (size_t)NP * 16), reinterpret_cast<unsigned*>(smem_raw + (size_t)NP * 48 + kDbgGap),
+                                reinterpret_cast<unsigned*>(scr + kScrBytes + kDbgScr), reinterpret_cast<unsigned*>(scr + kScrBytes + kDbgScr + kDbgGap + (size_t)NP * 6)};
+    for (int z = 0; z < 4; ++z)
+        for (int q = threadIdx.x; q < kDbgGap / 4; q += T) guard[z][q] = kDbgCanary;
+    for (int q = threadIdx.x; q < 512; q += T) dbg_done(sMisc)[q] = 0;
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<unsigned long long**>(sMisc + 24) = B.dbg;
+        sMisc[26] = B.dbg ? (int)B.dbg[2] : 0;       // fault injection switch (rl_set_option "debug_inject")
+        sMisc[27] = kDbgPhCoef;
+    }
+    __syncthreads();
+#endif
 #ifdef RL_PHASE_TIMERS
     long long* sPh = reinterpret_cast<long long*>(scr + kScrMisc + 128);
 #endif
@@ -2055,7 +2127,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
                 corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
                                           segI0, segO0, segE, guard0, flagged, loc, hic, ray_tests, ex_scans);
         }
-        corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
+        corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi, sMisc);
         if (!same_track)
             fast_update = (sMisc[8] & 2) && (sMisc[9] & 2) && (segO0 - segI0 > 2 * kWin + 1) && (segE - segO0 > 2 * kWin + 1);
     } else if (!ev)
@@ -2106,9 +2178,11 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
 #pragma unroll
             for (int k = 0; k < K; ++k) kap[k] = (k < cnt) ? N0[k] / Wd[k] : 0.0;    // kappa, main.cpp:618
             block_sync<T>();   // region B is free: lo/hi are in registers, coefficients not yet built
+            RL_DBG_ENTER(T, sMisc, kDbgPhVsweep);
             vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed);
             block_sync<T>();
             lap_outer = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32, closed);
+            RL_DBG_LEAVE(sMisc, kDbgPhVsweep);
             ph ^= 1;
             double v_avg = 0.0;
             if (C.time_weight_use_inv_v) {            // main.cpp:951
@@ -2143,6 +2217,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         }
         RL_PH(2);   // v(s) profile + time weights
         // ---- stencil coefficients into region B (slot-major) ----
+        RL_DBG_ENTER(T, sMisc, kDbgPhCoef);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             double c0 = 0.0, cp = 0.0, cm = 0.0;
@@ -2210,6 +2285,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
                 if (outer == max_outer - 1) B.alpha_last[row0 + i] = al;
             }
         }
+        RL_DBG_LEAVE(sMisc, kDbgPhCoef);      // the stash (region B) has been read: the next corridor pass may take the region
         block_sync<T>();
 #pragma unroll
         for (int k = 0; k < K; ++k) if (k < cnt) sP[start + k] = Pn[k];
@@ -2233,7 +2309,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             if (block_or<T>(flagged != 0u))   // some certificate failed (or none exists yet): the searching path rebuilds those samples
                 corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
                                           segI0, segO0, segE, guard, flagged, loc, hic, ray_tests, ex_scans);
-            corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
+            corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi, sMisc);
             RL_PH(7);   // searching path for flagged samples + staging
         } else {
             corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
@@ -2280,9 +2356,11 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             }
         }
         block_sync<T>();
+        RL_DBG_ENTER(T, sMisc, kDbgPhVsweep);
         vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed);
         block_sync<T>();
         lap = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32, closed);
+        RL_DBG_LEAVE(sMisc, kDbgPhVsweep);
         ph ^= 1;
 #pragma unroll
         for (int k = 0; k < K; ++k)
@@ -2303,6 +2381,12 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap; st->exist_scans = (int)es;
         }
     }
+#ifdef RL_DEBUG_CHECKS
+    if (tid == 0)
+        for (int z = 0; z < 4; ++z)
+            for (int q = 0; q < kDbgGap / 4; ++q)
+                if (guard[z][q] != kDbgCanary) { dbg_fail(sMisc, 9000 + z); break; }
+#endif
     RL_PH(8);   // certificates hand-over, final geometry, final v(s) profile, stores
 #ifdef RL_PHASE_TIMERS
     if (tid == 0) for (int i = 0; i < 9; ++i) st->J0[16 + i] = (double)sPh[i];

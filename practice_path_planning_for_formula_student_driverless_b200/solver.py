@@ -308,6 +308,13 @@ class Context:
         self._check(lib().rl_solve_batch(self._h, C.byref(batch.desc), C.byref(batch.out)), "rl_solve_batch")
         return batch
 
+    def debug_check_failures(self):
+        """(count, first failure code, CTA of the first failure) of the -DRL_DEBUG_CHECKS build; raises on the product
+        build (RL_ERR_UNSUPPORTED)."""
+        out = (C.c_uint64 * 2)()
+        self._check(lib().rl_debug_check_failures(self._h, out), "rl_debug_check_failures")
+        return int(out[0]), int(out[1] & 0xffffffff), int(out[1] >> 32)
+
     def last_kernel_ms(self) -> float:
         """Device time of the kernels of the last centerline_geom_batch call on this context (copies excluded)."""
         return float(lib().rl_last_kernel_ms(self._h))
@@ -557,6 +564,74 @@ class CenterlineGeom:
         return self.xy[:self.samples]
 
 
+class PackedGeom:
+    """Host arrays in the rl_geom_desc layout + the matching output arrays (page-locked when a PinnedPool is given):
+    pack once, then `run(ctx)` is exactly one rl_centerline_geom_batch call."""
+
+    def __init__(self, mids: Sequence[np.ndarray], samples: Sequence[int], inner_rings: Sequence[np.ndarray],
+                 outer_rings: Sequence[np.ndarray], closed=True, cfg: Optional[Config] = None, emit_closed_duplicate=True,
+                 pool: Optional[PinnedPool] = None):
+        from ._abi import RlGeomDesc, RlGeomOut
+        cfg = cfg or Config()
+        nt = len(mids)
+        self.n_tracks = nt
+        self.closed_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(closed, dtype=bool), (nt,)).astype(np.int32))
+        mids = [_f64(m, 2) for m in mids]
+        segs = []
+        for a, b in zip(inner_rings, outer_rings):
+            segs += [_f64(a, 4), _f64(b, 4)]
+        self.mid_off = np.zeros(nt + 1, dtype=np.int64)
+        self.mid_off[1:] = np.cumsum([m.shape[0] for m in mids])
+        self.seg_off = np.zeros(2 * nt + 1, dtype=np.int64)
+        self.seg_off[1:] = np.cumsum([g.shape[0] for g in segs])
+        self.mids_xy = np.ascontiguousarray(np.concatenate(mids, axis=0)) if nt else np.zeros((0, 2))
+        self.seg = np.ascontiguousarray(np.concatenate(segs, axis=0)) if segs else np.zeros((0, 4))
+        zeros = (lambda shape: pool.empty(shape, np.float64)) if pool else (lambda shape: np.zeros(shape))
+        if pool:
+            self.mids_xy, self.seg = pool.copy(self.mids_xy), pool.copy(self.seg)
+        self.samples = np.ascontiguousarray(np.asarray(samples, dtype=np.int32).reshape(nt))
+        self.params = cfg.to_params()
+        d = RlGeomDesc()
+        d.n_tracks, d.emit_closed_duplicate = nt, int(bool(emit_closed_duplicate))
+        d.mid_off, d.mids_xy, d.samples, d.track_closed = _ptr(self.mid_off), _ptr(self.mids_xy), _ptr(self.samples), _ptr(self.closed_arr)
+        d.seg_off, d.seg, d.params = _ptr(self.seg_off), _ptr(self.seg), C.cast(C.pointer(self.params), C.c_void_p)
+        self.desc = d
+        self.off = np.zeros(nt + 1, dtype=np.int64)
+        st = lib().rl_geom_row_offsets(C.byref(d), self.off.ctypes.data_as(C.POINTER(C.c_int64)))
+        if st != RL_OK:
+            raise RacelineError(st, "rl_geom_row_offsets")
+        rows = int(self.off[nt])
+        self.rows = rows
+        self.arr = {k: zeros(rows) for k in ("s_rel", "heading", "curvature", "dist_inner", "dist_outer", "width", "v_kappa")}
+        self.xy, self.L, self.s0 = zeros((rows, 2)), np.zeros(nt), np.zeros(nt)
+        o = RlGeomOut()
+        o.xy, o.track_L, o.track_s0 = _ptr(self.xy), _ptr(self.L), _ptr(self.s0)
+        for k, a in self.arr.items():
+            setattr(o, k, _ptr(a))
+        self.out = o
+
+    @property
+    def h2d_bytes(self):
+        return int(self.mids_xy.nbytes + self.seg.nbytes + self.mid_off.nbytes + self.seg_off.nbytes + self.samples.nbytes + self.closed_arr.nbytes)
+
+    @property
+    def d2h_bytes(self):
+        return int(self.rows * 9 * 8 + self.n_tracks * 16)
+
+    def run(self, ctx: "Context"):
+        ctx._check(lib().rl_centerline_geom_batch(ctx._h, C.byref(self.desc), C.byref(self.out)), "rl_centerline_geom_batch")
+        return self
+
+    def results(self) -> List["CenterlineGeom"]:
+        out, arr = [], self.arr
+        for t in range(self.n_tracks):
+            a, b = int(self.off[t]), int(self.off[t + 1])
+            out.append(CenterlineGeom(self.xy[a:b], arr["s_rel"][a:b], arr["heading"][a:b], arr["curvature"][a:b], arr["dist_inner"][a:b],
+                                      arr["dist_outer"][a:b], arr["width"][a:b], arr["v_kappa"][a:b], float(self.L[t]), float(self.s0[t]),
+                                      int(self.samples[t])))
+        return out
+
+
 def centerline_geom_batch(mids: Sequence[np.ndarray], samples: Sequence[int], inner_rings: Sequence[np.ndarray],
                           outer_rings: Sequence[np.ndarray], closed=True, cfg: Optional[Config] = None,
                           ctx: Optional[Context] = None, emit_closed_duplicate=True,
@@ -565,46 +640,8 @@ def centerline_geom_batch(mids: Sequence[np.ndarray], samples: Sequence[int], in
     batch of tracks: ordered mid points in, centre line + heading/curvature/ring distances/width/v_kappa rows out.
     `inner_rings` / `outer_rings` are segment arrays (ring_edges / polyline_edges of the *_from_mids points).
     With a PinnedPool the packed inputs and the output rows are page-locked (copies at PCIe speed)."""
-    from ._abi import RlGeomDesc, RlGeomOut
-    cfg = cfg or Config()
     ctx = ctx or default_context()
-    nt = len(mids)
-    closed_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(closed, dtype=bool), (nt,)).astype(np.int32))
-    mids = [_f64(m, 2) for m in mids]
-    segs = []
-    for a, b in zip(inner_rings, outer_rings):
-        segs += [_f64(a, 4), _f64(b, 4)]
-    mid_off = np.zeros(nt + 1, dtype=np.int64)
-    mid_off[1:] = np.cumsum([m.shape[0] for m in mids])
-    seg_off = np.zeros(2 * nt + 1, dtype=np.int64)
-    seg_off[1:] = np.cumsum([g.shape[0] for g in segs])
-    mids_xy = np.ascontiguousarray(np.concatenate(mids, axis=0)) if nt else np.zeros((0, 2))
-    seg = np.ascontiguousarray(np.concatenate(segs, axis=0)) if segs else np.zeros((0, 4))
-    zeros = (lambda shape: pool.empty(shape, np.float64)) if pool else (lambda shape: np.zeros(shape))
-    if pool:
-        mids_xy, seg = pool.copy(mids_xy), pool.copy(seg)
-    smp = np.ascontiguousarray(np.asarray(samples, dtype=np.int32).reshape(nt))
-    p = cfg.to_params()
-    d = RlGeomDesc()
-    d.n_tracks, d.emit_closed_duplicate = nt, int(bool(emit_closed_duplicate))
-    d.mid_off, d.mids_xy, d.samples, d.track_closed = _ptr(mid_off), _ptr(mids_xy), _ptr(smp), _ptr(closed_arr)
-    d.seg_off, d.seg, d.params = _ptr(seg_off), _ptr(seg), C.cast(C.pointer(p), C.c_void_p)
-    off = np.zeros(nt + 1, dtype=np.int64)
-    ctx._check(lib().rl_geom_row_offsets(C.byref(d), off.ctypes.data_as(C.POINTER(C.c_int64))), "rl_geom_row_offsets")
-    rows = int(off[nt])
-    arr = {k: zeros(rows) for k in ("s_rel", "heading", "curvature", "dist_inner", "dist_outer", "width", "v_kappa")}
-    xy, Lv, s0 = zeros((rows, 2)), np.zeros(nt), np.zeros(nt)
-    o = RlGeomOut()
-    o.xy, o.track_L, o.track_s0 = _ptr(xy), _ptr(Lv), _ptr(s0)
-    for k, a in arr.items():
-        setattr(o, k, _ptr(a))
-    ctx._check(lib().rl_centerline_geom_batch(ctx._h, C.byref(d), C.byref(o)), "rl_centerline_geom_batch")
-    out = []
-    for t in range(nt):
-        a, b = int(off[t]), int(off[t + 1])
-        out.append(CenterlineGeom(xy[a:b], arr["s_rel"][a:b], arr["heading"][a:b], arr["curvature"][a:b], arr["dist_inner"][a:b],
-                                  arr["dist_outer"][a:b], arr["width"][a:b], arr["v_kappa"][a:b], float(Lv[t]), float(s0[t]), int(smp[t])))
-    return out
+    return PackedGeom(mids, samples, inner_rings, outer_rings, closed, cfg, emit_closed_duplicate, pool).run(ctx).results()
 
 
 def synth_tracks(n_tracks, n_samples, m_per_ring=None, seed_base=0xB200, first_id=0, threads=0, pool=None):

@@ -110,3 +110,23 @@ def test_baseline_config5_shape(ctx):
         return
     tr = rl.Track(center.reshape(nt, n, 2)[1], seg.reshape(nt, 2, m, 4)[1, 0], seg.reshape(nt, 2, m, 4)[1, 1], L[1])
     _check(first[3], tr, MT, cfg, ("config5", 1, MT))
+
+
+def test_track_longer_than_16384_on_a_16_cta_cluster(ctx):
+    """The reference solver has no length cap (N = center.size(), main.cpp:689).  Closed tracks of 16,385 .. 32,768
+    samples run on a 16-CTA thread-block cluster (a non-portable cluster size the launch has to opt in to); the test
+    skips where the device does not schedule such clusters.  Few cones per ring so that the brute-force oracle
+    (O(N*M) per corridor build) stays within seconds."""
+    n, m_ring = 20000, 400
+    center, seg, L, m = rl.synth_tracks(1, n, m_ring, seed_base=0x16C7)
+    tr = rl.Track(center.reshape(n, 2), seg.reshape(2, m, 4)[0], seg.reshape(2, m, 4)[1], float(L[0]))
+    cfg = rl.Config()
+    try:
+        res = rl.solve_batch([tr], [cfg], [(0, 0, MC), (0, 0, MT)], ctx=ctx)
+    except rl.RacelineError as e:
+        if e.status == rl.RL_ERR_UNSUPPORTED:
+            pytest.skip("this device does not schedule 16-CTA clusters of the kernel")
+        raise
+    for st, r in zip((MC, MT), res):
+        assert r.stats.status == 0 and r.stats.n == n
+        _check(r, tr, st, cfg, ("16-CTA cluster", n, st))

@@ -171,7 +171,7 @@ def test_errors_and_unsupported(ctx, goldens):
     with pytest.raises(rl.RacelineError) as e:
         rl.solve_batch([tr], [rl.Config()], [(0, 0, 7)], ctx=ctx)
     assert e.value.status == rl.RL_ERR_ARG
-    big = rl.Track(np.zeros((20000, 2)), tr.inner_seg, tr.outer_seg, 36000.0)    # N > 16384: beyond one portable cluster
+    big = rl.Track(np.zeros((40000, 2)), tr.inner_seg, tr.outer_seg, 72000.0)    # N > 32,768: beyond one 16-CTA cluster
     with pytest.raises(rl.RacelineError) as e:
         rl.solve_batch([big], [rl.Config()], [(0, 0, MC)], ctx=ctx)
     assert e.value.status == rl.RL_ERR_UNSUPPORTED

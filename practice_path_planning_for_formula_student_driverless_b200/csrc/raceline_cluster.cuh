@@ -164,9 +164,9 @@ __device__ __forceinline__ void normal_c(const PathView& pv, int il, double& nx,
     const double2 Pm = pv.at(il - 1), Pp = pv.at(il + 1);
     normal_from_tangent((Pp.x - Pm.x) * 0.5, (Pp.y - Pm.y) * 0.5, nx, ny);   // main.cpp:584-592
 }
-__device__ __forceinline__ void derivs_c(const PathView& pv, int il, double h, double& xp, double& yp, double& xpp, double& ypp)
+__device__ __forceinline__ void derivs_c(const PathView& pv, int il, const HStep& H, double& xp, double& yp, double& xpp, double& ypp)
 {
-    derivs_central(pv.at(il - 1), pv.at(il), pv.at(il + 1), h, xp, yp, xpp, ypp);
+    derivs_central(pv.at(il - 1), pv.at(il), pv.at(il + 1), H, xp, yp, xpp, ypp);
 }
 // publish the chunk's end points into the neighbours' halo slots (followed by a cluster barrier)
 __device__ __forceinline__ void exchange_path_halo(const double2* sP, double2* sHalo, const Clu& cl, int tid)
@@ -1022,11 +1022,12 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         const double a_total = C.use_total_ge_lat ? fmax(C.a_total_max, C.a_lat_max) : C.a_total_max;   // main.cpp:802-804
         q.a_tot2 = a_total * a_total;
     }
-    q.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; q.Fr = C.mass_kg * 9.81 * C.c_rr; q.mass = C.mass_kg; q.P = C.P_max_W;
+    q.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; q.Fr = C.mass_kg * 9.81 * C.c_rr; q.mass = C.mass_kg; q.inv_mass = 1.0 / C.mass_kg; q.P = C.P_max_W;
     q.acc_cap = C.a_long_acc_cap; q.brk_cap = C.a_long_brake_cap; q.h = h; q.has_power = (C.P_max_W > 0);
 
     const long long segI0 = B.seg_off[2 * trk], segO0 = B.seg_off[2 * trk + 1], segE = B.seg_off[2 * trk + 2];
-    const double inv2h = 1.0 / (2 * h), invh2 = 1.0 / (h * h);          // DiffOps, main.cpp:547
+    const HStep H(h);
+    const double inv2h = H.inv2h, invh2 = H.invh2;                       // DiffOps, main.cpp:547
     const double lamJ = C.lambda_smooth * inv2h * inv2h;
     long long ray_tests = 0;
     int vrounds = 0, ph = 0;
@@ -1080,7 +1081,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
                 const int il = start + k;
                 double nx, ny, xp, yp, xpp, ypp;
                 normal_c(pv, il, nx, ny);
-                derivs_c(pv, il, h, xp, yp, xpp, ypp);
+                derivs_c(pv, il, H, xp, yp, xpp, ypp);
                 A1[k] = nx * ypp - ny * xpp;          // main.cpp:644-646
                 A2[k] = xp * ny - yp * nx;
                 N0[k] = xp * ypp - yp * xpp;
@@ -1254,7 +1255,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             if (k < cnt) {
                 const int il = start + k;
                 double xp, yp, xpp, ypp;
-                derivs_c(pv, il, h, xp, yp, xpp, ypp);
+                derivs_c(pv, il, H, xp, yp, xpp, ypp);
                 kap[k] = (xp * ypp - yp * xpp) / pow15(xp * xp + yp * yp);
                 B.heading[row0 + il] = atan2(yp, xp);
                 B.curvature[row0 + il] = kap[k];

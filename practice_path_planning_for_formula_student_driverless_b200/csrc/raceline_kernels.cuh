@@ -207,13 +207,13 @@ struct Part {
 constexpr int kModeClosed = 0, kModeExact = 1, kModeOpen = 2;
 
 // tangent -> unit normal with the degenerate-case rules of main.cpp:588-592
+// One square root and one reciprocal: |(-ty, tx)| = |(tx, ty)|, so the reference's two length tests coincide (after its
+// first fix-up t := (1, 0) the second can never fire), and nv / len is taken as nv * (1 / len) (<= 1 ulp apart).
 __device__ __forceinline__ void normal_from_tangent(double tx, double ty, double& nx, double& ny)
 {
-    if (sqrt(tx * tx + ty * ty) < 1e-15) { tx = 1.0; ty = 0.0; }
-    const double nvx = -ty, nvy = tx;
-    const double len = sqrt(nvx * nvx + nvy * nvy);
-    if (len < 1e-15) { nx = 0.0; ny = 0.0; }
-    else { nx = nvx / len; ny = nvy / len; }
+    const double len = sqrt(ty * ty + tx * tx);
+    if (len < 1e-15) { nx = -0.0; ny = 1.0; }       // t := (1, 0)  ->  n = (-0, 1)
+    else { const double r = 1.0 / len; nx = -ty * r; ny = tx * r; }
 }
 // normals_from_points_generic, main.cpp:581-593 (closed: periodic central difference; open: one-sided ends)
 __device__ __forceinline__ void normal_at(const double2* sP, int i, int N, bool closed, double& nx, double& ny)
@@ -228,29 +228,33 @@ __device__ __forceinline__ void normal_at(const double2* sP, int i, int N, bool 
     else { tx = (sP[i + 1].x - sP[i - 1].x) * 0.5; ty = (sP[i + 1].y - sP[i - 1].y) * 0.5; }
     normal_from_tangent(tx, ty, nx, ny);
 }
+// the sample spacing and its reciprocals, formed once per job: the difference quotients below multiply by them
+// (the reference divides by 2h, h*h and h; <= 1 ulp apart, and six FP64 divisions per sample and outer iteration fewer)
+struct HStep {
+    double h, inv_h, inv2h, invh2;
+    __device__ __forceinline__ explicit HStep(double hh) : h(hh), inv_h(1.0 / hh), inv2h(1.0 / (2 * hh)), invh2(1.0 / (hh * hh)) {}
+};
 // central-difference derivatives of the `deriv` lambda (interior / periodic case), main.cpp:599-603 / 625-629
-__device__ __forceinline__ void derivs_central(double2 Pm, double2 Pc, double2 Pp, double h,
+__device__ __forceinline__ void derivs_central(double2 Pm, double2 Pc, double2 Pp, const HStep& H,
                                                double& xp, double& yp, double& xpp, double& ypp)
 {
-    const double h2 = 2 * h, hh = h * h;
-    xp = (Pp.x - Pm.x) / h2; yp = (Pp.y - Pm.y) / h2;
-    xpp = (Pp.x - 2 * Pc.x + Pm.x) / hh; ypp = (Pp.y - 2 * Pc.y + Pm.y) / hh;
+    xp = (Pp.x - Pm.x) * H.inv2h; yp = (Pp.y - Pm.y) * H.inv2h;
+    xpp = (Pp.x - 2 * Pc.x + Pm.x) * H.invh2; ypp = (Pp.y - 2 * Pc.y + Pm.y) * H.invh2;
 }
 // the `deriv` lambda, main.cpp:599-613 / 625-639
-__device__ __forceinline__ void derivs_at(const double2* sP, int i, int N, double h, bool closed,
+__device__ __forceinline__ void derivs_at(const double2* sP, int i, int N, const HStep& H, bool closed,
                                           double& xp, double& yp, double& xpp, double& ypp)
 {
     if (N == 1) { xp = 1.0; yp = 0.0; xpp = 0.0; ypp = 0.0; return; }
-    const double h2 = 2 * h, hh = h * h;
     if (closed || (i > 0 && i < N - 1)) {
-        derivs_central(sP[(i == 0) ? N - 1 : i - 1], sP[i], sP[(i == N - 1) ? 0 : i + 1], h, xp, yp, xpp, ypp);
+        derivs_central(sP[(i == 0) ? N - 1 : i - 1], sP[i], sP[(i == N - 1) ? 0 : i + 1], H, xp, yp, xpp, ypp);
     } else if (i == 0) {
-        xp = (sP[1].x - sP[0].x) / h; yp = (sP[1].y - sP[0].y) / h;
-        if (N >= 3) { xpp = (sP[2].x - 2 * sP[1].x + sP[0].x) / hh; ypp = (sP[2].y - 2 * sP[1].y + sP[0].y) / hh; }
+        xp = (sP[1].x - sP[0].x) * H.inv_h; yp = (sP[1].y - sP[0].y) * H.inv_h;
+        if (N >= 3) { xpp = (sP[2].x - 2 * sP[1].x + sP[0].x) * H.invh2; ypp = (sP[2].y - 2 * sP[1].y + sP[0].y) * H.invh2; }
         else { xpp = 0.0; ypp = 0.0; }
     } else {
-        xp = (sP[N - 1].x - sP[N - 2].x) / h; yp = (sP[N - 1].y - sP[N - 2].y) / h;
-        if (N >= 3) { xpp = (sP[N - 1].x - 2 * sP[N - 2].x + sP[N - 3].x) / hh; ypp = (sP[N - 1].y - 2 * sP[N - 2].y + sP[N - 3].y) / hh; }
+        xp = (sP[N - 1].x - sP[N - 2].x) * H.inv_h; yp = (sP[N - 1].y - sP[N - 2].y) * H.inv_h;
+        if (N >= 3) { xpp = (sP[N - 1].x - 2 * sP[N - 2].x + sP[N - 3].x) * H.invh2; ypp = (sP[N - 1].y - 2 * sP[N - 2].y + sP[N - 3].y) * H.invh2; }
         else { xpp = 0.0; ypp = 0.0; }
     }
 }
@@ -263,7 +267,7 @@ __device__ __forceinline__ double pow15(double q)
 
 // ---- v(s) profile pieces: the ax_max_at lambda, main.cpp:797-824 -----------------------------------
 struct VPar {
-    double v_cap, a_lat_max, kappa_eps, a_tot2, kd, Fr, mass, P, acc_cap, brk_cap, h;
+    double v_cap, a_lat_max, kappa_eps, a_tot2, kd, Fr, mass, inv_mass, P, acc_cap, brk_cap, h;
     int has_power;
 };
 __device__ __forceinline__ double f_acc(const VPar& q, double vi, double ki)
@@ -272,7 +276,7 @@ __device__ __forceinline__ double f_acc(const VPar& q, double vi, double ki)
     const double a_res = sqrt(fmax(0.0, q.a_tot2 - alat * alat));
     const double Fd = q.kd * vi * vi;
     double a_power = 1e9;
-    if (q.has_power && vi > 1e-6) a_power = q.P / (q.mass * vi) - (Fd + q.Fr) / q.mass;
+    if (q.has_power && vi > 1e-6) a_power = q.P / (q.mass * vi) - (Fd + q.Fr) * q.inv_mass;
     double a_acc = fmin(fmin(a_res, q.acc_cap), a_power);
     a_acc = fmax(0.0, a_acc);
     return sqrt(fmax(0.0, vi * vi + 2.0 * a_acc * q.h));
@@ -282,7 +286,7 @@ __device__ __forceinline__ double f_brk(const VPar& q, double vi, double ki)
     const double alat = vi * vi * fabs(ki);
     const double a_res = sqrt(fmax(0.0, q.a_tot2 - alat * alat));
     const double Fd = q.kd * vi * vi;
-    double a_brk = fmin(a_res, q.brk_cap) + (Fd + q.Fr) / q.mass;
+    double a_brk = fmin(a_res, q.brk_cap) + (Fd + q.Fr) * q.inv_mass;
     a_brk = fmax(0.0, a_brk);
     return sqrt(fmax(0.0, vi * vi + 2.0 * a_brk * q.h));
 }
@@ -1745,7 +1749,10 @@ __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, doub
     } else normal_at(sP, i, c.N, c.closed, nx, ny);
     const unsigned hw = reinterpret_cast<const unsigned*>(smem_raw + c.oHint)[i];
     const unsigned cw = reinterpret_cast<const unsigned short*>(smem_raw + c.oClr)[i];
-    const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
+    // upper bound of the sample's displacement from the centre line, in FP32: the components are rounded up, the few
+    // ulps sqrtf / fmaf may lose are covered by the factor (the bound only has to be conservative)
+    const float dfx = __double2float_ru(fabs(Pc.x - cx0)), dfy = __double2float_ru(fabs(Pc.y - cy0));
+    const float disp = sqrtf(fmaf(dfx, dfx, dfy * dfy)) * (1.f + 2e-6f);
     const float px = (float)(Pc.x - c.ox), py = (float)(Pc.y - c.oy), fnx = (float)nx, fny = (float)ny;
     const float pmax = 2e-6f * fmaxf(fabsf(px), fabsf(py)) + 1e-5f;
     bool flag = false;
@@ -2082,11 +2089,12 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         const double a_total = C.use_total_ge_lat ? fmax(C.a_total_max, C.a_lat_max) : C.a_total_max;   // main.cpp:802-804
         q.a_tot2 = a_total * a_total;
     }
-    q.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; q.Fr = C.mass_kg * 9.81 * C.c_rr; q.mass = C.mass_kg; q.P = C.P_max_W;
+    q.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; q.Fr = C.mass_kg * 9.81 * C.c_rr; q.mass = C.mass_kg; q.inv_mass = 1.0 / C.mass_kg; q.P = C.P_max_W;
     q.acc_cap = C.a_long_acc_cap; q.brk_cap = C.a_long_brake_cap; q.h = h; q.has_power = (C.P_max_W > 0);
 
     const long long segI0 = B.seg_off[2 * trk], segO0 = B.seg_off[2 * trk + 1], segE = B.seg_off[2 * trk + 2];
-    const double inv2h = 1.0 / (2 * h), invh2 = 1.0 / (h * h);          // DiffOps, main.cpp:547
+    const HStep H(h);
+    const double inv2h = H.inv2h, invh2 = H.invh2;                       // DiffOps, main.cpp:547
     const double lamJ = C.lambda_smooth * inv2h * inv2h;
     long long ray_tests = 0;
     int vrounds = 0, ph = 0, ex_scans = 0;
@@ -2150,7 +2158,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
                 const int i = start + k;
                 double nx, ny, xp, yp, xpp, ypp;
                 normal_at(sP, i, N, closed, nx, ny);
-                derivs_at(sP, i, N, h, closed, xp, yp, xpp, ypp);
+                derivs_at(sP, i, N, H, closed, xp, yp, xpp, ypp);
                 A1[k] = nx * ypp - ny * xpp;          // main.cpp:644-646
                 A2[k] = xp * ny - yp * nx;
                 N0[k] = xp * ypp - yp * xpp;
@@ -2336,7 +2344,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         const int i = tid + j * T;
         if (i < N) {
             double xp, yp, xpp, ypp;
-            derivs_at(sP, i, N, h, closed, xp, yp, xpp, ypp);
+            derivs_at(sP, i, N, H, closed, xp, yp, xpp, ypp);
             B.heading[row0 + i] = atan2(yp, xp);
             B.curvature[row0 + i] = (xp * ypp - yp * xpp) / pow15(xp * xp + yp * yp);
         }
@@ -2351,7 +2359,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             if (k < cnt) {
                 const int i = start + k;
                 double xp, yp, xpp, ypp;
-                derivs_at(sP, i, N, h, closed, xp, yp, xpp, ypp);
+                derivs_at(sP, i, N, H, closed, xp, yp, xpp, ypp);
                 kap[k] = (xp * ypp - yp * xpp) / pow15(xp * xp + yp * yp);
             }
         }

@@ -19,6 +19,16 @@ TOL_V = 1e-4
 TOL_LAP_REL = 1e-5
 
 
+# how often the backtrack-count assertion was waived because the oracle itself stalled (test_gpu_parity.stalled)
+STALLED_TALLY = {"asked": 0, "stalled": 0}
+
+
+def pytest_terminal_summary(terminalreporter):
+    if STALLED_TALLY["asked"]:
+        terminalreporter.write_line(f"backtrack-count assertions: {STALLED_TALLY['asked'] - STALLED_TALLY['stalled']} checked, "
+                                    f"{STALLED_TALLY['stalled']} waived (the oracle's own iteration stalled at rounding level)")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

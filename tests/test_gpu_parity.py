@@ -33,8 +33,13 @@ def oracle_ref(stage, tr, params):
 def stalled(st):
     """True when some outer iteration of the oracle made no progress beyond rounding noise (e.g. the N=16
     synthetic track is an exact circle): the Armijo test then compares numbers that differ in the last bit
-    and the backtrack count is not a property of the algorithm any more."""
-    return any(abs(st.J0[o] - st.Jend[o]) <= 1e-12 * abs(st.J0[o]) for o in range(st.outer_done))
+    and the backtrack count is not a property of the algorithm any more.  Every call is tallied; the totals are
+    printed at the end of the session (conftest.pytest_terminal_summary)."""
+    from conftest import STALLED_TALLY
+    hit = any(abs(st.J0[o] - st.Jend[o]) <= 1e-12 * abs(st.J0[o]) for o in range(st.outer_done))
+    STALLED_TALLY["asked"] += 1
+    STALLED_TALLY["stalled"] += int(hit)
+    return hit
 
 
 def test_shipped_maps_batched_parity(ctx, goldens):

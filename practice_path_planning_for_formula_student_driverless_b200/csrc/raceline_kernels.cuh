@@ -303,7 +303,7 @@ __device__ __forceinline__ double f_brk(const VPar& q, double vi, double ki)
 // sX: 6*T doubles of exchange space.  Returns v[] (blocked); *rounds += relaxation rounds.
 template <int T, int K>
 __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, const double (&kap)[K], double (&v)[K],
-                                                 int max_iters, double* sX, int& rounds, bool closed)
+                                                 int max_iters, double* sX, int& rounds, bool closed, double (&vkap)[K])
 {
     double* sVL = sX;           // [2][T] last-slot value of each thread
     double* sVF = sX + 2 * T;   // [2][T] first-slot value
@@ -313,8 +313,10 @@ __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, 
     const bool act = cnt > 0;
     const bool hasL = act && tid > 0, hasR = act && tid < pt.Tact - 1;
 #pragma unroll
-    for (int k = 0; k < K; ++k)
-        v[k] = (k < cnt) ? fmin(q.v_cap, sqrt(q.a_lat_max / fmax(fabs(kap[k]), q.kappa_eps))) : 0.0;   // main.cpp:787-794
+    for (int k = 0; k < K; ++k) {
+        vkap[k] = (k < cnt) ? sqrt(q.a_lat_max / fmax(fabs(kap[k]), q.kappa_eps)) : 0.0;   // also the v_kappa of the time weights (main.cpp:956)
+        v[k] = (k < cnt) ? fmin(q.v_cap, vkap[k]) : 0.0;                                  // main.cpp:787-794
+    }
     {
         double kl = kap[0];
 #pragma unroll
@@ -2162,7 +2164,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
                 A1[k] = nx * ypp - ny * xpp;          // main.cpp:644-646
                 A2[k] = xp * ny - yp * nx;
                 N0[k] = xp * ypp - yp * xpp;
-                Wd[k] = pow15(xp * xp + yp * yp);     // denom; W = 1/denom (main.cpp:647-648)
+                Wd[k] = 1.0 / pow15(xp * xp + yp * yp);   // W = 1/denom (main.cpp:647-648)
             }
         }
         // ---- park the path in global memory (the job's xy rows) while the PGD runs: its shared-memory
@@ -2182,12 +2184,12 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         RL_PH(1);   // linearisation + parking the path
         if (mt) {
             // ============ v(s) profile + time weights (main.cpp:944-977) ============
-            double kap[K], vv[K], axd[K];
+            double kap[K], vv[K], axd[K], vkap[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) kap[k] = (k < cnt) ? N0[k] / Wd[k] : 0.0;    // kappa, main.cpp:618
+            for (int k = 0; k < K; ++k) kap[k] = (k < cnt) ? N0[k] * Wd[k] : 0.0;    // kappa = N0 / denom, main.cpp:618
             block_sync<T>();   // region B is free: lo/hi are in registers, coefficients not yet built
             RL_DBG_ENTER(T, sMisc, kDbgPhVsweep);
-            vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed);
+            vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed, vkap);
             block_sync<T>();
             lap_outer = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32, closed);
             RL_DBG_LEAVE(sMisc, kDbgPhVsweep);
@@ -2204,7 +2206,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 if (k < cnt) {                         // main.cpp:954-975
-                    const double vk = sqrt(C.a_lat_max / fmax(fabs(kap[k]), C.kappa_eps));
+                    const double vk = vkap[k];     // sqrt(a_lat_max / max(|kappa|, kappa_eps)), main.cpp:956
                     double r = fmin(1.0, vv[k] / fmax(1e-6, vk));
                     r = r * r;
                     r = fmin(1.0, fmax(0.0, r));
@@ -2230,7 +2232,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         for (int k = 0; k < K; ++k) {
             double c0 = 0.0, cp = 0.0, cm = 0.0;
             if (k < cnt) {
-                const double gw = gam[k] / Wd[k];
+                const double gw = gam[k] * Wd[k];
                 c0 = gw * N0[k];
                 const double c1 = gw * A1[k] * inv2h, c2 = gw * A2[k] * invh2;
                 cp = c1 + c2; cm = c2 - c1;
@@ -2352,7 +2354,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
     double lap = 0.0;
     if (mt) {
         // final v(s) profile (main.cpp:1047)
-        double kap[K], vv[K], axd[K];
+        double kap[K], vv[K], axd[K], vkap[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             kap[k] = 0.0;
@@ -2365,7 +2367,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         }
         block_sync<T>();
         RL_DBG_ENTER(T, sMisc, kDbgPhVsweep);
-        vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed);
+        vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed, vkap);
         block_sync<T>();
         lap = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32, closed);
         RL_DBG_LEAVE(sMisc, kDbgPhVsweep);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -123,6 +124,39 @@ namespace {
 
 int c_sm(const rl_batch* b);
 
+// Length of the job chains of one launch.  A chain of c jobs on one track saves every job after the first the corridor
+// search of its first build (measured: about a fifth of a job), but the launch has c times fewer items to spread over
+// the CTA slots of the device.  Pick the c that minimises the modelled time: one item's cost(c) = c - (c - 1) * saving
+// job units, times the waves the items need -- items / slots plus half a wave of tail when there are several waves
+// (CTAs finish at different times and, in the pipelined path, the next chunk's launch fills the tail), exactly one when
+// all items are resident at once.  `max_run` = the longest run of consecutive jobs on one track.
+int pick_chain(size_t n_jobs, int slots, int max_chain, int max_run)
+{
+    constexpr double kChainSaving = 0.2;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int c = 1; c <= std::max(1, std::min(max_chain, max_run)); ++c) {
+        const double items = std::ceil((double)n_jobs / c);
+        const double waves = (items <= (double)slots) ? 1.0 : items / (double)std::max(1, slots) + 0.5;
+        const double cost = waves * ((double)c - (double)(c - 1) * kChainSaving);
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+template <class Jobs>
+int longest_run(const rl_batch_desc* d, const Jobs& list)
+{
+    int best = 0, run = 0, last_t = -1;
+    for (size_t q = 0; q < list.size(); ++q) {
+        const rl_job& jb = d->jobs[list[q]];
+        if (jb.stage == RL_STAGE_EVAL) { run = 0; last_t = -1; continue; }
+        run = (jb.track == last_t) ? run + 1 : 1;
+        last_t = jb.track;
+        best = std::max(best, run);
+    }
+    return best;
+}
+
 int fail(rl_ctx* c, int status, const std::string& msg)
 {
     if (c) c->err = msg;
@@ -237,10 +271,7 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
         for (int k = 0; k < rl::kNumClasses * 3; ++k) {
             if (bucket[k].empty()) continue;
             const int slots = std::max(1, c_sm(b) * rl::ctas_per_sm(k / 3));
-            // a chain saves every job after the first the corridor search of its first build: worth more than the
-            // load balance of the tail as soon as the items still fill the device twice
-            int chain = std::max(1, std::min(max_chain, (int)(bucket[k].size() / (size_t)(6 * slots))));
-            if (chain < 2 && bucket[k].size() >= (size_t)(4 * slots)) chain = std::min(2, max_chain);
+            int chain = pick_chain(bucket[k].size(), slots, max_chain, longest_run(d, bucket[k]));
             if (force_chain > 0) chain = force_chain;
             ClassList l = {k / 3, k % 3, (int)b->joblist.size(), (int)bucket[k].size(), c, (int)b->itemoff.size(), 0};
             int run = 0, last_t = -1;
@@ -258,8 +289,7 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
             if (cbucket[k].empty()) continue;
             const int cs = (int)(k / 2);
             const int slots = std::max(1, (c_sm(b) * 2) / cs);      // two CTAs per SM, cs CTAs per cluster
-            int chain = std::max(1, std::min(max_chain, (int)(cbucket[k].size() / (size_t)(6 * slots))));
-            if (chain < 2 && cbucket[k].size() >= (size_t)(4 * slots)) chain = std::min(2, max_chain);
+            int chain = pick_chain(cbucket[k].size(), slots, max_chain, longest_run(d, cbucket[k]));
             if (force_chain > 0) chain = force_chain;
             ClassList l = {rl::kClusterClassBase + cs, (int)(k % 2), (int)b->joblist.size(), (int)cbucket[k].size(), c, (int)b->itemoff.size(), 0};
             int run = 0, last_t = -1;

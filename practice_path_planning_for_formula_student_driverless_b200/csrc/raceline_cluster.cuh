@@ -411,13 +411,20 @@ __device__ __forceinline__ void vprofile_c(const Part& pt, const Clu& cl, const 
             if (tid == T - 1) cl_st1(cl_map(&sVL[b * S + T], cl.right), last);
         }
         cl_sync();
+        // (as in vprofile_blocked: a chunk whose input did not change since the previous round is not recomputed)
+        bool first_round = true;
+        double vin_prev = 0.0, u = 0.0;
         for (;;) {
             const double vin = sVL[b * S + iL];
-            double u = gfirst ? v0[0] : fmin(v0[0], f_acc(q, vin, kapL));
-            v[0] = u;
+            if (first_round || vin != vin_prev) {
+                u = gfirst ? v0[0] : fmin(v0[0], f_acc(q, vin, kapL));
+                v[0] = u;
 #pragma unroll
-            for (int k = 1; k < K; ++k)
-                if (k < cnt) { u = fmin(v0[k], f_acc(q, u, kap[k - 1])); v[k] = u; }
+                for (int k = 1; k < K; ++k)
+                    if (k < cnt) { u = fmin(v0[k], f_acc(q, u, kap[k - 1])); v[k] = u; }
+                vin_prev = vin;
+            }
+            first_round = false;
             const bool changed = (u != sVL[b * S + tid]);
             sVL[(b ^ 1) * S + tid] = u;
             if (tid == T - 1) cl_st1(cl_map(&sVL[(b ^ 1) * S + T], cl.right), u);
@@ -433,14 +440,19 @@ __device__ __forceinline__ void vprofile_c(const Part& pt, const Clu& cl, const 
         sVF[b * S + tid] = v[0];
         if (tid == 0) cl_st1(cl_map(&sVF[b * S + T], cl.left), v[0]);
         cl_sync();
+        first_round = true;
         for (;;) {
             const double vin = sVF[b * S + iR];
-            double u = 0.0;
+            if (first_round || vin != vin_prev) {
+                u = 0.0;
 #pragma unroll
-            for (int k = K - 1; k >= 0; --k) {
-                if (k == cnt - 1) { u = glast ? v0[k] : fmin(v0[k], f_brk(q, vin, kapR)); v[k] = u; }
-                else if (k < cnt - 1) { u = fmin(v0[k], f_brk(q, u, kap[k + 1])); v[k] = u; }
+                for (int k = K - 1; k >= 0; --k) {
+                    if (k == cnt - 1) { u = glast ? v0[k] : fmin(v0[k], f_brk(q, vin, kapR)); v[k] = u; }
+                    else if (k < cnt - 1) { u = fmin(v0[k], f_brk(q, u, kap[k + 1])); v[k] = u; }
+                }
+                vin_prev = vin;
             }
+            first_round = false;
             const bool changed = (u != sVF[b * S + tid]);
             sVF[(b ^ 1) * S + tid] = u;
             if (tid == 0) cl_st1(cl_map(&sVF[(b ^ 1) * S + T], cl.left), u);

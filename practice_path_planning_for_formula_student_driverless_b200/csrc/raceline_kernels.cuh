@@ -342,19 +342,27 @@ __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, 
             sVL[b * T + tid] = last;
         }
         block_sync<T>();
+        // A round recomputes the chunk from the start-of-sweep values and the neighbour's published value only: when that
+        // input is the one of the previous round, so is the output.  After the first round the recurrences (two square
+        // roots and a division per step, all dependent) therefore only run in the warps the change is passing through.
+        bool first_round = true;
+        double vin_prev = 0.0, last = 0.0;
         for (;;) {
             bool changed = false;
-            double last = 0.0;
             if (act) {
                 const double vin = sVL[b * T + pt.tL];
-                double u = hasL ? fmin(v0[0], f_acc(q, vin, kapL)) : v0[0];
-                v[0] = u;
+                if (first_round || vin != vin_prev) {
+                    double u = hasL ? fmin(v0[0], f_acc(q, vin, kapL)) : v0[0];
+                    v[0] = u;
 #pragma unroll
-                for (int k = 1; k < K; ++k)
-                    if (k < cnt) { u = fmin(v0[k], f_acc(q, u, kap[k - 1])); v[k] = u; }
-                last = u;
+                    for (int k = 1; k < K; ++k)
+                        if (k < cnt) { u = fmin(v0[k], f_acc(q, u, kap[k - 1])); v[k] = u; }
+                    last = u;
+                    vin_prev = vin;
+                }
                 changed = (last != sVL[b * T + tid]);
             }
+            first_round = false;
             sVL[(b ^ 1) * T + tid] = last;
             b ^= 1;
             ++rounds;
@@ -367,20 +375,25 @@ __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, 
         for (int k = 0; k < K; ++k) v0[k] = v[k];
         sVF[b * T + tid] = v[0];
         block_sync<T>();
+        first_round = true;
+        double first = 0.0;
         for (;;) {
             bool changed = false;
-            double first = 0.0;
             if (act) {
                 const double vin = sVF[b * T + pt.tR];
-                double u = 0.0;
+                if (first_round || vin != vin_prev) {
+                    double u = 0.0;
 #pragma unroll
-                for (int k = K - 1; k >= 0; --k) {
-                    if (k == cnt - 1) { u = hasR ? fmin(v0[k], f_brk(q, vin, kapR)) : v0[k]; v[k] = u; }
-                    else if (k < cnt - 1) { u = fmin(v0[k], f_brk(q, u, kap[k + 1])); v[k] = u; }
+                    for (int k = K - 1; k >= 0; --k) {
+                        if (k == cnt - 1) { u = hasR ? fmin(v0[k], f_brk(q, vin, kapR)) : v0[k]; v[k] = u; }
+                        else if (k < cnt - 1) { u = fmin(v0[k], f_brk(q, u, kap[k + 1])); v[k] = u; }
+                    }
+                    first = u;
+                    vin_prev = vin;
                 }
-                first = u;
                 changed = (first != sVF[b * T + tid]);
             }
+            first_round = false;
             sVF[(b ^ 1) * T + tid] = first;
             b ^= 1;
             ++rounds;

@@ -311,7 +311,7 @@ def run_extras(args, rl, ctx, stream, fp64_peak, world, rank, dist):
     pb = rl.PackedBatch([tr], [c.to_params() for c in cfgs], jobs, pool=pool)
     e = extra_resident(rl, ctx, stream, "configs[2]", "Config sweep on competition_map2 (N=252): 4096 combos of lambda_smooth x mu x "
                        "P_max_W x w_time_gain, min-curv + min-time each, one copy of the geometry", pb, jobs, fp64_peak,
-                       max(2, args.extra_steps), 2, len(cfgs), 1, None)
+                       max(10, args.extra_steps), 3, len(cfgs), 1, None)
     laps = np.array([pb.out_stats[j].lap_time for j in range(1, pb.n_jobs, 2)])
     e["best_combo"] = int(np.argmin(laps)); e["best_lap_s"] = float(laps.min()); e["worst_lap_s"] = float(laps.max())
     extras.append(e)

@@ -108,8 +108,8 @@ int launch_geom(const GeomBatch& G, int n_tracks, int max_pts, void* stream);   
 // job_list[item_off[k] .. item_off[k+1]) of jobs on the same track (item_off has n_items+1 entries, relative to
 // job_list); a cluster class gives each item to one thread-block cluster.  Returns a cudaError_t as int.
 int launch_solve(const DevBatch& B, const int* job_list, int n_list, const int* item_off, int n_items, int cls, int mode, void* stream);
-// CTAs of class `cls` one SM holds at a time (registers and shared memory)
-inline int ctas_per_sm(int cls) { const int np = kClasses[cls].T * kClasses[cls].K; return np >= 4096 ? 1 : (4096 / np > 16 ? 16 : 4096 / np); }
+// CTAs of class `cls` one SM holds at a time: the occupancy the runtime reports for the kernel (set by configure_kernels)
+int ctas_per_sm(int cls);
 int configure_kernels();  // sets max dynamic shared memory on every instantiation
 int launch_fp64_peak(double* d_out, int blocks, int threads, int iters, void* stream);
 

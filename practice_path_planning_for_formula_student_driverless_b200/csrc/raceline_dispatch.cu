@@ -7,7 +7,8 @@ namespace rl {
 
 #define RL_DECL(T)                                                                                   \
     int launch_solve_##T(const DevBatch& B, const int* job_list, const int* item_off, int n_items, int mode, void* stream); \
-    int configure_solve_##T();
+    int configure_solve_##T();                                                                       \
+    int occupancy_solve_##T();
 RL_DECL(32) RL_DECL(64) RL_DECL(128) RL_DECL(256) RL_DECL(512)
 #undef RL_DECL
 
@@ -26,6 +27,8 @@ __global__ void fp64_peak_kernel(double* out, int iters)
 }
 }  // namespace
 
+namespace { int g_occ[kNumClasses] = {0, 0, 0, 0, 0}; }
+
 int configure_kernels()
 {
     int e = configure_solve_32();
@@ -35,7 +38,18 @@ int configure_kernels()
     if (!e) e = configure_solve_512();
     if (!e) e = configure_solve_cluster();
     if (!e) e = configure_geom();
+    if (!e) {   // what the device really holds per SM (registers, shared memory + its per-CTA reserve): the host plan's CTA slots
+        g_occ[0] = occupancy_solve_32(); g_occ[1] = occupancy_solve_64(); g_occ[2] = occupancy_solve_128();
+        g_occ[3] = occupancy_solve_256(); g_occ[4] = occupancy_solve_512();
+    }
     return e;
+}
+
+int ctas_per_sm(int cls)
+{
+    if (cls >= 0 && cls < kNumClasses && g_occ[cls] > 0) return g_occ[cls];
+    const int np = kClasses[cls].T * kClasses[cls].K;
+    return np >= 4096 ? 1 : (4096 / np > 16 ? 16 : 4096 / np);
 }
 
 int launch_solve(const DevBatch& B, const int* job_list, int n_list, const int* item_off, int n_items, int cls, int mode, void* stream)

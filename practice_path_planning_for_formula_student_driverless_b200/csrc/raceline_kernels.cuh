@@ -2444,6 +2444,12 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             e = cudaFuncSetAttribute(solve_kernel<T, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
         return (int)e;                                                                                                \
     }                                                                                                                 \
+    int occupancy_solve_##NAME()                                                                                         \
+    {                                                                                                                 \
+        int n = 0;                                                                                                    \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, solve_kernel<T, K, 0>, T, smem_bytes_for_class(T, K)) != cudaSuccess) { cudaGetLastError(); n = 0; } \
+        return n;                                                                                                     \
+    }                                                                                                                 \
     }
 
 #define RL_INSTANTIATE(T, K) RL_INSTANTIATE_AS(T, K, T)

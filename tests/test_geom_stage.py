@@ -119,3 +119,22 @@ def test_geom_gpu_errors_and_edge_cases(ctx, goldens):
     mt = rl.solve_batch([tr], [rl.Config()], [(0, 0, rl.RL_STAGE_MINTIME)], ctx=ctx)[0]
     ref = goldens["training_map"]
     assert abs(mt.lap_time - ref["mt_lap_time"]) <= 1e-5 * ref["mt_lap_time"]
+
+
+@pytest.mark.gpu
+def test_packed_geom_pinned_reuse_and_kernel_time(ctx):
+    """PackedGeom: pack once (page-locked), run the C-ABI call repeatedly -- the shape bench.py times; same rows as the
+    one-shot wrapper, and the library reports the device time of its two kernels."""
+    gs = [load_golden(n) for n in GEOM_CASES[:3]]
+    args = ([g["mids_xy"] for g in gs], [int(g["samples"]) for g in gs], [g["inner_seg"] for g in gs], [g["outer_seg"] for g in gs])
+    once = rl.centerline_geom_batch(*args, closed=True, ctx=ctx)
+    pool = rl.PinnedPool()
+    pg = rl.PackedGeom(*args, closed=True, pool=pool)
+    for _ in range(3):
+        pg.run(ctx)
+    assert ctx.last_kernel_ms() > 0.0
+    for a, b in zip(once, pg.results()):
+        assert np.array_equal(a.xy, b.xy) and np.array_equal(a.width, b.width) and a.L == b.L
+    assert pg.d2h_bytes == pg.rows * 72 + 16 * len(gs)
+    del pg, b
+    pool.close(force=True)

@@ -891,21 +891,21 @@ __device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const Path
             V[q] = v; F[q] = make_float2((float)(v.x - org.x), (float)(v.y - org.y));
         }
     }
-    if (!__syncthreads_and(linked)) return 0xffffffffu;
-    UpdCtx c;
-    {
+    if (tid == 0) {   // the CTA-uniform context of corridor_update_sample (static shared memory), published by the barrier below
+        UpdCtx& c = s_upd;
         const unsigned char* base = reinterpret_cast<const unsigned char*>(pv.sP);    // start of the dynamic shared memory
         c.oV0 = (int)(reinterpret_cast<const unsigned char*>(V0) - base); c.oV1 = (int)(reinterpret_cast<const unsigned char*>(V1) - base);
         c.oF0 = (int)(reinterpret_cast<const unsigned char*>(F0) - base); c.oF1 = (int)(reinterpret_cast<const unsigned char*>(F1) - base);
         c.oHint = (int)(reinterpret_cast<const unsigned char*>(sHint) - base); c.oClr = (int)(reinterpret_cast<const unsigned char*>(sClr) - base);
         c.oHalo = (int)(reinterpret_cast<const unsigned char*>(sHalo) - base);
+        c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
+        c.ox = org.x; c.oy = org.y; c.guard = guard; c.N = Nl; c.M0 = M[0]; c.M1 = M[1]; c.rf0 = sMisc[8] & 1; c.rf1 = sMisc[9] & 1;
+        c.mr0 = __int_as_float(sMisc[10]); c.mr1 = __int_as_float(sMisc[11]);
+        c.parity_ok = parity_ok; c.closed = true;
+        c.base0 = basev[0]; c.base1 = basev[1]; c.len0 = nseg[0]; c.len1 = nseg[1];
+        c.gs0 = gseg + 4 * segI0; c.gs1 = gseg + 4 * segO0;
     }
-    c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
-    c.ox = org.x; c.oy = org.y; c.guard = guard; c.N = Nl; c.M0 = M[0]; c.M1 = M[1]; c.rf0 = sMisc[8] & 1; c.rf1 = sMisc[9] & 1;
-    c.mr0 = __int_as_float(sMisc[10]); c.mr1 = __int_as_float(sMisc[11]);
-    c.parity_ok = parity_ok; c.closed = true;
-    c.base0 = basev[0]; c.base1 = basev[1]; c.len0 = nseg[0]; c.len1 = nseg[1];
-    c.gs0 = gseg + 4 * segI0; c.gs1 = gseg + 4 * segO0;
+    if (!__syncthreads_and(linked)) return 0xffffffffu;
     unsigned flagged = 0u;
     double2 cn = make_double2(0.0, 0.0);
     unsigned long long wn = 0ull, an = 0ull;
@@ -917,9 +917,10 @@ __device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const Path
         const unsigned long long wc = wn, ac = an;
         if (j + 1 < K && i + T < Nl) { cn = *reinterpret_cast<const double2*>(gcenter + 2 * (i + T)); wn = gcert[i + T]; an = gapex[i + T]; }
         if (i >= Nl) continue;
-        double hv = 0.0, lv = 0.0;
-        if (corridor_update_sample<true>(c, i, cc.x, cc.y, wc, ac, hv, lv, ray_tests)) flagged |= (1u << j);
-        else { hic[j] = hv; loc[j] = lv; }
+        const UpdRes r = corridor_update_sample<true>(i, cc.x, cc.y, wc, ac);
+        ray_tests += r.tests;
+        if (r.flagged) flagged |= (1u << j);
+        else { hic[j] = r.hv; loc[j] = r.lv; }
     }
     return flagged;
 }

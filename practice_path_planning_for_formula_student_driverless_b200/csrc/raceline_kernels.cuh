@@ -270,6 +270,7 @@ struct VPar {
     double v_cap, a_lat_max, kappa_eps, a_tot2, kd, Fr, mass, inv_mass, P, acc_cap, brk_cap, h;
     int has_power;
 };
+__shared__ VPar s_vpar;   // solve_kernel: the current job's constants (written by thread 0 at the start of the job)
 __device__ __forceinline__ double f_acc(const VPar& q, double vi, double ki)
 {   // forward step value sqrt(max(0, v^2 + 2 a_acc h)), main.cpp:830-831
     const double alat = vi * vi * fabs(ki);
@@ -1743,11 +1744,16 @@ struct UpdCtx {
 // ring-global segment index -> index into the chunk-local vertex arrays
 __device__ __forceinline__ int loc_idx(int sg, int base, int M) { const int li = sg - base; return (li < 0) ? li + M : li; }
 // one sample of corridor_update: true = FLAGGED (hv/lv untouched), else the corridor bounds hv >= 0 >= lv
+// CTA-uniform, so it lives in static shared memory: thread 0 fills it before the barrier that precedes the sample loop
+// (as an argument it sat in local memory and every call read its fields back through L1)
+__shared__ UpdCtx s_upd;
+// result of one sample, returned BY VALUE (registers): reference out-parameters of a real function live in local memory
+struct UpdRes { double hv, lv; int tests; bool flagged; };
 template <bool LOCAL>
-__device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, double cx0, double cy0, unsigned long long cert_w,
-                                                    unsigned long long apex_w, double& hv_out, double& lv_out, long long& tests_io)
+__device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double cy0, unsigned long long cert_w, unsigned long long apex_w)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const UpdCtx& c = s_upd;
     const double2* sP = reinterpret_cast<const double2*>(smem_raw);
     const double2* cV0 = reinterpret_cast<const double2*>(smem_raw + c.oV0);
     const double2* cV1 = reinterpret_cast<const double2*>(smem_raw + c.oV1);
@@ -1910,14 +1916,15 @@ __device__ __noinline__ bool corridor_update_sample(const UpdCtx& c, int i, doub
         }
         dres[dir] = res;
     }
-    tests_io += ray_tests;
-    if (flag) return true;
+    UpdRes r;
+    r.tests = (int)ray_tests; r.flagged = flag; r.hv = 0.0; r.lv = 0.0;
+    if (flag) return r;
     double hv = fmax(0.0, fmax(0.0, dres[0]) - c.guard);
     double lv = -fmax(0.0, fmax(0.0, dres[1]) - c.guard);
     if (!isfinite(hv)) hv = 0.0;
     if (!isfinite(lv)) lv = 0.0;
-    hv_out = hv; lv_out = lv;
-    return false;
+    r.hv = hv; r.lv = lv;
+    return r;
 }
 
 template <int T, int K>
@@ -1947,20 +1954,19 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
         const double2 v = (q < M1) ? *reinterpret_cast<const double2*>(gseg + 4 * (segO0 + q)) : *reinterpret_cast<const double2*>(gseg + 4 * (segO0 + M1 - 1) + 2);
         V1[q] = v; F1[q] = make_float2((float)(v.x - org.x), (float)(v.y - org.y));
     }
-    const int rf0 = sMisc[8], rf1 = sMisc[9];
-    const float mr0 = __int_as_float(sMisc[10]), mr1 = __int_as_float(sMisc[11]);
-    block_sync<T>();
-    UpdCtx c;
-    {
+    if (tid == 0) {
+        UpdCtx& c = s_upd;
         const unsigned char* base = reinterpret_cast<const unsigned char*>(sP);    // sP is the start of the dynamic shared memory
         c.oV0 = (int)(reinterpret_cast<const unsigned char*>(V0) - base); c.oV1 = (int)(reinterpret_cast<const unsigned char*>(V1) - base);
         c.oF0 = (int)(reinterpret_cast<const unsigned char*>(F0) - base); c.oF1 = (int)(reinterpret_cast<const unsigned char*>(F1) - base);
         c.oHint = (int)(reinterpret_cast<const unsigned char*>(sHint) - base); c.oClr = (int)(reinterpret_cast<const unsigned char*>(sClr) - base);
+        c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
+        c.ox = org.x; c.oy = org.y; c.guard = guard; c.N = N; c.M0 = M0; c.M1 = M1; c.rf0 = sMisc[8]; c.rf1 = sMisc[9];
+        c.mr0 = __int_as_float(sMisc[10]); c.mr1 = __int_as_float(sMisc[11]);
+        c.parity_ok = parity_ok; c.closed = closed;
+        c.base0 = 0; c.base1 = 0; c.len0 = M0; c.len1 = M1; c.oHalo = 0; c.gs0 = nullptr; c.gs1 = nullptr;
     }
-    c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
-    c.ox = org.x; c.oy = org.y; c.guard = guard; c.N = N; c.M0 = M0; c.M1 = M1; c.rf0 = rf0; c.rf1 = rf1; c.mr0 = mr0; c.mr1 = mr1;
-    c.parity_ok = parity_ok; c.closed = closed;
-    c.base0 = 0; c.base1 = 0; c.len0 = M0; c.len1 = M1; c.oHalo = 0; c.gs0 = nullptr; c.gs1 = nullptr;
+    block_sync<T>();
     unsigned flagged = 0u;
     // the per-sample code exists once (a real function): the instruction cache matters more than the call, and the
     // results stay in registers (static j)
@@ -1976,9 +1982,10 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
         const unsigned long long wc = wn, ac = an;
         if (j + 1 < K && i + T < N) { cn = *reinterpret_cast<const double2*>(gcenter + 2 * (i + T)); wn = gcert[i + T]; an = gapex[i + T]; }
         if (i >= N) continue;
-        double hv = 0.0, lv = 0.0;
-        if (corridor_update_sample<false>(c, i, cc.x, cc.y, wc, ac, hv, lv, ray_tests)) flagged |= (1u << j);
-        else { hic[j] = hv; loc[j] = lv; }
+        const UpdRes r = corridor_update_sample<false>(i, cc.x, cc.y, wc, ac);
+        ray_tests += r.tests;
+        if (r.flagged) flagged |= (1u << j);
+        else { hic[j] = r.hv; loc[j] = r.lv; }
     }
     RL_DBG_LEAVE(const_cast<int*>(sMisc), kDbgPhVerts);
     return flagged;
@@ -2082,6 +2089,14 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         for (int o = 0; o < RL_MAX_OUTER_LOG; ++o) {
             st->J0[o] = 0.0; st->Jend[o] = 0.0; st->lap_outer[o] = 0.0; st->acc_outer[o] = 0; st->bt_outer[o] = 0;
         }
+        VPar& w = s_vpar;
+        w.v_cap = C.v_cap_mps; w.a_lat_max = C.a_lat_max; w.kappa_eps = C.kappa_eps;
+        {
+            const double a_total = C.use_total_ge_lat ? fmax(C.a_total_max, C.a_lat_max) : C.a_total_max;   // main.cpp:802-804
+            w.a_tot2 = a_total * a_total;
+        }
+        w.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; w.Fr = C.mass_kg * 9.81 * C.c_rr; w.mass = C.mass_kg; w.inv_mass = 1.0 / C.mass_kg; w.P = C.P_max_W;
+        w.acc_cap = C.a_long_acc_cap; w.brk_cap = C.a_long_brake_cap; w.h = h; w.has_power = (C.P_max_W > 0);
         fence_proxy_async();
     }
     block_sync<T>();
@@ -2098,14 +2113,9 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
     for (int k = 0; k < K; ++k)
         if (k < cnt) { B.alpha_total[row0 + start + k] = 0.0; B.alpha_last[row0 + start + k] = 0.0; }
 
-    VPar q;
-    q.v_cap = C.v_cap_mps; q.a_lat_max = C.a_lat_max; q.kappa_eps = C.kappa_eps;
-    {
-        const double a_total = C.use_total_ge_lat ? fmax(C.a_total_max, C.a_lat_max) : C.a_total_max;   // main.cpp:802-804
-        q.a_tot2 = a_total * a_total;
-    }
-    q.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; q.Fr = C.mass_kg * 9.81 * C.c_rr; q.mass = C.mass_kg; q.inv_mass = 1.0 / C.mass_kg; q.P = C.P_max_W;
-    q.acc_cap = C.a_long_acc_cap; q.brk_cap = C.a_long_brake_cap; q.h = h; q.has_power = (C.P_max_W > 0);
+    // the v(s) constants of the job are CTA-uniform and live in static shared memory (13 values that would otherwise
+    // occupy 25 registers from here to the end of the job); thread 0 writes them, the barrier below publishes them
+    const VPar& q = s_vpar;
 
     const long long segI0 = B.seg_off[2 * trk], segO0 = B.seg_off[2 * trk + 1], segE = B.seg_off[2 * trk + 2];
     const HStep H(h);

@@ -1,8 +1,9 @@
 #!/bin/bash
+# development helper: what one gpurun call runs (edit per experiment)
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:solve_kernel -s 3 -c 1 -f -o $O/r02_sweep_kernel python tools/sweep_probe.py 0 > $O/sweep_ncu.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:solve_kernel -s 1 -c 1 -f -o $O/r02_n252_kernel python tools/phase_report.py --tracks 4096 --n 252 --m 115 > $O/n252_ncu.log 2>&1
+timeout 600 python bench.py --tracks-total 8192 --steps 3 --warmup 3 --no-cpu-baseline --no-extras > $O/q_bench.json 2> $O/q_bench.err
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_chains.py tests/test_gpu_cluster.py -m gpu -q -x > $O/q_pytest.txt 2>&1
 ls -la $O > $O/ls.txt

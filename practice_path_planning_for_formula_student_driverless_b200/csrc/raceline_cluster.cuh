@@ -399,9 +399,10 @@ __device__ __forceinline__ void vprofile_c(const Part& pt, const Clu& cl, const 
     const double kapL = sKL[iL], kapR = sKF[iR];
     int b = 0;
     for (int iter = 0; iter < max_iters; ++iter) {
-        double v0[K], vstart[K];
+        double v0[K];
+        bool chg_iter = false;   // as in vprofile_blocked: v only decreases, so "changed" is gathered from the two sweeps
 #pragma unroll
-        for (int k = 0; k < K; ++k) { vstart[k] = v[k]; v0[k] = v[k]; }
+        for (int k = 0; k < K; ++k) v0[k] = v[k];
         // ---------------- forward sweep (main.cpp:829-833) ----------------
         {
             double last = v[0];
@@ -434,6 +435,8 @@ __device__ __forceinline__ void vprofile_c(const Part& pt, const Clu& cl, const 
         }
         // closed-loop wrap: v[0] = min(v[0], f_acc(v[N-1])), main.cpp:834-839
         if (gfirst) v[0] = fmin(v[0], f_acc(q, sVL[b * S + iL], kapL));
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (k < cnt && v[k] != v0[k]) chg_iter = true;
         // ---------------- backward sweep (main.cpp:841-845) ----------------
 #pragma unroll
         for (int k = 0; k < K; ++k) v0[k] = v[k];
@@ -466,9 +469,8 @@ __device__ __forceinline__ void vprofile_c(const Part& pt, const Clu& cl, const 
 #pragma unroll
             for (int k = 0; k < K; ++k) if (k == cnt - 1) v[k] = fmin(v[k], w);
         }
-        bool chg_iter = false;
 #pragma unroll
-        for (int k = 0; k < K; ++k) if (k < cnt && v[k] != vstart[k]) chg_iter = true;
+        for (int k = 0; k < K; ++k) if (k < cnt && v[k] != v0[k]) chg_iter = true;
         if (!cluster_or(chg_iter, sFlag, fslot, cl, tid, pt.lane)) break;
     }
 }
@@ -1047,9 +1049,6 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
     int acc_total = 0, bt_total = 0, ev_total = 0;
     const int max_outer = ev ? 0 : C.max_outer_iters;
 
-    double lo[K], hi[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) { lo[k] = 0.0; hi[k] = 0.0; }
     // initial corridor from the centre line: guard uses the veh_width ARGUMENT (main.cpp:706 / 930)
     const double* gcenter = B.center_xy + 2 * (s0 + cl.n0);
     unsigned long long* gcert = reinterpret_cast<unsigned long long*>(B.heading + row0);      // certificates: scratch in the chunk's
@@ -1076,7 +1075,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
                 corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
                                      guard0, flagged, false, parity_ok, loc, hic, ray_tests, ex_scans);
         }
-        corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
+        corridor_stage_out<T, K>(pt, sB, loc, hic);
     }
 
     double* sC0 = sB + tid;
@@ -1108,8 +1107,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         block_sync<T>();
         double* sLo = pair_base_a(reinterpret_cast<double*>(sP), NP, tid);
         double* sHi = pair_base_b(reinterpret_cast<double*>(sP), NP, tid);
-#pragma unroll
-        for (int k = 0; k < K; ++k) st_pair<T>(sLo, sHi, k, lo[k], hi[k]);
+        staged_bounds_home<T, K>(pt, sB, sLo, sHi);   // the corridor's bounds: staging area -> their home for the PGD
         double gam[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) gam[k] = 1.0;
@@ -1242,7 +1240,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             if (block_or<T>(flagged != 0u))   // per CTA: the searching path rebuilds the flagged samples (no cluster traffic inside)
                 corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
                                      guard, flagged, false, parity_ok, loc, hic, ray_tests, ex_scans);
-            corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi);
+            corridor_stage_out<T, K>(pt, sB, loc, hic);
         }
     }
 

@@ -329,10 +329,9 @@ __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, 
     int b = 0;
     for (int iter = 0; iter < max_iters; ++iter) {
         double v0[K];
+        // "did this iteration change anything": every update is a min with the old value, so v[k] at the end differs from
+        // v[k] at the start exactly when the forward or the backward sweep (or a wrap update) lowered it
         bool chg_iter = false;
-        double vstart[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) vstart[k] = v[k];
         // ---------------- forward sweep (main.cpp:829-833) ----------------
 #pragma unroll
         for (int k = 0; k < K; ++k) v0[k] = v[k];
@@ -371,6 +370,8 @@ __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, 
         }
         // closed-loop wrap: v[0] = min(v[0], f_acc(v[N-1])), main.cpp:834-839
         if (closed && tid == 0) v[0] = fmin(v[0], f_acc(q, sVL[b * T + pt.tL], kapL));
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (k < cnt && v[k] != v0[k]) chg_iter = true;
         // ---------------- backward sweep (main.cpp:841-845) ----------------
 #pragma unroll
         for (int k = 0; k < K; ++k) v0[k] = v[k];
@@ -407,7 +408,7 @@ __device__ __forceinline__ void vprofile_blocked(const Part& pt, const VPar& q, 
             for (int k = 0; k < K; ++k) if (k == cnt - 1) v[k] = fmin(v[k], w);
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) if (k < cnt && v[k] != vstart[k]) chg_iter = true;
+        for (int k = 0; k < K; ++k) if (k < cnt && v[k] != v0[k]) chg_iter = true;
         if (!block_or<T>(chg_iter)) break;
     }
 }
@@ -1693,8 +1694,11 @@ __device__ __forceinline__ void corridor_build_fast(const Part& pt, const double
 
 // corridor bounds from the consecutive mapping (sample tid + j*T) to the blocked layout, through region B
 template <int T, int K>
+// The bounds stay in the staging area (sample-major lo | hi at the start of region B) until the next outer iteration
+// has parked the path and their home in the path area is free (staged_bounds_home): they never occupy registers across
+// the linearisation.
 __device__ __forceinline__ void corridor_stage_out(const Part& pt, double* sB, const double (&loc)[K], const double (&hic)[K],
-                                                   double (&lo)[K], double (&hi)[K], int* dbgMisc = nullptr)
+                                                   int* dbgMisc = nullptr)
 {
     constexpr int NP = T * K;
     (void)dbgMisc;
@@ -1708,13 +1712,34 @@ __device__ __forceinline__ void corridor_stage_out(const Part& pt, double* sB, c
         if (i < pt.N) { sHiS[i] = hic[j]; sLoS[i] = loc[j]; }
     }
     block_sync<T>();
+}
+// corridor_build_tiled returns the bounds in registers (blocked layout): same staging area, same hand-over
+template <int T, int K>
+__device__ __forceinline__ void corridor_stage_blocked(const Part& pt, double* sB, const double (&lo)[K], const double (&hi)[K], int* dbgMisc = nullptr)
+{
+    constexpr int NP = T * K;
+    (void)dbgMisc;
+    block_sync<T>();
+    if (dbgMisc) RL_DBG_ENTER(T, dbgMisc, kDbgPhStage);
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if (k < pt.cnt) { sB[pt.start + k] = lo[k]; sB[NP + pt.start + k] = hi[k]; }
+    block_sync<T>();
+}
+// staging area -> (lo, hi) pairs of the owned slots in the (parked) path area; unused slots get (0, 0)
+template <int T, int K>
+__device__ __forceinline__ void staged_bounds_home(const Part& pt, const double* sB, double* sLo, double* sHi, int* dbgMisc = nullptr)
+{
+    constexpr int NP = T * K;
+    (void)dbgMisc;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        lo[k] = 0.0; hi[k] = 0.0;
-        if (k < pt.cnt) { lo[k] = sLoS[pt.start + k]; hi[k] = sHiS[pt.start + k]; }
+        double l = 0.0, h = 0.0;
+        if (k < pt.cnt) { l = sB[pt.start + k]; h = sB[NP + pt.start + k]; }
+        st_pair<T>(sLo, sHi, k, l, h);
     }
     if (dbgMisc) RL_DBG_LEAVE(dbgMisc, kDbgPhStage);
-    block_sync<T>();
+    block_sync<T>();   // region B is free again
 }
 
 // ---- corridor update, common case (every build after the first) ------------------------------------------------
@@ -2126,9 +2151,6 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
     int acc_total = 0, bt_total = 0, ev_total = 0;
     const int max_outer = ev ? 0 : C.max_outer_iters;
 
-    double lo[K], hi[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) { lo[k] = 0.0; hi[k] = 0.0; }
     // initial corridor from the centre line: guard uses the veh_width ARGUMENT (main.cpp:706 / 930)
     constexpr int CAPF = fast_tile_cap(NP);
     const bool fast_rays = !ev && (segO0 - segI0 <= CAPF) && (segE - segO0 <= CAPF) && (CAPF < 8192);
@@ -2160,12 +2182,17 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
                 corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
                                           segI0, segO0, segE, guard0, flagged, loc, hic, ray_tests, ex_scans);
         }
-        corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi, sMisc);
+        corridor_stage_out<T, K>(pt, sB, loc, hic, sMisc);
         if (!same_track)
             fast_update = (sMisc[8] & 2) && (sMisc[9] & 2) && (segO0 - segI0 > 2 * kWin + 1) && (segE - segO0 > 2 * kWin + 1);
-    } else if (!ev)
+    } else if (!ev) {
+        double lo[K], hi[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { lo[k] = 0.0; hi[k] = 0.0; }
         corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                    C.veh_width_arg * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+        corridor_stage_blocked<T, K>(pt, sB, lo, hi, sMisc);
+    }
 
     double* sC0 = sB + tid;
     double* sCp = pair_base_a(sB + NP, NP, tid);
@@ -2198,8 +2225,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         block_sync<T>();
         double* sLo = pair_base_a(reinterpret_cast<double*>(sP), NP, tid);
         double* sHi = pair_base_b(reinterpret_cast<double*>(sP), NP, tid);
-#pragma unroll
-        for (int k = 0; k < K; ++k) st_pair<T>(sLo, sHi, k, lo[k], hi[k]);
+        staged_bounds_home<T, K>(pt, sB, sLo, sHi, sMisc);   // the corridor's bounds: staging area -> their home for the PGD
         double gam[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) gam[k] = 1.0;
@@ -2210,8 +2236,11 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             double kap[K], vv[K], axd[K], vkap[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) kap[k] = (k < cnt) ? N0[k] * Wd[k] : 0.0;    // kappa = N0 / denom, main.cpp:618
-            block_sync<T>();   // region B is free: lo/hi are in registers, coefficients not yet built
             RL_DBG_ENTER(T, sMisc, kDbgPhVsweep);
+            // the linearisation (48 registers) waits behind the exchange arrays of the sweeps (first NP doubles of region B)
+            // while the v(s) profile runs: own slots only, written and read back by the same thread
+#pragma unroll
+            for (int k = 0; k < K; ++k) { sB[NP + k * T + tid] = A1[k]; sB[2 * NP + k * T + tid] = A2[k]; sB[3 * NP + k * T + tid] = Wd[k]; }
             vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed, vkap);
             block_sync<T>();
             lap_outer = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32, closed);
@@ -2246,6 +2275,8 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
                     gam[k] = corner_w * invv_w;
                 }
             }
+#pragma unroll
+            for (int k = 0; k < K; ++k) { A1[k] = sB[NP + k * T + tid]; A2[k] = sB[2 * NP + k * T + tid]; Wd[k] = sB[3 * NP + k * T + tid]; }
             block_sync<T>();
         }
         RL_PH(2);   // v(s) profile + time weights
@@ -2342,11 +2373,15 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             if (block_or<T>(flagged != 0u))   // some certificate failed (or none exists yet): the searching path rebuilds those samples
                 corridor_build_fast<T, K>(pt, sP, sB, mbar, bar_phase, sMisc, sHint, sClr, false, parity_ok, closed, B.seg, B.center_xy + 2 * s0, gcert, gapex,
                                           segI0, segO0, segE, guard, flagged, loc, hic, ray_tests, ex_scans);
-            corridor_stage_out<T, K>(pt, sB, loc, hic, lo, hi, sMisc);
+            corridor_stage_out<T, K>(pt, sB, loc, hic, sMisc);
             RL_PH(7);   // searching path for flagged samples + staging
         } else {
+            double lo[K], hi[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { lo[k] = 0.0; hi[k] = 0.0; }
             corridor_build_tiled<T, K>(pt, sP, sB, mbar, bar_phase, closed, B.seg, segI0, segO0, segE,
                                        C.veh_width_m * 0.5 + C.safety_margin_m, lo, hi, ray_tests);
+            corridor_stage_blocked<T, K>(pt, sB, lo, hi, sMisc);
             RL_PH(7);
         }
     }

@@ -37,7 +37,7 @@ constexpr int kcExF = kcRed + 2 * kMaxCS * kcNW * 16; // [2][NW+1][2] doubles; s
 constexpr int kcExL = kcExF + 2 * (kcNW + 1) * 16;    // [2][NW+1][2] doubles; slot NW = left neighbour CTA's last two samples
 constexpr int kcMisc = kcExL + 2 * (kcNW + 1) * 16;   // a few ints
 constexpr int kcEbar = kcMisc + 64;                   // uint64[2]: the two mbarriers of the per-evaluation exchange (even / odd)
-constexpr int kcBytes = 4992;
+constexpr int kcBytes = 4880;                         // two CTAs (+ their static UpdCtx and the 1 KB reserve each) fill the SM's 228 KB to 112 bytes
 static_assert(kcEbar + 16 <= kcBytes && kcEbar % 8 == 0, "cluster scratch layout");
 
 struct Clu {
@@ -896,8 +896,8 @@ __device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const Path
     if (tid == 0) {   // the CTA-uniform context of corridor_update_sample (static shared memory), published by the barrier below
         UpdCtx& c = s_upd;
         const unsigned char* base = reinterpret_cast<const unsigned char*>(pv.sP);    // start of the dynamic shared memory
-        c.oV0 = (int)(reinterpret_cast<const unsigned char*>(V0) - base); c.oV1 = (int)(reinterpret_cast<const unsigned char*>(V1) - base);
-        c.oF0 = (int)(reinterpret_cast<const unsigned char*>(F0) - base); c.oF1 = (int)(reinterpret_cast<const unsigned char*>(F1) - base);
+        c.oV0 = (int)(reinterpret_cast<const unsigned char*>(V0) - base);
+        c.oF0 = (int)(reinterpret_cast<const unsigned char*>(F0) - base);
         c.oHint = (int)(reinterpret_cast<const unsigned char*>(sHint) - base); c.oClr = (int)(reinterpret_cast<const unsigned char*>(sClr) - base);
         c.oHalo = (int)(reinterpret_cast<const unsigned char*>(sHalo) - base);
         c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
@@ -905,7 +905,7 @@ __device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const Path
         c.mr0 = __int_as_float(sMisc[10]); c.mr1 = __int_as_float(sMisc[11]);
         c.parity_ok = parity_ok; c.closed = true;
         c.base0 = basev[0]; c.base1 = basev[1]; c.len0 = nseg[0]; c.len1 = nseg[1];
-        c.gs0 = gseg + 4 * segI0; c.gs1 = gseg + 4 * segO0;
+        c.gs0 = gseg + 4 * segI0;   // ring 1's segment records follow ring 0's (segO0 = segI0 + M0)
     }
     if (!__syncthreads_and(linked)) return 0xffffffffu;
     unsigned flagged = 0u;

@@ -46,13 +46,21 @@ inline int class_for_n(int n)
     return -1;
 }
 
+// scratch area (barrier, reduction and halo exchange buffers, a few ints); the debug-checks and phase-timer builds keep
+// more words there.  The product size lets the T = 128 class keep four CTAs per SM next to the kernels' static shared
+// memory (job constants, 384 bytes).
+#if defined(RL_DEBUG_CHECKS) || defined(RL_PHASE_TIMERS)
+constexpr int kScratchBytes = 2048;
+#else
+constexpr int kScratchBytes = 1664;
+#endif
 // dynamic shared memory of one CTA of class (T,K): see layout in raceline_kernels.cu
 inline size_t smem_bytes_for_class(int T, int K)
 {
     const size_t np = (size_t)T * K;
     size_t b = np * 16      /* path points, double2            */
                + np * 8 * 4 /* region B: PGD coefficients+stash / ray tile+corridor staging */
-               + 2048       /* barriers, reduction + halo exchange scratch */
+               + kScratchBytes /* barriers, reduction + halo exchange scratch */
                + np * 6;    /* per-sample corridor state: anchor segments + parity bits (4 B), clearances (2 B) */
 #ifdef RL_DEBUG_CHECKS
     b += 4 * 64 + 2048;     /* four guard zones + the per-thread phase counters (raceline_kernels.cuh) */

@@ -44,7 +44,8 @@ constexpr int kScrRed = 64;             // [2][16][2] doubles
 constexpr int kScrExF = kScrRed + 512;  // [2][16][2] doubles: first two samples of each warp's lane 0
 constexpr int kScrExL = kScrExF + 512;  // [2][16][2] doubles: last two samples of each warp's lane 31
 constexpr int kScrMisc = kScrExL + 512; // a few ints
-constexpr int kScrBytes = 2048;         // followed by the per-sample corridor hint words [T*K]
+constexpr int kScrBytes = kScratchBytes; // (raceline_device.h) followed by the per-sample corridor hint words [T*K]
+static_assert(kScrMisc + 64 <= kScrBytes, "scratch layout");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -232,8 +233,12 @@ __device__ __forceinline__ void normal_at(const double2* sP, int i, int N, bool 
 // (the reference divides by 2h, h*h and h; <= 1 ulp apart, and six FP64 divisions per sample and outer iteration fewer)
 struct HStep {
     double h, inv_h, inv2h, invh2;
+    __device__ __forceinline__ HStep() {}
     __device__ __forceinline__ explicit HStep(double hh) : h(hh), inv_h(1.0 / hh), inv2h(1.0 / (2 * hh)), invh2(1.0 / (hh * hh)) {}
 };
+// solve_kernel keeps the current job's step constants in static shared memory (CTA-uniform; thread 0 writes them at the
+// start of the job), like the v(s) constants below: read where they are needed instead of held in registers for the job
+__shared__ double s_hstep[4];
 // central-difference derivatives of the `deriv` lambda (interior / periodic case), main.cpp:599-603 / 625-629
 __device__ __forceinline__ void derivs_central(double2 Pm, double2 Pc, double2 Pp, const HStep& H,
                                                double& xp, double& yp, double& xpp, double& ypp)
@@ -993,13 +998,14 @@ __device__ __forceinline__ bool ray_box(const float4 bx, float px, float py, flo
 // scan one ring for one sample.  bp/bn: running nearest +n / -n hit over both rings (pruning bound);
 // pos_r/neg_r: nearest hit found on THIS ring (INF if none inside the bound).  hint: box to start at.
 // Returns the segment of the nearest hit (-1 if none).
-__device__ __noinline__ int ray_scan(const RayTile& tl_in, double2 P, double nx, double ny, float px, float py, float fnx, float fny,
-                                        float m, int hint, bool wp, bool wn, bool first_hit_only,
-                                        double& bp_io, double& bn_io, double& pos_io, double& neg_io, long long& tests_io)
+// Arguments and results of the real (noinline) functions travel BY VALUE: a reference parameter (the tile description,
+// the in/out bounds) lives in the caller's local memory and is read and written back through L1 at every call.
+struct RayRes { double bp, bn, pos, neg; int seg, tests; };
+__device__ __noinline__ RayRes ray_scan_v(const RayTile tl_in, double2 P, double nx, double ny, float px, float py, float fnx, float fny,
+                                          float m, int hint, bool wp, bool wn, bool first_hit_only,
+                                          double bp, double bn, double pos_r, double neg_r)
 {
-    // a real function (one copy): keep the tile description and the in/out values in registers
     const RayTile tl = tile_in_smem(tl_in);
-    double bp = bp_io, bn = bn_io, pos_r = pos_io, neg_r = neg_io;
     int tests = 0;
     const double INF = dinf();
     const float anx = fabsf(fnx), any = fabsf(fny);
@@ -1050,13 +1056,23 @@ __device__ __noinline__ int ray_scan(const RayTile& tl_in, double2 P, double nx,
         }
     }
 done:
-    bp_io = bp; bn_io = bn; pos_io = pos_r; neg_io = neg_r; tests_io += tests;
-    return best_box;
+    RayRes r;
+    r.bp = bp; r.bn = bn; r.pos = pos_r; r.neg = neg_r; r.seg = best_box; r.tests = tests;
+    return r;
+}
+// the in/out form the callers use (inlined: its references are the caller's registers)
+__device__ __forceinline__ int ray_scan(const RayTile& tl, double2 P, double nx, double ny, float px, float py, float fnx, float fny,
+                                        float m, int hint, bool wp, bool wn, bool first_hit_only,
+                                        double& bp_io, double& bn_io, double& pos_io, double& neg_io, long long& tests_io)
+{
+    const RayRes r = ray_scan_v(tl, P, nx, ny, px, py, fnx, fny, m, hint, wp, wn, first_hit_only, bp_io, bn_io, pos_io, neg_io);
+    bp_io = r.bp; bn_io = r.bn; pos_io = r.pos; neg_io = r.neg; tests_io += r.tests;
+    return r.seg;
 }
 
 // nearest point-segment distance to the ring (minDistanceToSegments_global, main.cpp:501-512); ub: any known
 // upper bound (a hit point lies on the ring) or INF.
-__device__ __noinline__ double dist_scan(const RayTile& tl_in, double2 P, float px, float py, float m, int hint, double ub)
+__device__ __noinline__ double dist_scan(const RayTile tl_in, double2 P, float px, float py, float m, int hint, double ub)
 {
     const RayTile tl = tile_in_smem(tl_in);
     const double INF = dinf();
@@ -1106,7 +1122,7 @@ __device__ __noinline__ double dist_scan(const RayTile& tl_in, double2 P, float 
 }
 
 // parity of the crossings of the +x ray from P with a CLOSED chain (vertices shared bit for bit): P inside?
-__device__ __noinline__ bool inside_ring(const RayTile& tl_in, double2 P, float px, float py, float m)
+__device__ __noinline__ bool inside_ring(const RayTile tl_in, double2 P, float px, float py, float m)
 {
     const RayTile tl = tile_in_smem(tl_in);
     int cnt = 0;
@@ -1302,7 +1318,7 @@ __device__ __forceinline__ double window_dist(const RayTile& tl, double2 P, floa
 
 // conservative (rounded down) distance from p to every segment of the ring outside the window of j0
 // s_off / m_ring: the tile holds segments [s_off, s_off + nt) of a ring of m_ring segments (a streamed ring); j0 is ring-global
-__device__ __noinline__ float clearance_scan(const RayTile& tl_in, float px, float py, float m, int j0, int s_off = 0, int m_ring = -1)
+__device__ __noinline__ float clearance_scan(const RayTile tl_in, float px, float py, float m, int j0, int s_off = 0, int m_ring = -1)
 {
     const RayTile tl = tile_in_smem(tl_in);
     const int M = (m_ring < 0) ? tl.nt : m_ring;
@@ -1368,7 +1384,7 @@ __device__ __forceinline__ bool cone_prune(const float4 bx, float ax, float ay, 
 // largest cosine of the angle between the unit axis (dx,dy) and any point of the ring seen from the apex (ax,ay)
 // (tile coordinates), rounded UP.  Returns 2 when no cone exists (a segment crosses the axis ahead of the apex, or
 // FP32 cannot tell).  Along a segment that does not cross the forward axis the angle is extremal at its end points.
-__device__ __noinline__ float cone_scan(const RayTile& tl_in, float ax, float ay, float dx, float dy, float m, int hint)
+__device__ __noinline__ float cone_scan(const RayTile tl_in, float ax, float ay, float dx, float dy, float m, int hint)
 {
     const RayTile tl = tile_in_smem(tl_in);
     const float e = 2.f * m + 1e-6f;
@@ -1423,9 +1439,13 @@ __device__ __forceinline__ void cert_axis(unsigned w1, double& dx, double& dy)
 // does the ray of direction `dir` (0: +n, 1: -n) from the sample hit the ring at all?  (certificates: see above)
 // certificate word: w0 = state[1:0] | ring[2] | dir[3] | cos(half-angle) [31:16];  w1 = cone axis (2 x int16) or the
 // far-hit segment; apex word: the cone apex relative to the centre-line sample, 2 floats.
-__device__ __noinline__ bool far_hit_exists(const RayTile& tl, const ExQuery& qy, unsigned long long* __restrict__ gcert,
-                                            unsigned long long* __restrict__ gapex, long long& tests_io, int& scans_io)
+struct ExRes { int tests, scans; bool ex; };
+__device__ __noinline__ ExRes far_hit_exists_v(const RayTile tl, const ExQuery& qy, unsigned long long* __restrict__ gcert,
+                                               unsigned long long* __restrict__ gapex)
 {
+    long long tests_io = 0;
+    int scans_io = 0;
+    ExRes res; res.tests = 0; res.scans = 0; res.ex = false;
     const double INF = dinf();
     const int i = qy.i, dir = qy.dir;
     const double2 Pc = qy.P;
@@ -1440,7 +1460,7 @@ __device__ __noinline__ bool far_hit_exists(const RayTile& tl, const ExQuery& qy
         if (f < qy.mr) {
             double tp = INF, tn = INF; int s_p = -1, s_n = -1;
             seg_hit(tl.segD + 4 * f, Pc, nx, ny, tp, tn, f, s_p, s_n, tests);
-            if ((dir ? tn : tp) < INF) { tests_io += tests; return true; }
+            if ((dir ? tn : tp) < INF) { res.tests = (int)tests; res.ex = true; return res; }
         }
     } else if (mine && (w0 & 3u) == kCertCone) {
         double d0x, d0y;
@@ -1448,7 +1468,7 @@ __device__ __noinline__ bool far_hit_exists(const RayTile& tl, const ExQuery& qy
         const double cc = (double)(w0 >> 16) * (1.0 / 32767.0) - 1.0 + 2e-6;
         const double ux = (Pc.x - qy.cx0) - (double)__uint_as_float((unsigned)qy.apex);
         const double uy = (Pc.y - qy.cy0) - (double)__uint_as_float((unsigned)(qy.apex >> 32));
-        if (ux * d0x + uy * d0y >= sqrt(ux * ux + uy * uy) * cc && sg * (nx * d0x + ny * d0y) >= cc) return false;
+        if (ux * d0x + uy * d0y >= sqrt(ux * ux + uy * uy) * cc && sg * (nx * d0x + ny * d0y) >= cc) return res;
     }
     // ---- no certificate applies: full search, then leave a certificate for the next builds ----
     double ubp = INF, ubn = INF, pr = INF, nr = INF;
@@ -1479,7 +1499,15 @@ __device__ __noinline__ bool far_hit_exists(const RayTile& tl, const ExQuery& qy
         gcert[i] = ((unsigned long long)nw1 << 32) | (unsigned long long)nw0;
         gapex[i] = ((unsigned long long)__float_as_uint(oyf) << 32) | (unsigned long long)__float_as_uint(oxf);
     }
-    return ex;
+    res.tests = (int)tests_io; res.scans = scans_io; res.ex = ex;
+    return res;
+}
+__device__ __forceinline__ bool far_hit_exists(const RayTile& tl, const ExQuery& qy, unsigned long long* __restrict__ gcert,
+                                               unsigned long long* __restrict__ gapex, long long& tests_io, int& scans_io)
+{
+    const ExRes r = far_hit_exists_v(tl, qy, gcert, gapex);
+    tests_io += r.tests; scans_io += r.scans;
+    return r.ex;
 }
 
 template <int T, int K>
@@ -1755,17 +1783,21 @@ __device__ __forceinline__ void staged_bounds_home(const Part& pt, const double*
 // which also refreshes its anchors / clearances / certificates.  Returns the flag mask (bit j = sample tid + j*T).
 struct UpdCtx {
     // byte offsets into the CTA's dynamic shared memory (pointers rebuilt from the extern array keep the loads LDS)
-    int oV0, oV1, oF0, oF1, oHint, oClr;
-    const double* gcenter; const unsigned long long* gcert; const unsigned long long* gapex;
-    double ox, oy, guard;
+    // (ring 1's arrays follow ring 0's: V1 = V0 + len0 + 1, F1 = F0 + len0 + 1)
+    int oV0, oF0, oHint, oClr, oHalo;
     int N, M0, M1, rf0, rf1;
-    float mr0, mr1;
-    bool parity_ok, closed;
     // LOCAL form (a chunk of a long track): shared memory holds vertices [base, base + len] of each ring only; the
-    // path has one halo point each side (oHalo); FAR segments outside the range come from global memory (gs0/gs1)
-    int base0, base1, len0, len1, oHalo;
-    const double* gs0; const double* gs1;
+    // path has one halo point each side (oHalo); FAR segments outside the range come from global memory (gs0; ring 1's
+    // records follow ring 0's: gs0 + 4 * M0)
+    int base0, base1, len0, len1;
+    float mr0, mr1;
+    int parity_ok, closed;
+    const double* gcenter; const unsigned long long* gcert; const unsigned long long* gapex; const double* gs0;
+    double ox, oy, guard;
 };
+// it lives in static shared memory, which is rounded up to the 128-byte alignment of the dynamic part: the cluster kernel's
+// two CTAs per SM have exactly that much room
+static_assert(sizeof(UpdCtx) <= 128, "UpdCtx must fit one 128-byte unit of static shared memory");
 // ring-global segment index -> index into the chunk-local vertex arrays
 __device__ __forceinline__ int loc_idx(int sg, int base, int M) { const int li = sg - base; return (li < 0) ? li + M : li; }
 // one sample of corridor_update: true = FLAGGED (hv/lv untouched), else the corridor bounds hv >= 0 >= lv
@@ -1781,9 +1813,9 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
     const UpdCtx& c = s_upd;
     const double2* sP = reinterpret_cast<const double2*>(smem_raw);
     const double2* cV0 = reinterpret_cast<const double2*>(smem_raw + c.oV0);
-    const double2* cV1 = reinterpret_cast<const double2*>(smem_raw + c.oV1);
+    const double2* cV1 = cV0 + (c.len0 + 1);
     const float2* cF0 = reinterpret_cast<const float2*>(smem_raw + c.oF0);
-    const float2* cF1 = reinterpret_cast<const float2*>(smem_raw + c.oF1);
+    const float2* cF1 = cF0 + (c.len0 + 1);
     const double INF = dinf();
     long long ray_tests = 0;
     const double2 Pc = sP[i];
@@ -1876,6 +1908,9 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
                     }
                     sg = (sg + 1 == M) ? 0 : sg + 1;
                 }
+                // the exact window distance is at least the FP32 minimum less the margin: when even that cannot undercut
+                // the certified hit b, the point distance does not matter (main.cpp:696) and is not computed
+                if ((double)(sqrtf(dminf) * (1.f - 2e-6f) - 8.f * m) >= b) continue;
                 const float lim = sqrtf(dminf) + 8.f * m;
                 const float lim2 = lim * lim * (1.f + 1e-5f);
                 double best2 = INF;
@@ -1915,7 +1950,7 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
                             double2 a, bb;
                             const int li = LOCAL ? loc_idx(fq, ring ? c.base1 : c.base0, M) : fq;
                             if (LOCAL && li >= (ring ? c.len1 : c.len0)) {     // far away: the segment record itself (x0,y0,x1,y1)
-                                const double* g = (ring ? c.gs1 : c.gs0) + 4 * (size_t)fq;
+                                const double* g = c.gs0 + 4 * ((size_t)fq + (ring ? (size_t)c.M0 : 0));
                                 a = make_double2(g[0], g[1]); bb = make_double2(g[2], g[3]);
                             } else { a = V[li]; bb = V[li + 1]; }
                             const double sd[4] = {a.x, a.y, bb.x - a.x, bb.y - a.y};
@@ -1982,14 +2017,14 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
     if (tid == 0) {
         UpdCtx& c = s_upd;
         const unsigned char* base = reinterpret_cast<const unsigned char*>(sP);    // sP is the start of the dynamic shared memory
-        c.oV0 = (int)(reinterpret_cast<const unsigned char*>(V0) - base); c.oV1 = (int)(reinterpret_cast<const unsigned char*>(V1) - base);
-        c.oF0 = (int)(reinterpret_cast<const unsigned char*>(F0) - base); c.oF1 = (int)(reinterpret_cast<const unsigned char*>(F1) - base);
+        c.oV0 = (int)(reinterpret_cast<const unsigned char*>(V0) - base);
+        c.oF0 = (int)(reinterpret_cast<const unsigned char*>(F0) - base);
         c.oHint = (int)(reinterpret_cast<const unsigned char*>(sHint) - base); c.oClr = (int)(reinterpret_cast<const unsigned char*>(sClr) - base);
         c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
         c.ox = org.x; c.oy = org.y; c.guard = guard; c.N = N; c.M0 = M0; c.M1 = M1; c.rf0 = sMisc[8]; c.rf1 = sMisc[9];
         c.mr0 = __int_as_float(sMisc[10]); c.mr1 = __int_as_float(sMisc[11]);
         c.parity_ok = parity_ok; c.closed = closed;
-        c.base0 = 0; c.base1 = 0; c.len0 = M0; c.len1 = M1; c.oHalo = 0; c.gs0 = nullptr; c.gs1 = nullptr;
+        c.base0 = 0; c.base1 = 0; c.len0 = M0; c.len1 = M1; c.oHalo = 0; c.gs0 = nullptr;
     }
     block_sync<T>();
     unsigned flagged = 0u;
@@ -2114,6 +2149,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         for (int o = 0; o < RL_MAX_OUTER_LOG; ++o) {
             st->J0[o] = 0.0; st->Jend[o] = 0.0; st->lap_outer[o] = 0.0; st->acc_outer[o] = 0; st->bt_outer[o] = 0;
         }
+        *reinterpret_cast<HStep*>(s_hstep) = HStep(h);
         VPar& w = s_vpar;
         w.v_cap = C.v_cap_mps; w.a_lat_max = C.a_lat_max; w.kappa_eps = C.kappa_eps;
         {
@@ -2143,9 +2179,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
     const VPar& q = s_vpar;
 
     const long long segI0 = B.seg_off[2 * trk], segO0 = B.seg_off[2 * trk + 1], segE = B.seg_off[2 * trk + 2];
-    const HStep H(h);
-    const double inv2h = H.inv2h, invh2 = H.invh2;                       // DiffOps, main.cpp:547
-    const double lamJ = C.lambda_smooth * inv2h * inv2h;
+    const HStep& H = *reinterpret_cast<const HStep*>(s_hstep);          // h, 1/h, 1/(2h), 1/h^2 (DiffOps, main.cpp:547)
     long long ray_tests = 0;
     int vrounds = 0, ph = 0, ex_scans = 0;
     int acc_total = 0, bt_total = 0, ev_total = 0;
@@ -2288,7 +2322,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             if (k < cnt) {
                 const double gw = gam[k] * Wd[k];
                 c0 = gw * N0[k];
-                const double c1 = gw * A1[k] * inv2h, c2 = gw * A2[k] * invh2;
+                const double c1 = gw * A1[k] * H.inv2h, c2 = gw * A2[k] * H.invh2;
                 cp = c1 + c2; cm = c2 - c1;
                 if (OPEN) {   // DiffOpsOpen, main.cpp:563-575: D1 one-sided with 1/h at the ends, D2 zero there
                     const int i = start + k;
@@ -2317,6 +2351,7 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
         }
         RL_PH(3);   // stencil coefficients
         // =================== projected gradient with Armijo (main.cpp:723-742 / 996-1026) ===================
+        const double lamJ = C.lambda_smooth * H.inv2h * H.inv2h;
         const PgdOut po = pgd_outer<T, K, MODE>(pt, sLo, sHi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,
                                                  C.step_init, C.step_min, C.armijo_c, C.max_inner_iters);
         acc_total += po.acc; bt_total += po.bt; ev_total += po.ev;

@@ -810,6 +810,359 @@ __device__ __forceinline__ void corridor_search_c(const Part& pt, const PathView
     }
 }
 
+// ---- the searching path for a FEW flagged samples ------------------------------------------------------------------
+// After the first build the update path flags a handful of samples per chunk and outer iteration (round-2 timers: about
+// 100 per job, all because an existence certificate no longer applies), and corridor_search_c answers them by streaming
+// every tile of both rings through shared memory again: about 24 tile builds = 500 k cycles for 4 samples, during which
+// the other CTAs of the cluster wait at the next cluster barrier (30 % of a job).  Here the whole CTA works on ONE flagged
+// sample at a time straight from global memory (the rings are L2-resident): every thread takes every T-th segment of a
+// ring, runs the same FP32 side test and the same exact FP64 formulas (main.cpp:478-512) as ray_scan_seg / dist_scan /
+// clearance_scan / cone_scan, and block-wide minima replace the scan order (they do not depend on it: hits, distances
+// and clearances are minima over the ring; equal hits keep the lower segment index).  Results, per-sample state and
+// certificates are those of corridor_search_c(first = false).
+constexpr int kFewMax = 24;      // more flagged samples than this in one chunk: the tile-streaming search is cheaper
+
+// A ring streams from global memory (L2 or HBM: with 16,384-sample jobs the rings do not stay in L2) through two 30 KB
+// buffers in region B: TMA bulk copies of kFewChunk segment records (x0,y0 | x1,y1), the next chunk in flight while the
+// threads work on the current one -- no per-thread load latency chain.  fbar: the two mbarriers of the buffers (scratch
+// words sMisc[2..5]), fpar: their wait parities (kept by the kernel).  BODY sees four segments at a time: a4[u], b4[u] (end
+// points), sg4[u] (index in the ring), ok4[u] (false: past the end of the ring, the data repeat segment 0 of the group).
+constexpr int kFewChunk = 1024 - 64;   // 960 = 3.75 x 256: four segments per thread and chunk
+#define RL_FEW_FOREACH(gs_, mr_, BODY)                                                                                   \
+    if ((mr_) > 0) {                                                                                                     \
+        const int nch__ = ((mr_) + kFewChunk - 1) / kFewChunk;                                                           \
+        if (tid == 0) {                                                                                                  \
+            const uint32_t by__ = (uint32_t)min(kFewChunk, (mr_)) * 32u;                                                 \
+            fence_proxy_async(); mbar_expect_tx(fbar, by__); bulk_g2s(fbuf, (gs_), by__, fbar);                          \
+        }                                                                                                                \
+        for (int c__ = 0; c__ < nch__; ++c__) {                                                                          \
+            const int cb__ = c__ & 1;                                                                                    \
+            if (c__ + 1 < nch__ && tid == 0) {                                                                           \
+                const uint32_t by__ = (uint32_t)min(kFewChunk, (mr_) - (c__ + 1) * kFewChunk) * 32u;                      \
+                fence_proxy_async(); mbar_expect_tx(fbar + (cb__ ^ 1), by__);                                            \
+                bulk_g2s(fbuf + (cb__ ^ 1) * (kFewChunk * 4), (gs_) + 4 * (size_t)(c__ + 1) * kFewChunk, by__, fbar + (cb__ ^ 1)); \
+            }                                                                                                            \
+            mbar_wait(fbar + cb__, (fpar >> cb__) & 1u); fpar ^= (1u << cb__);                                           \
+            const int n__ = min(kFewChunk, (mr_) - c__ * kFewChunk);                                                     \
+            const double2* ch__ = reinterpret_cast<const double2*>(fbuf + cb__ * (kFewChunk * 4));                       \
+            /* 8 warps and one dependent chain per segment: the sweep is latency-bound, so the body gets FOUR segments    \
+               (a4/b4/sg4/ok4[u]) and is written branch-free over u, which lets the chains overlap */                    \
+            for (int s0__ = tid; s0__ < n__; s0__ += 4 * kcT) {                                                          \
+                double2 a4[4], b4[4]; int sg4[4]; bool ok4[4];                                                           \
+                _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                          \
+                    const int sl__ = s0__ + u * kcT;                                                                     \
+                    ok4[u] = sl__ < n__;                                                                                 \
+                    const int si__ = ok4[u] ? sl__ : s0__;                                                               \
+                    a4[u] = ch__[2 * si__]; b4[u] = ch__[2 * si__ + 1];                                                  \
+                    sg4[u] = c__ * kFewChunk + sl__;                                                                     \
+                }                                                                                                        \
+                { BODY }                                                                                                 \
+            }                                                                                                            \
+            __syncthreads();   /* the buffer is free for the chunk after next */                                         \
+        }                                                                                                                \
+    }
+// FP32 margin of ONE segment's copy relative to the job origin (the tiles use the largest of their segments)
+__device__ __forceinline__ float few_margin(float x0, float y0, float x1, float y1)
+{
+    return 2e-6f * fmaxf(fmaxf(fabsf(x0), fabsf(y0)), fmaxf(fabsf(x1), fabsf(y1))) + 1e-6f;
+}
+struct MinHit { double t; int s; };
+__device__ __forceinline__ void minhit_take(MinHit& a, double t, int sidx)
+{
+    if (t < a.t || (t == a.t && sidx >= 0 && (a.s < 0 || sidx < a.s))) { a.t = t; a.s = sidx; }
+}
+// block-wide lexicographic minimum of (t, s); every thread returns the same pair.  scratch: 2 * kcNW doubles.
+__device__ __forceinline__ MinHit block_minhit(MinHit v, double* scratch, int lane, int warp)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t2 = __shfl_xor_sync(kFull, v.t, o);
+        const int s2 = __shfl_xor_sync(kFull, v.s, o);
+        minhit_take(v, t2, s2);
+    }
+    __syncthreads();   // the scratch may still be read from the previous reduction
+    if (lane == 0) { scratch[2 * warp] = v.t; scratch[2 * warp + 1] = __longlong_as_double((long long)v.s); }
+    __syncthreads();
+    MinHit r; r.t = scratch[0]; r.s = (int)__double_as_longlong(scratch[1]);
+#pragma unroll
+    for (int w = 1; w < kcNW; ++w) minhit_take(r, scratch[2 * w], (int)__double_as_longlong(scratch[2 * w + 1]));
+    return r;
+}
+__device__ __forceinline__ double block_min_d(double v, double* scratch, int lane, int warp)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double r = scratch[0];
+#pragma unroll
+    for (int w = 1; w < kcNW; ++w) r = fmin(r, scratch[w]);
+    return r;
+}
+
+template <int K>
+__device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const PathView& pv, double* sB, int* sMisc, uint32_t& fpar,
+                                                      unsigned* sHint, unsigned short* sClr,
+                                                      const double* __restrict__ gseg, const double* __restrict__ gcenter,
+                                                      unsigned long long* __restrict__ gcert, unsigned long long* __restrict__ gapex,
+                                                      long long segI0, long long segO0, long long segE, double guard, unsigned mask,
+                                                      bool parity_ok, double (&loc)[K], double (&hic)[K], long long& ray_tests, int& ex_scans,
+                                                      double* tdbg = nullptr)
+{
+    constexpr int T = kcT;
+    const int tid = pt.tid, lane = pt.lane, warp = pt.warp;
+#ifdef RL_PHASE_TIMERS
+#define RL_TF(k) do { if (tdbg && tid == 0) { const long long t__ = clock64(); tdbg[k] += (double)(t__ - tf_last); tf_last = t__; } } while (0)
+    long long tf_last = clock64();
+#else
+#define RL_TF(k) do { } while (0)
+#endif
+    const double INF = dinf();
+    const float FINF = __int_as_float(0x7f800000);
+    int* sList = reinterpret_cast<int*>(sB);                 // region B is free between the update pass and the staging
+    double* sScr = sB + 64;                                  // reduction scratch behind the list
+    double* fbuf = sB + 128;                                 // the two stream buffers (2 x kFewChunk records)
+    uint64_t* fbar = reinterpret_cast<uint64_t*>(sMisc + 2);  // their mbarriers (initialised at kernel start)
+    static_assert(128 * 8 + 2 * kFewChunk * 32 <= kcT * K * 32, "stream buffers fit region B");
+    if (tid == 0) sMisc[0] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if ((mask >> j) & 1u) { const int slot = atomicAdd(&sMisc[0], 1); if (slot < kFewMax) sList[slot] = tid + j * T; }
+    __syncthreads();
+    const int nfl = sMisc[0];
+    if (nfl > kFewMax) return false;                         // uniform: the caller runs the tile-streaming search instead
+    const double2 org = pv.sP[0];
+    const int M[2] = {(int)(segO0 - segI0), (int)(segE - segO0)};
+    const int rfl[2] = {sMisc[8] & 1, sMisc[9] & 1};
+    const float mring[2] = {__int_as_float(sMisc[10]), __int_as_float(sMisc[11])};   // the margin the update passes allow for (>= any segment's)
+    long long tests = 0;
+    for (int q = 0; q < nfl; ++q) {
+        const int i = sList[q];
+        const double2 Pc = pv.sP[i];
+        double nx, ny;
+        normal_c(pv, i, nx, ny);
+        const float px = (float)(Pc.x - org.x), py = (float)(Pc.y - org.y), fnx = (float)nx, fny = (float)ny;
+        const float pm = 2e-6f * fmaxf(fabsf(px), fabsf(py));
+        MinHit hp[2], hn[2];
+        double dist[2] = {INF, INF};
+        float clr[2] = {3e18f, 3e18f};
+        const unsigned hw_old = sHint[i];
+        RL_TF(0);
+        // ---- sweep 1: exact nearest hits of both rays on both rings (ray_scan_seg without the box hierarchy); the
+        //      clearance is taken along the way for the OLD anchor, which the new one usually equals ----
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            MinHit bp, bn; bp.t = INF; bp.s = -1; bn.t = INF; bn.s = -1;
+            const double* gs = gseg + 4 * (r ? segO0 : segI0);
+            const int mr = M[r];
+            const bool clr_ok = (mr <= 8191 && mr > 2 * kWin + 1);
+            int anchor_old = ((hw_old >> (28 + r)) & 1u) ? (int)((hw_old >> (13 * r)) & 0x1fffu) : -1;
+            if (anchor_old >= mr || !clr_ok) anchor_old = -1;
+            float best = 64.f;
+            RL_FEW_FOREACH(gs, mr, {
+                float fx0[4]; float fy0[4]; float fx1[4]; float fy1[4]; float m4[4];
+                unsigned pass = 0u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    fx0[u] = (float)(a4[u].x - org.x); fy0[u] = (float)(a4[u].y - org.y);
+                    fx1[u] = (float)(b4[u].x - org.x); fy1[u] = (float)(b4[u].y - org.y);
+                    m4[u] = few_margin(fx0[u], fy0[u], fx1[u], fy1[u]) + pm;
+                    const float sa = fnx * (fy0[u] - py) - fny * (fx0[u] - px); const float sbb = fnx * (fy1[u] - py) - fny * (fx1[u] - px);
+                    if (ok4[u] && !(fminf(sa, sbb) > m4[u] || fmaxf(sa, sbb) < -m4[u])) pass |= (1u << u);
+                }
+                if (anchor_old >= 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        int dj = sg4[u] - anchor_old; if (dj < 0) dj += mr;
+                        const bool outside = ok4[u] && !(dj <= kWin || dj >= mr - kWin);
+                        const float d = sqrtf(seg_dist2_f(make_float4(fx0[u], fy0[u], fx1[u], fy1[u]), px, py)) - 4.f * m4[u];
+                        best = outside ? fminf(best, fmaxf(d, 0.f)) : best;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if ((pass >> u) & 1u) {                                                  // rare: the exact test (main.cpp:478-490)
+                        const double vx = b4[u].x - a4[u].x; const double vy = b4[u].y - a4[u].y;   // main.cpp:482
+                        const double den = nx * (-vy) + ny * vx;                         // main.cpp:483
+                        ++tests;
+                        if (!(fabs(den) < 1e-15)) {                                      // main.cpp:484
+                            const double ax = a4[u].x - Pc.x; const double ay = a4[u].y - Pc.y;  // main.cpp:485
+                            const double inv = 1.0 / den;
+                            const double t = (ax * (-vy) + ay * vx) * inv;              // main.cpp:486
+                            const double u2 = (nx * ay - ny * ax) * inv;                // main.cpp:487
+                            if (u2 >= -1e-12 && u2 <= 1.0 + 1e-12) {                    // main.cpp:488
+                                if (t > 0.0) minhit_take(bp, t, sg4[u]);                // +n ray, main.cpp:497
+                                else if (t < 0.0) minhit_take(bn, -t, sg4[u]);          // -n ray: t' = -t
+                            }
+                        }
+                    }
+                }
+            })
+            hp[r] = block_minhit(bp, sScr, lane, warp);
+            hn[r] = block_minhit(bn, sScr, lane, warp);
+            const int anchor = (hp[r].t <= hn[r].t) ? hp[r].s : hn[r].s;
+            if (anchor_old >= 0) {                           // uniform
+                const float c = (float)block_min_d((double)best, sScr, lane, warp);
+                if (anchor == anchor_old) clr[r] = c;
+            }
+        }
+        RL_TF(1);
+        // ---- sweep 2, only where needed: the clearance of a NEW anchor (clearance_scan) and, for a ring some ray misses,
+        //      the exact point-ring distance (dist_scan; main.cpp:501-512) ----
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int mr = M[r];
+            if (mr == 0) continue;
+            const int anchor = (hp[r].t <= hn[r].t) ? hp[r].s : hn[r].s;
+            const bool want_clr = (anchor >= 0 && mr <= 8191 && mr > 2 * kWin + 1) && !(clr[r] < 1e18f);
+            const bool want_dist = (hp[r].t == INF || hn[r].t == INF);
+            if (!want_clr && !want_dist) continue;
+            const double* gs = gseg + 4 * (r ? segO0 : segI0);
+            float best = 64.f;
+            double best2 = INF;
+            RL_FEW_FOREACH(gs, mr, {
+                if (want_clr) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        int dj = sg4[u] - anchor; if (dj < 0) dj += mr;
+                        const bool outside = ok4[u] && !(dj <= kWin || dj >= mr - kWin);
+                        const float4 f = make_float4((float)(a4[u].x - org.x), (float)(a4[u].y - org.y), (float)(b4[u].x - org.x), (float)(b4[u].y - org.y));
+                        const float m = few_margin(f.x, f.y, f.z, f.w) + pm;
+                        const float d = sqrtf(seg_dist2_f(f, px, py)) - 4.f * m;
+                        best = outside ? fminf(best, fmaxf(d, 0.f)) : best;
+                    }
+                }
+                if (want_dist) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double vx = b4[u].x - a4[u].x; const double vy = b4[u].y - a4[u].y;
+                        const double apx = Pc.x - a4[u].x; const double apy = Pc.y - a4[u].y;
+                        const double denom = fmax(1e-30, vx * vx + vy * vy);
+                        const double tt = fmin(1.0, fmax(0.0, (vx * apx + vy * apy) / denom));
+                        const double qx = a4[u].x + vx * tt; const double qy = a4[u].y + vy * tt;
+                        const double ex = Pc.x - qx; const double ey = Pc.y - qy;
+                        best2 = ok4[u] ? fmin(best2, ex * ex + ey * ey) : best2;
+                    }
+                }
+            })
+            if (want_clr) clr[r] = (float)block_min_d((double)best, sScr, lane, warp);
+            if (want_dist) { const double d2 = block_min_d(best2, sScr, lane, warp); dist[r] = (d2 < INF) ? sqrt(d2) : INF; }
+        }
+        RL_TF(2);
+        // ---- combine (main.cpp:696-710), per-sample state, certificate decision: as in corridor_search_c ----
+        double dpos = INF, dneg = INF;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            double vp, vn;
+            if (M[r] == 0) { vp = 0.0; vn = 0.0; }
+            else {
+                const double dd = (dist[r] < INF) ? dist[r] : 0.0;
+                vp = (hp[r].t < INF) ? hp[r].t : dd;
+                vn = (hn[r].t < INF) ? hn[r].t : dd;
+            }
+            dpos = fmin(dpos, fmax(0.0, vp));
+            dneg = fmin(dneg, fmax(0.0, vn));
+        }
+        double hv = fmax(0.0, dpos - guard), lv = -fmax(0.0, dneg - guard);
+        if (!isfinite(hv)) hv = 0.0;
+        if (!isfinite(lv)) lv = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (i == tid + j * T) { hic[j] = hv; loc[j] = lv; }
+        const double cx0 = gcenter[2 * i], cy0 = gcenter[2 * i + 1];
+        const float disp = __double2float_ru(sqrt((Pc.x - cx0) * (Pc.x - cx0) + (Pc.y - cy0) * (Pc.y - cy0))) * (1.f + 1e-6f);
+        unsigned hw = hw_old & (3u << 26);     // parity bits are kept
+        unsigned cw = 0u;
+        float rcv[2] = {0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int mr = M[r];
+            const int anchor = (hp[r].t <= hn[r].t) ? hp[r].s : hn[r].s;
+            if (anchor >= 0 && mr > 2 * kWin + 1 && mr <= 8191) {
+                const float cval = clr[r] - disp;
+                const unsigned cq = (cval >= 63.75f) ? 255u : (cval > 0.f ? (unsigned)(cval * 4.f) : 0u);
+                hw |= ((unsigned)anchor << (13 * r)) | (1u << (28 + r));
+                cw |= cq << (8 * r);
+                rcv[r] = 0.25f * (float)cq - disp - 4.f * (mring[r] * 1.001f + pm + 1e-5f);
+            }
+        }
+        __syncthreads();                          // every thread has read the old hint word
+        if (tid == 0) { sHint[i] = hw; sClr[i] = (unsigned short)cw; }
+        int cone_r = -1, cone_dir = 0;
+        unsigned long long cert_new = 0ull;
+        bool cert_set = false;
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const MinHit& h = dir ? hn[r] : hp[r];
+                if (h.t <= (double)rcv[r]) continue;                                  // a near hit: no question to answer
+                if (parity_ok && rfl[r] && ((hw >> (26 + r)) & 1u)) continue;        // inside a closed ring: every ray hits it
+                const unsigned key = ((unsigned)r << 2) | ((unsigned)dir << 3);
+                if (h.t < INF) { cert_new = ((unsigned long long)(unsigned)h.s << 32) | (unsigned long long)(key | kCertFar); cert_set = true; }
+                else { cone_r = r; cone_dir = dir; }
+            }
+        }
+        if (cert_set && tid == 0) gcert[i] = cert_new;
+        RL_TF(3);
+        // ---- a ring-free cone for the ray that misses (cone_scan over the whole ring) ----
+        if (cone_r >= 0) {
+            const int r = cone_r, dir = cone_dir;
+            const double sgn = dir ? -1.0 : 1.0;
+            const int qx = __double2int_rn(sgn * nx * 32767.0), qy = __double2int_rn(sgn * ny * 32767.0);
+            const unsigned nw1 = ((unsigned)qx & 0xffffu) | ((unsigned)qy << 16);
+            double d0x, d0y;
+            cert_axis(nw1, d0x, d0y);
+            const double toward = dir ? hp[r].t : hn[r].t;     // this ring's hit on the opposite ray
+            const double back = (toward < INF) ? fmax(0.0, toward - fmax(0.05, 0.5 * guard)) : 0.0;
+            const float oxf = (float)((Pc.x - cx0) - back * d0x), oyf = (float)((Pc.y - cy0) - back * d0y);
+            const double axd = cx0 + (double)oxf, ayd = cy0 + (double)oyf;
+            const float ax = (float)(axd - org.x), ay = (float)(ayd - org.y), dx = (float)d0x, dy = (float)d0y;
+            float cbest = 0.9396926f;
+            const double* gs = gseg + 4 * (r ? segO0 : segI0);
+            RL_FEW_FOREACH(gs, M[r], {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float fx0 = (float)(a4[u].x - org.x); const float fy0 = (float)(a4[u].y - org.y);
+                    const float fx1 = (float)(b4[u].x - org.x); const float fy1 = (float)(b4[u].y - org.y);
+                    const float e = 2.f * (few_margin(fx0, fy0, fx1, fy1) + pm) + 1e-6f;
+                    const float ux = fx0 - ax; const float uy = fy0 - ay; const float wx = fx1 - ax; const float wy = fy1 - ay;
+                    const float t1 = ux * dx + uy * dy; const float c1 = ux * dy - uy * dx;    // along / across the axis
+                    const float t2 = wx * dx + wy * dy; const float c2 = wx * dy - wy * dx;
+                    const float r1 = sqrtf(ux * ux + uy * uy); const float r2 = sqrtf(wx * wx + wy * wy);
+                    bool none = (r1 <= 8.f * e || r2 <= 8.f * e);                               // apex (almost) on the ring
+                    const bool crosses = !((c1 > e && c2 > e) || (c1 < -e && c2 < -e));
+                    const float ds = c1 - c2;
+                    const float tc = t1 + (t2 - t1) * __fdividef(c1, ds);
+                    none = none || (crosses && (fabsf(ds) < 16.f * e || tc > -e * (4.f + 2.f * __fdividef(fabsf(t2 - t1), fabsf(ds)))));
+                    const float k1 = __fdividef(t1 + e, r1) + 2e-6f; const float k2 = __fdividef(t2 + e, r2) + 2e-6f;
+                    const float cnew = none ? 2.f : fmaxf(k1, k2);
+                    cbest = ok4[u] ? fmaxf(cbest, cnew) : cbest;
+                }
+            })
+            const float cb = -(float)block_min_d(-(double)cbest, sScr, lane, warp);
+            if (tid == 0) {
+                const unsigned key = ((unsigned)r << 2) | ((unsigned)dir << 3);
+                unsigned nw0 = key | kCertNoCone;
+                if (cb < 0.9995f) {
+                    const unsigned qc = (unsigned)ceilf((cb + 1.f) * 32767.f + 0.5f);
+                    if (qc < 65535u) nw0 = key | kCertCone | (qc << 16);
+                }
+                gcert[i] = ((unsigned long long)nw1 << 32) | (unsigned long long)nw0;
+                gapex[i] = ((unsigned long long)__float_as_uint(oyf) << 32) | (unsigned long long)__float_as_uint(oxf);
+                ++ex_scans;
+            }
+        }
+        RL_TF(4);
+    }
+    (void)FINF;
+    ray_tests += tests;
+    __syncthreads();      // region B is handed on to the staging
+    return true;
+}
+
 // the UPDATE path of one chunk: returns the mask of samples the searching path has to rebuild
 template <int K>
 __device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const PathView& pv, double* sB, int* sMisc,
@@ -927,6 +1280,14 @@ __device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const Path
     return flagged;
 }
 
+// Development build only (-DRL_PHASE_TIMERS): thread 0 of CTA 0 adds clock64() cycles per phase to stats.J0[16..24]
+// (global memory; same phase numbering as solve_kernel)
+#ifdef RL_PHASE_TIMERS
+#define RL_PHC(i) do { if (threadIdx.x == 0 && cl.rank == 0) { const long long t__ = clock64(); st->J0[16 + (i)] += (double)(t__ - ph_last); ph_last = t__; } } while (0)
+#else
+#define RL_PHC(i) do { } while (0)
+#endif
+
 // ---- the cluster solver kernel -----------------------------------------------------------------------------
 template <int K, int MODE>
 __global__ void __launch_bounds__(kcT, 2)
@@ -961,11 +1322,13 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
     uint32_t bar_phase = 0;
     int fslot = 0, prev_trk = -1;
     uint64_t* ebar = reinterpret_cast<uint64_t*>(scr + kcEbar);   // per-evaluation exchange barriers: one arrival per local warp + tx bytes
-    uint32_t epar = 0;
+    uint32_t epar = 0, fpar = 0;
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         mbar_init(ebar, kcNW);
         mbar_init(ebar + 1, kcNW);
+        mbar_init(reinterpret_cast<uint64_t*>(sMisc + 2), 1);      // stream buffers of corridor_search_few_c
+        mbar_init(reinterpret_cast<uint64_t*>(sMisc + 4), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sFlag[0] = 0; sFlag[1] = 0; sFlag[2] = 0;
     }
@@ -1014,9 +1377,15 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             for (int o = 0; o < RL_MAX_OUTER_LOG; ++o) {
                 st->J0[o] = 0.0; st->Jend[o] = 0.0; st->lap_outer[o] = 0.0; st->acc_outer[o] = 0; st->bt_outer[o] = 0;
             }
+#ifdef RL_PHASE_TIMERS
+            for (int i = 0; i < 9; ++i) st->J0[16 + i] = 0.0;
+#endif
         }
         fence_proxy_async();
     }
+#ifdef RL_PHASE_TIMERS
+    long long ph_last = clock64();
+#endif
     block_sync<T>();
 
     // ---- load this chunk of the centre line (TMA bulk copy) and trade end points with the neighbours ----
@@ -1071,12 +1440,16 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         } else {
             unsigned flagged = corridor_update_c<K>(pt, pv, sB, sMisc, sHint, sClr, sHalo, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
                                                     guard0, parity_ok, loc, hic, ray_tests);
-            if (block_or<T>(flagged != 0u))
-                corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
-                                     guard0, flagged, false, parity_ok, loc, hic, ray_tests, ex_scans);
+            if (block_or<T>(flagged != 0u)) {
+                if (!corridor_search_few_c<K>(pt, pv, sB, sMisc, fpar, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                                              guard0, flagged, parity_ok, loc, hic, ray_tests, ex_scans))
+                    corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                                         guard0, flagged, false, parity_ok, loc, hic, ray_tests, ex_scans);
+            }
         }
         corridor_stage_out<T, K>(pt, sB, loc, hic);
     }
+    RL_PHC(0);   // setup + first corridor of the job
 
     double* sC0 = sB + tid;
     double* sCp = pair_base_a(sB + NP, NP, tid);
@@ -1108,6 +1481,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         double* sLo = pair_base_a(reinterpret_cast<double*>(sP), NP, tid);
         double* sHi = pair_base_b(reinterpret_cast<double*>(sP), NP, tid);
         staged_bounds_home<T, K>(pt, sB, sLo, sHi);   // the corridor's bounds: staging area -> their home for the PGD
+        RL_PHC(1);   // linearisation + parking the path
         double gam[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) gam[k] = 1.0;
@@ -1153,6 +1527,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             }
             block_sync<T>();
         }
+        RL_PHC(2);   // v(s) profile + time weights
         // ---- stencil coefficients into region B (slot-major); edge samples also go to the neighbour CTAs ----
         {
             double f0 = 0.0, fp = 0.0, fm = 0.0, l0 = 0.0, lp = 0.0, lm = 0.0;   // first / last owned sample
@@ -1192,6 +1567,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             // the first unused slot mirrors the right neighbour's first sample (position cnt+1 of the window)
             if (cnt < K) { sC0[cnt * T] = cR[0]; st_pair<T>(sCp, sCm, cnt, cR[1], cR[2]); }
         }
+        RL_PHC(3);   // stencil coefficients (+ their exchange)
         // =================== projected gradient with Armijo (main.cpp:723-742 / 996-1026) ===================
         const PgdOut po = pgd_outer_c<K, MODE>(pt, cl, sLo, sHi, cL, cR, sC0, sCp, sCm, sSt, sRed, sExF, sExL, ph, lamJ,
                                                C.step_init, C.step_min, C.armijo_c, C.max_inner_iters, ebar, epar);
@@ -1200,6 +1576,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             st->J0[outer] = po.J0; st->Jend[outer] = po.Jend; st->lap_outer[outer] = lap_outer;
             st->acc_outer[outer] = po.acc; st->bt_outer[outer] = po.bt;
         }
+        RL_PHC(4);   // projected-gradient loop
         // ---- bring the chunk of the path back ----
         block_sync<T>();
         if (tid == 0) {
@@ -1229,18 +1606,54 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         for (int k = 0; k < K; ++k) if (k < cnt) sP[start + k] = Pn[k];
         block_sync<T>();
         exchange_path_halo(sP, sHalo, cl, tid);
+        RL_PHC(5);   // path back + path update + halo exchange
         // =================== corridor from the new path (main.cpp:749-756 / 1033-1040) ===================
         // (the reference also rebuilds it after the LAST path update, but nothing reads that corridor: skipped)
         if (outer + 1 == max_outer) continue;
         {
             const double guard = C.veh_width_m * 0.5 + C.safety_margin_m;
             double loc[K], hic[K];
+#ifdef RL_PHASE_TIMERS
+            const long long tc0 = clock64();   // per-RANK corridor times (the other timers run on rank 0 only): Jend / lap_outer / acc_outer[16 + rank]
+#endif
             unsigned flagged = corridor_update_c<K>(pt, pv, sB, sMisc, sHint, sClr, sHalo, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
                                                     guard, parity_ok, loc, hic, ray_tests);
-            if (block_or<T>(flagged != 0u))   // per CTA: the searching path rebuilds the flagged samples (no cluster traffic inside)
-                corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
-                                     guard, flagged, false, parity_ok, loc, hic, ray_tests, ex_scans);
+            RL_PHC(6);   // corridor update pass
+#ifdef RL_PHASE_TIMERS
+            const long long tc1 = clock64();
+            int fb = 0;
+#endif
+            if (block_or<T>(flagged != 0u)) {  // per CTA: the searching path rebuilds the flagged samples (no cluster traffic inside)
+#ifdef RL_PHASE_TIMERS
+                const long long tf0 = clock64();
+#endif
+                const bool few = corridor_search_few_c<K>(pt, pv, sB, sMisc, fpar, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                                                          guard, flagged, parity_ok, loc, hic, ray_tests, ex_scans
+#ifdef RL_PHASE_TIMERS
+                                                          , (cl.rank == 0) ? &st->J0[25] : nullptr
+#endif
+                                                          );
+#ifdef RL_PHASE_TIMERS
+                if (tid == 0 && (cl.rank & 7) == cl.rank) {
+                    if (few) { st->Jend[24 + cl.rank] += (double)(clock64() - tf0); st->bt_outer[24 + cl.rank] += sMisc[0]; }
+                    else st->acc_outer[24 + cl.rank] += 1;
+                }
+#endif
+                if (!few)
+                    corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                                         guard, flagged, false, parity_ok, loc, hic, ray_tests, ex_scans);
+#ifdef RL_PHASE_TIMERS
+                fb = 1;
+#endif
+            }
             corridor_stage_out<T, K>(pt, sB, loc, hic);
+#ifdef RL_PHASE_TIMERS
+            if (tid == 0) {
+                const long long tc2 = clock64();
+                st->Jend[16 + cl.rank] += (double)(tc1 - tc0); st->lap_outer[16 + cl.rank] += (double)(tc2 - tc1); st->acc_outer[16 + cl.rank] += fb;
+            }
+#endif
+            RL_PHC(7);   // searching path for flagged samples + staging
         }
     }
 
@@ -1300,6 +1713,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             st->vpass_rounds = vrounds; st->ray_tests = (long long)rt; st->lap_time = lap; st->exist_scans = (int)es;
         }
     }
+    RL_PHC(8);   // certificates hand-over, final geometry, final v(s) profile, stores
     cl_sync();   // the next job of the chain reuses the shared-memory regions of every CTA
   }
 }

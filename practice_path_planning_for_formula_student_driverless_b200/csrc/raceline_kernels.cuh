@@ -1805,7 +1805,17 @@ __device__ __forceinline__ int loc_idx(int sg, int base, int M) { const int li =
 // (as an argument it sat in local memory and every call read its fields back through L1)
 __shared__ UpdCtx s_upd;
 // result of one sample, returned BY VALUE (registers): reference out-parameters of a real function live in local memory
-struct UpdRes { double hv, lv; int tests; bool flagged; };
+struct UpdRes { double hv, lv; int tests; bool flagged;
+#ifdef RL_PHASE_TIMERS
+    int why;   // development: which rule flagged the sample (bit 0 no state, 1 clearance used up, 2 window outside the local range,
+               // 3 window hit beyond Rc, 4 no certified bound, 5 FAR certificate failed, 6 CONE certificate failed, 7 no certificate)
+#endif
+};
+#ifdef RL_PHASE_TIMERS
+#define RL_WHY(b) (why |= (1 << (b)))
+#else
+#define RL_WHY(b) ((void)0)
+#endif
 template <bool LOCAL>
 __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double cy0, unsigned long long cert_w, unsigned long long apex_w)
 {
@@ -1834,6 +1844,9 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
     const float px = (float)(Pc.x - c.ox), py = (float)(Pc.y - c.oy), fnx = (float)nx, fny = (float)ny;
     const float pmax = 2e-6f * fmaxf(fabsf(px), fabsf(py)) + 1e-5f;
     bool flag = false;
+#ifdef RL_PHASE_TIMERS
+    int why = 0;
+#endif
     double w[2][2], Rc[2], wd[2];
     bool ins[2];
 #pragma unroll
@@ -1847,7 +1860,7 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
         if (j0 >= M) j0 = 0;
         const unsigned cq = (cw >> (8 * ring)) & 0xffu;
         const float rc = 0.25f * (float)cq - disp - 4.f * m;
-        if (!((hw >> (28 + ring)) & 1u) || !(rc > 0.f)) flag = true;
+        if (!((hw >> (28 + ring)) & 1u) || !(rc > 0.f)) { flag = true; RL_WHY(((hw >> (28 + ring)) & 1u) ? 1 : 0); }
         Rc[ring] = (double)rc;
         ins[ring] = c.parity_ok && (rf & 1) && ((hw >> (26 + ring)) & 1u);
         double pos = INF, neg = INF;
@@ -1857,7 +1870,7 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
         for (int q = 0; q < 2 * kWin + 1; ++q) {
             // side of the ray's line each end point lies on (FP32, margin m): both clearly on one side -> no hit
             const int li = LOCAL ? loc_idx(sg, ring ? c.base1 : c.base0, M) : sg;
-            if (LOCAL && li >= (ring ? c.len1 : c.len0)) flag = true;          // window outside the chunk-local range
+            if (LOCAL && li >= (ring ? c.len1 : c.len0)) { flag = true; RL_WHY(2); }         // window outside the chunk-local range
             else {
                 const float2 fa = F[li], fb = F[li + 1];
                 const float sa = fnx * (fa.y - py) - fny * (fa.x - px), sb = fnx * (fb.y - py) - fny * (fb.x - px);
@@ -1879,13 +1892,13 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
 #pragma unroll
         for (int ring = 0; ring < 2; ++ring) {
             if (w[ring][dir] <= Rc[ring]) b = fmin(b, w[ring][dir]);
-            else if (w[ring][dir] < INF) flag = true;            // a window hit that is not certified nearest
+            else if (w[ring][dir] < INF) { flag = true; RL_WHY(3); }           // a window hit that is not certified nearest
         }
         double res = b;
 #pragma unroll
         for (int ring = 0; ring < 2; ++ring) {
             if (w[ring][dir] < INF) continue;
-            if (!(b <= Rc[ring])) { flag = true; continue; }    // nothing certified undercuts this ring's far hits
+            if (!(b <= Rc[ring])) { flag = true; RL_WHY(4); continue; }    // nothing certified undercuts this ring's far hits
             if (ins[ring]) continue;                             // parity: it hits, beyond Rc >= b
             if (wd[ring] < 0.0) {
                 // exact point-ring distance over the window (minDistanceToSegments_global body, main.cpp:504-509)
@@ -1961,7 +1974,7 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
                                 const_cast<unsigned long long*>(c.gcert)[i] = ((unsigned long long)(unsigned)fq << 32) | (unsigned long long)w0;
                         }
                     }
-                    if (!hit) flag = true;
+                    if (!hit) { flag = true; RL_WHY(5); }
                 } else if (stt == kCertCone) {
                     double d0x, d0y;
                     cert_axis(w1, d0x, d0y);
@@ -1970,14 +1983,17 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
                     const double uy = (Pc.y - cy0) - (double)__uint_as_float((unsigned)(apex_w >> 32));
                     const double sgd = dir ? -1.0 : 1.0;
                     if (ux * d0x + uy * d0y >= sqrt(ux * ux + uy * uy) * cc && sgd * (nx * d0x + ny * d0y) >= cc) res = fmin(res, wd[ring]);
-                    else flag = true;
-                } else flag = true;
+                    else { flag = true; RL_WHY(6); }
+                } else { flag = true; RL_WHY(7); }
             }
         }
         dres[dir] = res;
     }
     UpdRes r;
     r.tests = (int)ray_tests; r.flagged = flag; r.hv = 0.0; r.lv = 0.0;
+#ifdef RL_PHASE_TIMERS
+    r.why = why;
+#endif
     if (flag) return r;
     double hv = fmax(0.0, fmax(0.0, dres[0]) - c.guard);
     double lv = -fmax(0.0, fmax(0.0, dres[1]) - c.guard);

@@ -60,6 +60,24 @@ def main():
         print(f"{stage}: mean {tot / 1e6:.3f} Mcycles per job, evals {np.mean([pb.out_stats[j].evals for j in idx]):.0f}")
         for i, nm in enumerate(NAMES):
             print(f"   {nm:38s} {100 * ph[:, i].mean() / tot:6.2f} %   {ph[:, i].mean() / 1e3:9.1f} kcycles")
+    if a.n > 4096:   # cluster kernel: per-rank corridor times (update pass | fallback + staging | outers with a fallback)
+        for stage, sl in (("min-curv", slice(0, None, 2)), ("min-time", slice(1, None, 2))):
+            idx = range(pb.n_jobs)[sl]
+            upd = np.array([[pb.out_stats[j].Jend[16 + r] for r in range(16)] for j in idx]).mean(axis=0)
+            fbk = np.array([[pb.out_stats[j].lap_outer[16 + r] for r in range(16)] for j in idx]).mean(axis=0)
+            nfb = np.array([[pb.out_stats[j].acc_outer[16 + r] for r in range(16)] for j in idx]).mean(axis=0)
+            print(f"{stage}: per rank kcycles per job: update " + " ".join(f"{x / 1e3:.0f}" for x in upd[:8]))
+            print(f"{stage}:                        fallback " + " ".join(f"{x / 1e3:.0f}" for x in fbk[:8]))
+            print(f"{stage}:           outers with a fallback " + " ".join(f"{x:.1f}" for x in nfb[:8]))
+            fewt = np.array([[pb.out_stats[j].Jend[24 + r] for r in range(8)] for j in idx]).mean(axis=0)
+            fewn = np.array([[pb.out_stats[j].bt_outer[24 + r] for r in range(8)] for j in idx]).mean(axis=0)
+            tile = np.array([[pb.out_stats[j].acc_outer[24 + r] for r in range(8)] for j in idx]).mean(axis=0)
+            print(f"{stage}: few-sample search kcycles per job " + " ".join(f"{x / 1e3:.0f}" for x in fewt) + " | samples " + " ".join(f"{x:.1f}" for x in fewn)
+                  + " | tile-streaming searches " + " ".join(f"{x:.2f}" for x in tile))
+    if a.n > 4096:
+        idx = range(pb.n_jobs)
+        tf = np.array([[pb.out_stats[j].J0[25 + k] for k in range(5)] for j in idx]).mean(axis=0)
+        print("rank 0 few-sample search, kcycles per job: setup %.0f | sweep 1 %.0f | sweep 2 %.0f | combine + state %.0f | cone %.0f" % tuple(tf / 1e3))
     ctx.close()
 
 

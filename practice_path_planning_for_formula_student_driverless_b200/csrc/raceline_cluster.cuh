@@ -822,45 +822,95 @@ __device__ __forceinline__ void corridor_search_c(const Part& pt, const PathView
 // certificates are those of corridor_search_c(first = false).
 constexpr int kFewMax = 24;      // more flagged samples than this in one chunk: the tile-streaming search is cheaper
 
-// A ring streams from global memory (L2 or HBM: with 16,384-sample jobs the rings do not stay in L2) through two 30 KB
-// buffers in region B: TMA bulk copies of kFewChunk segment records (x0,y0 | x1,y1), the next chunk in flight while the
-// threads work on the current one -- no per-thread load latency chain.  fbar: the two mbarriers of the buffers (scratch
-// words sMisc[2..5]), fpar: their wait parities (kept by the kernel).  BODY sees four segments at a time: a4[u], b4[u] (end
-// points), sg4[u] (index in the ring), ok4[u] (false: past the end of the ring, the data repeat segment 0 of the group).
-constexpr int kFewChunk = 1024 - 64;   // 960 = 3.75 x 256: four segments per thread and chunk
-#define RL_FEW_FOREACH(gs_, mr_, BODY)                                                                                   \
+// Every job leaves an exact bounding box (xmin, ymin, xmax, ymax) per GROUP of 32 consecutive segments of each ring in
+// global memory (few_boxes_build: the job's ax rows, which nothing else touches before the final profile).  A pass over a
+// ring first tests the boxes (one per thread) and lists the groups that can matter -- the ray's line crosses the box, the
+// box is within the radius a distance or clearance question reaches, the box is not wholly outside the 20-degree cone --
+// and then one warp takes one listed group at a time, one lane per segment.  About 30 of the 233 groups of a 7447-segment
+// ring survive; the culled ones provably cannot change a minimum (the tests are exact FP64 box geometry with slack).
+// BODY sees a4[u], b4[u] (end points), sg4[u] (index in the ring), ok4[u] (false: past the end of the ring) for
+// u < kFewW; PRED is an expression over the box `bx`.
+constexpr int kFewW = 1;
+constexpr int kFewMaxGroups = 1024;        // listed groups fit 4 KB of region B: rings of up to 32,768 segments
+#define RL_FEW_FOREACH(gs_, mr_, gbox_, PRED, BODY)                                                                      \
     if ((mr_) > 0) {                                                                                                     \
-        const int nch__ = ((mr_) + kFewChunk - 1) / kFewChunk;                                                           \
-        if (tid == 0) {                                                                                                  \
-            const uint32_t by__ = (uint32_t)min(kFewChunk, (mr_)) * 32u;                                                 \
-            fence_proxy_async(); mbar_expect_tx(fbar, by__); bulk_g2s(fbuf, (gs_), by__, fbar);                          \
+        const int ng__ = ((mr_) + 31) >> 5;                                                                              \
+        __syncthreads();               /* the list of the previous pass has been consumed */                             \
+        if (tid == 0) sMisc[0] = 0;                                                                                      \
+        __syncthreads();                                                                                                 \
+        for (int g__ = tid; g__ < ng__; g__ += kcT) {                                                                    \
+            const double2 lo__ = __ldcg(reinterpret_cast<const double2*>((gbox_) + 4 * (size_t)g__));                    \
+            const double2 hi__ = __ldcg(reinterpret_cast<const double2*>((gbox_) + 4 * (size_t)g__ + 2));                \
+            const double4 bx = make_double4(lo__.x, lo__.y, hi__.x, hi__.y);                                             \
+            if (PRED) sCand[atomicAdd(&sMisc[0], 1)] = g__;                                                              \
         }                                                                                                                \
-        for (int c__ = 0; c__ < nch__; ++c__) {                                                                          \
-            const int cb__ = c__ & 1;                                                                                    \
-            if (c__ + 1 < nch__ && tid == 0) {                                                                           \
-                const uint32_t by__ = (uint32_t)min(kFewChunk, (mr_) - (c__ + 1) * kFewChunk) * 32u;                      \
-                fence_proxy_async(); mbar_expect_tx(fbar + (cb__ ^ 1), by__);                                            \
-                bulk_g2s(fbuf + (cb__ ^ 1) * (kFewChunk * 4), (gs_) + 4 * (size_t)(c__ + 1) * kFewChunk, by__, fbar + (cb__ ^ 1)); \
-            }                                                                                                            \
-            mbar_wait(fbar + cb__, (fpar >> cb__) & 1u); fpar ^= (1u << cb__);                                           \
-            const int n__ = min(kFewChunk, (mr_) - c__ * kFewChunk);                                                     \
-            const double2* ch__ = reinterpret_cast<const double2*>(fbuf + cb__ * (kFewChunk * 4));                       \
-            /* 8 warps and one dependent chain per segment: the sweep is latency-bound, so the body gets FOUR segments    \
-               (a4/b4/sg4/ok4[u]) and is written branch-free over u, which lets the chains overlap */                    \
-            for (int s0__ = tid; s0__ < n__; s0__ += 4 * kcT) {                                                          \
-                double2 a4[4], b4[4]; int sg4[4]; bool ok4[4];                                                           \
-                _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                          \
-                    const int sl__ = s0__ + u * kcT;                                                                     \
-                    ok4[u] = sl__ < n__;                                                                                 \
-                    const int si__ = ok4[u] ? sl__ : s0__;                                                               \
-                    a4[u] = ch__[2 * si__]; b4[u] = ch__[2 * si__ + 1];                                                  \
-                    sg4[u] = c__ * kFewChunk + sl__;                                                                     \
-                }                                                                                                        \
-                { BODY }                                                                                                 \
-            }                                                                                                            \
-            __syncthreads();   /* the buffer is free for the chunk after next */                                         \
+        __syncthreads();                                                                                                 \
+        const int nc__ = sMisc[0];                                                                                       \
+        for (int ci__ = warp; ci__ < nc__; ci__ += kcNW) {                                                               \
+            const int g__ = sCand[ci__];                                                                                 \
+            double2 a4[kFewW], b4[kFewW]; int sg4[kFewW]; bool ok4[kFewW];                                               \
+            sg4[0] = 32 * g__ + lane; ok4[0] = sg4[0] < (mr_);                                                           \
+            const size_t si__ = (size_t)(ok4[0] ? sg4[0] : 32 * g__);                                                    \
+            a4[0] = __ldg(reinterpret_cast<const double2*>(gs_) + 2 * si__);                                             \
+            b4[0] = __ldg(reinterpret_cast<const double2*>(gs_) + 2 * si__ + 1);                                         \
+            { BODY }                                                                                                     \
         }                                                                                                                \
     }
+// box tests (exact FP64 geometry; the slack covers the rounding of the few operations and the 1e-12 tolerance of main.cpp:488)
+__device__ __forceinline__ bool few_box_line(const double4 bx, double2 P, double nx, double ny)
+{
+    const double cx = 0.5 * (bx.x + bx.z) - P.x, cy = 0.5 * (bx.y + bx.w) - P.y, hx = 0.5 * (bx.z - bx.x), hy = 0.5 * (bx.w - bx.y);
+    return fabs(nx * cy - ny * cx) <= (fabs(nx) * hy + fabs(ny) * hx) * (1.0 + 1e-9) + 1e-9 * (fabs(cx) + fabs(cy) + 1.0);
+}
+__device__ __forceinline__ bool few_box_near(const double4 bx, double2 P, double R)
+{
+    const double dx = fmax(0.0, fmax(bx.x - P.x, P.x - bx.z)), dy = fmax(0.0, fmax(bx.y - P.y, P.y - bx.w));
+    return !(dx * dx + dy * dy > R * R * (1.0 + 1e-9) + 1e-9);      // R = INF: every box
+}
+// false: no point of the box is seen from the apex within 20 degrees of the axis (cone_scan never looks wider)
+__device__ __forceinline__ bool few_box_cone(const double4 bx, double ax, double ay, double dx, double dy)
+{
+    const double cx = 0.5 * (bx.x + bx.z) - ax, cy = 0.5 * (bx.y + bx.w) - ay, hx = 0.5 * (bx.z - bx.x), hy = 0.5 * (bx.w - bx.y);
+    const double R2 = (hx * hx + hy * hy) * (1.0 + 1e-6) + 1e-6, r2 = cx * cx + cy * cy;
+    if (r2 <= R2 * 1.001) return true;                         // apex inside (or at) the box's disk
+    const double ir = 1.0 / sqrt(r2);
+    const double ct = (cx * dx + cy * dy) * ir, so = sqrt(R2) * ir;
+    const double co = sqrt(fmax(0.0, 1.0 - so * so));
+    if (ct >= co - 1e-6) return true;                          // the axis passes through (or close to) the disk
+    const double st = sqrt(fmax(0.0, 1.0 - ct * ct));
+    return ct * co + st * so + 1e-5 > 0.9396926;              // cos(theta_c - omega) against cos(20 degrees), with slack
+}
+// the boxes of one job: groups are dealt to the warps of the whole cluster; a cluster barrier must follow before any read
+__device__ __forceinline__ void few_boxes_build(const Clu& cl, int tid, const double* __restrict__ gseg, long long segI0, long long segO0,
+                                                long long segE, double* __restrict__ gbox)
+{
+    const int lane = tid & 31, gw = (int)cl.rank * kcNW + (tid >> 5), nw = (int)cl.CS * kcNW;
+    const double INF = dinf();
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+        const double* gs = gseg + 4 * (r ? segO0 : segI0);
+        const int mr = (int)(r ? (segE - segO0) : (segO0 - segI0));
+        const int ng = (mr + 31) >> 5;
+        double* gb = gbox + (r ? 4 * (size_t)(((int)(segO0 - segI0) + 31) >> 5) : 0);
+        for (int g = gw; g < ng; g += nw) {
+            const int sg = 32 * g + lane;
+            double xmin = INF, ymin = INF, xmax = -INF, ymax = -INF;
+            if (sg < mr) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(gs) + 2 * (size_t)sg), b = __ldg(reinterpret_cast<const double2*>(gs) + 2 * (size_t)sg + 1);
+                xmin = fmin(a.x, b.x); xmax = fmax(a.x, b.x); ymin = fmin(a.y, b.y); ymax = fmax(a.y, b.y);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                xmin = fmin(xmin, __shfl_xor_sync(kFull, xmin, o)); ymin = fmin(ymin, __shfl_xor_sync(kFull, ymin, o));
+                xmax = fmax(xmax, __shfl_xor_sync(kFull, xmax, o)); ymax = fmax(ymax, __shfl_xor_sync(kFull, ymax, o));
+            }
+            if (lane == 0) {
+                __stcg(reinterpret_cast<double2*>(gb + 4 * (size_t)g), make_double2(xmin, ymin));
+                __stcg(reinterpret_cast<double2*>(gb + 4 * (size_t)g + 2), make_double2(xmax, ymax));
+            }
+        }
+    }
+}
 // FP32 margin of ONE segment's copy relative to the job origin (the tiles use the largest of their segments)
 __device__ __forceinline__ float few_margin(float x0, float y0, float x1, float y1)
 {
@@ -902,7 +952,7 @@ __device__ __forceinline__ double block_min_d(double v, double* scratch, int lan
 }
 
 template <int K>
-__device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const PathView& pv, double* sB, int* sMisc, uint32_t& fpar,
+__device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const PathView& pv, double* sB, int* sMisc, const double* __restrict__ gbox,
                                                       unsigned* sHint, unsigned short* sClr,
                                                       const double* __restrict__ gseg, const double* __restrict__ gcenter,
                                                       unsigned long long* __restrict__ gcert, unsigned long long* __restrict__ gapex,
@@ -921,10 +971,12 @@ __device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const Path
     const double INF = dinf();
     const float FINF = __int_as_float(0x7f800000);
     int* sList = reinterpret_cast<int*>(sB);                 // region B is free between the update pass and the staging
-    double* sScr = sB + 64;                                  // reduction scratch behind the list
-    double* fbuf = sB + 128;                                 // the two stream buffers (2 x kFewChunk records)
-    uint64_t* fbar = reinterpret_cast<uint64_t*>(sMisc + 2);  // their mbarriers (initialised at kernel start)
-    static_assert(128 * 8 + 2 * kFewChunk * 32 <= kcT * K * 32, "stream buffers fit region B");
+    double* sScr = sB + 16;                                  // reduction scratch (16 doubles) behind the list
+    int* sCand = reinterpret_cast<int*>(sB + 32);            // groups a pass has to visit (<= kFewMaxGroups)
+    const int M[2] = {(int)(segO0 - segI0), (int)(segE - segO0)};
+    const int ngr[2] = {(M[0] + 31) >> 5, (M[1] + 31) >> 5};
+    if (ngr[0] > kFewMaxGroups || ngr[1] > kFewMaxGroups || !gbox) return false;
+    const double* gbx[2] = {gbox, gbox + 4 * (size_t)ngr[0]};
     if (tid == 0) sMisc[0] = 0;
     __syncthreads();
 #pragma unroll
@@ -933,8 +985,8 @@ __device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const Path
     __syncthreads();
     const int nfl = sMisc[0];
     if (nfl > kFewMax) return false;                         // uniform: the caller runs the tile-streaming search instead
+    __syncthreads();                                         // every thread has read the count before a pass reuses the word
     const double2 org = pv.sP[0];
-    const int M[2] = {(int)(segO0 - segI0), (int)(segE - segO0)};
     const int rfl[2] = {sMisc[8] & 1, sMisc[9] & 1};
     const float mring[2] = {__int_as_float(sMisc[10]), __int_as_float(sMisc[11])};   // the margin the update passes allow for (>= any segment's)
     long long tests = 0;
@@ -961,11 +1013,11 @@ __device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const Path
             int anchor_old = ((hw_old >> (28 + r)) & 1u) ? (int)((hw_old >> (13 * r)) & 0x1fffu) : -1;
             if (anchor_old >= mr || !clr_ok) anchor_old = -1;
             float best = 64.f;
-            RL_FEW_FOREACH(gs, mr, {
-                float fx0[4]; float fy0[4]; float fx1[4]; float fy1[4]; float m4[4];
+            RL_FEW_FOREACH(gs, mr, gbx[r], (few_box_line(bx, Pc, nx, ny) || (anchor_old >= 0 && few_box_near(bx, Pc, 64.5))), {
+                float fx0[kFewW]; float fy0[kFewW]; float fx1[kFewW]; float fy1[kFewW]; float m4[kFewW];
                 unsigned pass = 0u;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kFewW; ++u) {
                     fx0[u] = (float)(a4[u].x - org.x); fy0[u] = (float)(a4[u].y - org.y);
                     fx1[u] = (float)(b4[u].x - org.x); fy1[u] = (float)(b4[u].y - org.y);
                     m4[u] = few_margin(fx0[u], fy0[u], fx1[u], fy1[u]) + pm;
@@ -974,7 +1026,7 @@ __device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const Path
                 }
                 if (anchor_old >= 0) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < kFewW; ++u) {
                         int dj = sg4[u] - anchor_old; if (dj < 0) dj += mr;
                         const bool outside = ok4[u] && !(dj <= kWin || dj >= mr - kWin);
                         const float d = sqrtf(seg_dist2_f(make_float4(fx0[u], fy0[u], fx1[u], fy1[u]), px, py)) - 4.f * m4[u];
@@ -982,7 +1034,7 @@ __device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const Path
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kFewW; ++u) {
                     if ((pass >> u) & 1u) {                                                  // rare: the exact test (main.cpp:478-490)
                         const double vx = b4[u].x - a4[u].x; const double vy = b4[u].y - a4[u].y;   // main.cpp:482
                         const double den = nx * (-vy) + ny * vx;                         // main.cpp:483
@@ -1022,10 +1074,12 @@ __device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const Path
             const double* gs = gseg + 4 * (r ? segO0 : segI0);
             float best = 64.f;
             double best2 = INF;
-            RL_FEW_FOREACH(gs, mr, {
+            const double ub = fmin(hp[r].t, hn[r].t);     // a hit point lies on the ring: the point-ring distance is at most that
+            const double reach = fmax(want_clr ? 64.5 : 0.0, want_dist ? ub : 0.0);
+            RL_FEW_FOREACH(gs, mr, gbx[r], few_box_near(bx, Pc, reach), {
                 if (want_clr) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < kFewW; ++u) {
                         int dj = sg4[u] - anchor; if (dj < 0) dj += mr;
                         const bool outside = ok4[u] && !(dj <= kWin || dj >= mr - kWin);
                         const float4 f = make_float4((float)(a4[u].x - org.x), (float)(a4[u].y - org.y), (float)(b4[u].x - org.x), (float)(b4[u].y - org.y));
@@ -1036,7 +1090,7 @@ __device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const Path
                 }
                 if (want_dist) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < kFewW; ++u) {
                         const double vx = b4[u].x - a4[u].x; const double vy = b4[u].y - a4[u].y;
                         const double apx = Pc.x - a4[u].x; const double apy = Pc.y - a4[u].y;
                         const double denom = fmax(1e-30, vx * vx + vy * vy);
@@ -1122,9 +1176,9 @@ __device__ __forceinline__ bool corridor_search_few_c(const Part& pt, const Path
             const float ax = (float)(axd - org.x), ay = (float)(ayd - org.y), dx = (float)d0x, dy = (float)d0y;
             float cbest = 0.9396926f;
             const double* gs = gseg + 4 * (r ? segO0 : segI0);
-            RL_FEW_FOREACH(gs, M[r], {
+            RL_FEW_FOREACH(gs, M[r], gbx[r], few_box_cone(bx, axd, ayd, d0x, d0y), {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kFewW; ++u) {
                     const float fx0 = (float)(a4[u].x - org.x); const float fy0 = (float)(a4[u].y - org.y);
                     const float fx1 = (float)(b4[u].x - org.x); const float fy1 = (float)(b4[u].y - org.y);
                     const float e = 2.f * (few_margin(fx0, fy0, fx1, fy1) + pm) + 1e-6f;
@@ -1322,13 +1376,11 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
     uint32_t bar_phase = 0;
     int fslot = 0, prev_trk = -1;
     uint64_t* ebar = reinterpret_cast<uint64_t*>(scr + kcEbar);   // per-evaluation exchange barriers: one arrival per local warp + tx bytes
-    uint32_t epar = 0, fpar = 0;
+    uint32_t epar = 0;
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         mbar_init(ebar, kcNW);
         mbar_init(ebar + 1, kcNW);
-        mbar_init(reinterpret_cast<uint64_t*>(sMisc + 2), 1);      // stream buffers of corridor_search_few_c
-        mbar_init(reinterpret_cast<uint64_t*>(sMisc + 4), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sFlag[0] = 0; sFlag[1] = 0; sFlag[2] = 0;
     }
@@ -1394,6 +1446,14 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         bulk_g2s(sP, B.center_xy + 2 * (s0 + cl.n0), (uint32_t)Nl * 16u, mbar);
     }
     mbar_wait(mbar, bar_phase); bar_phase ^= 1;
+    // per-group bounding boxes of both rings for corridor_search_few_c: in the job's ax rows (free until the final profile),
+    // built by the whole cluster and published by the cluster barrier of the halo exchange
+    const long long segI0 = B.seg_off[2 * trk], segO0 = B.seg_off[2 * trk + 1], segE = B.seg_off[2 * trk + 2];
+    double* gbox = nullptr;
+    if (!ev && 4ll * ((((segO0 - segI0) + 31) >> 5) + (((segE - segO0) + 31) >> 5)) <= (long long)N) {
+        gbox = B.ax + B.job_off[jid];
+        few_boxes_build(cl, tid, B.seg, segI0, segO0, segE, gbox);
+    }
     exchange_path_halo(sP, sHalo, cl, tid);
 
 #pragma unroll
@@ -1409,7 +1469,6 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
     q.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; q.Fr = C.mass_kg * 9.81 * C.c_rr; q.mass = C.mass_kg; q.inv_mass = 1.0 / C.mass_kg; q.P = C.P_max_W;
     q.acc_cap = C.a_long_acc_cap; q.brk_cap = C.a_long_brake_cap; q.h = h; q.has_power = (C.P_max_W > 0);
 
-    const long long segI0 = B.seg_off[2 * trk], segO0 = B.seg_off[2 * trk + 1], segE = B.seg_off[2 * trk + 2];
     const HStep H(h);
     const double inv2h = H.inv2h, invh2 = H.invh2;                       // DiffOps, main.cpp:547
     const double lamJ = C.lambda_smooth * inv2h * inv2h;
@@ -1441,7 +1500,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             unsigned flagged = corridor_update_c<K>(pt, pv, sB, sMisc, sHint, sClr, sHalo, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
                                                     guard0, parity_ok, loc, hic, ray_tests);
             if (block_or<T>(flagged != 0u)) {
-                if (!corridor_search_few_c<K>(pt, pv, sB, sMisc, fpar, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                if (!corridor_search_few_c<K>(pt, pv, sB, sMisc, gbox, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
                                               guard0, flagged, parity_ok, loc, hic, ray_tests, ex_scans))
                     corridor_search_c<K>(pt, pv, sB, mbar, bar_phase, sMisc, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
                                          guard0, flagged, false, parity_ok, loc, hic, ray_tests, ex_scans);
@@ -1627,7 +1686,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
 #ifdef RL_PHASE_TIMERS
                 const long long tf0 = clock64();
 #endif
-                const bool few = corridor_search_few_c<K>(pt, pv, sB, sMisc, fpar, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
+                const bool few = corridor_search_few_c<K>(pt, pv, sB, sMisc, gbox, sHint, sClr, B.seg, gcenter, gcert, gapex, segI0, segO0, segE,
                                                           guard, flagged, parity_ok, loc, hic, ray_tests, ex_scans
 #ifdef RL_PHASE_TIMERS
                                                           , (cl.rank == 0) ? &st->J0[25] : nullptr

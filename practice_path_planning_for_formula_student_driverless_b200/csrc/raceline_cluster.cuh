@@ -1450,8 +1450,8 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
     // built by the whole cluster and published by the cluster barrier of the halo exchange
     const long long segI0 = B.seg_off[2 * trk], segO0 = B.seg_off[2 * trk + 1], segE = B.seg_off[2 * trk + 2];
     double* gbox = nullptr;
-    if (!ev && 4ll * ((((segO0 - segI0) + 31) >> 5) + (((segE - segO0) + 31) >> 5)) <= (long long)N) {
-        gbox = B.ax + B.job_off[jid];
+    if (!ev && 4ll * ((((segO0 - segI0) + 31) >> 5) + (((segE - segO0) + 31) >> 5)) + 1 <= (long long)N) {
+        gbox = B.ax + ((B.job_off[jid] + 1) & ~1ll);        // 16-byte aligned (rows start at any multiple of 8 bytes)
         few_boxes_build(cl, tid, B.seg, segI0, segO0, segE, gbox);
     }
     exchange_path_halo(sP, sHalo, cl, tid);

@@ -2076,8 +2076,19 @@ __device__ __forceinline__ unsigned corridor_update(const Part& pt, const double
 #endif
 
 // ---- the solver kernel ------------------------------------------------------------------------------------
+// CTAs one SM holds of a size class: shared memory decides (228 KB per SM, 1 KB reserve per CTA, 384 B static), and the
+// launch bound promises no more than that, so the small classes may use the registers the missing CTAs leave free
+__host__ __device__ constexpr int class_ctas_per_sm(int T, int K)
+{
+    const int per = T * K * 54 + kScratchBytes + 2 * kDbgGap * 2 + kDbgScr + 384 + 1024;
+    const int n = 233472 / per;
+    // ptxas grants registers in tiers: a bound of 13..16 CTAs of one warp still means 128, 12 means 168 -- and the ragged
+    // one-warp kernel needs more than 128 to keep its projected-gradient loop out of local memory: 12 CTAs instead of 13
+    if (T == 32 && n >= 12 && n < 16) return 12;
+    return n > 16 ? 16 : (n < 1 ? 1 : n);
+}
 template <int T, int K, int MODE>
-__global__ void __launch_bounds__(T, (4096 / (T * K)) > 16 ? 16 : ((4096 / (T * K)) < 1 ? 1 : (4096 / (T * K))))
+__global__ void __launch_bounds__(T, class_ctas_per_sm(T, K))
 solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __restrict__ item_off, int n_items)
 {
     constexpr int NP = T * K;

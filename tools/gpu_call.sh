@@ -3,5 +3,6 @@ set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-timeout 2400 python -m pytest tests -m gpu -q > $O/pytest_gpu_r02c.txt 2>&1
+timeout 900 python bench.py --tracks-total 1184 --steps 2 --warmup 3 --no-cpu-baseline --long-tracks-total 0 --extra-steps 2 > $O/q_bench.json 2> $O/q_bench.err
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_chains.py -m gpu -q -x > $O/q_pytest.txt 2>&1
 ls -la $O > $O/ls.txt

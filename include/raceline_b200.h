@@ -187,6 +187,8 @@ int rl_set_stream(rl_ctx* ctx, void* cuda_stream);
  *   "max_chain"     longest chain of consecutive jobs on one track that one CTA / cluster works through
  *   "force_chain"   form chains of exactly this length whatever the batch size (tests)
  *   "force_cluster" route closed tracks of any length through the cluster kernel with this many CTAs (tests)
+ *   "no_few_search" test hook: 1 = the long-track kernel rebuilds flagged samples by tile streaming only (results
+ *                   are bit-identical either way; tests compare the two)
  *   "debug_inject"  debug-checks build only, see rl_debug_check_failures
  * Unknown names return RL_ERR_ARG.  The library reads no environment variables.
  */

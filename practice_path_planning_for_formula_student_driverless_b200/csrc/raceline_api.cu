@@ -26,7 +26,7 @@ struct rl_ctx {
     // may be shared by host threads (calls are serialised); use one context per thread for concurrency
     std::recursive_mutex mu;
     // tuning knobs and test hooks (rl_set_option); 0 = automatic
-    int opt_solve_chunks = 0, opt_max_chain = 0, opt_force_chain = 0, opt_force_cluster = 0;
+    int opt_solve_chunks = 0, opt_max_chain = 0, opt_force_chain = 0, opt_force_cluster = 0, opt_no_few_search = 0;
     bool pipeline_ready = false;
     struct GeomBufs* geom = nullptr;   // device buffers of rl_centerline_geom_batch, kept between calls (grow only)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // timing events around the kernels of the last geometry call
@@ -386,6 +386,7 @@ DevBatch dev_view(const rl_batch* b)
     B.job_off = b->d_job_off.p; B.xy = b->d_xy.p; B.heading = b->d_heading.p; B.curvature = b->d_curv.p;
     B.alpha_total = b->d_atot.p; B.alpha_last = b->d_alast.p; B.v = b->d_v.p; B.ax = b->d_ax.p; B.stats = b->d_stats.p;
     B.dbg = b->ctx ? b->ctx->d_dbg : nullptr;
+    B.no_few_search = b->ctx ? b->ctx->opt_no_few_search : 0;
     return B;
 }
 
@@ -541,6 +542,7 @@ int rl_set_option(rl_ctx* c, const char* name, int64_t value)
     else if (!std::strcmp(name, "max_chain")) c->opt_max_chain = v;
     else if (!std::strcmp(name, "force_chain")) c->opt_force_chain = v;
     else if (!std::strcmp(name, "force_cluster")) c->opt_force_cluster = v;
+    else if (!std::strcmp(name, "no_few_search")) c->opt_no_few_search = v;
     else if (!std::strcmp(name, "debug_inject")) {
         // debug-checks build only: make one warp skip a phase hand-over so that tests can see the checker fire
         if (!c->d_dbg) return fail(c, RL_ERR_UNSUPPORTED, "rl_set_option: debug_inject needs the -DRL_DEBUG_CHECKS build");

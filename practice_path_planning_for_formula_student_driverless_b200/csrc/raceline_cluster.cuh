@@ -518,14 +518,15 @@ __device__ __forceinline__ double lap_and_ax_c(const Part& pt, const Clu& cl, co
 
 // ray_scan with the nearest hit's SEGMENT per direction (tile-local; untouched when this tile does not improve it).
 // Both rays; pruned by this ring's own best hits so far (pos / neg), so INF afterwards means: no hit on this ring at all.
-__device__ __noinline__ void ray_scan_seg(const RayTile& tl_in, double2 P, double nx, double ny, float px, float py, float m,
-                                          double& pos_io, double& neg_io, int& segp_io, int& segn_io, long long& tests_io)
+// (arguments and results by value: see ray_scan_v)
+struct RaySegRes { double pos, neg; int sp, sn, tests; };
+__device__ __noinline__ RaySegRes ray_scan_seg_v(const RayTile tl_in, double2 P, double nx, double ny, float px, float py, float m,
+                                                 double bp, double bn)
 {
     const RayTile tl = tile_in_smem(tl_in);
     const double INF = dinf();
     const float FINF = __int_as_float(0x7f800000);
     const float fnx = (float)nx, fny = (float)ny, anx = fabsf(fnx), any = fabsf(fny);
-    double bp = pos_io, bn = neg_io;
     int sp = -1, sn = -1, tests = 0;
     float bpf = (bp < INF) ? __double2float_ru(bp) : FINF, bnf = (bn < INF) ? __double2float_ru(bn) : FINF;
     for (int sb = 0; sb < tl.nsup; ++sb) {
@@ -553,14 +554,22 @@ __device__ __noinline__ void ray_scan_seg(const RayTile& tl_in, double2 P, doubl
             }
         }
     }
-    pos_io = bp; neg_io = bn; tests_io += tests;
-    if (sp >= 0) segp_io = sp;
-    if (sn >= 0) segn_io = sn;
+    RaySegRes r;
+    r.pos = bp; r.neg = bn; r.sp = sp; r.sn = sn; r.tests = tests;
+    return r;
+}
+__device__ __forceinline__ void ray_scan_seg(const RayTile& tl, double2 P, double nx, double ny, float px, float py, float m,
+                                             double& pos_io, double& neg_io, int& segp_io, int& segn_io, long long& tests_io)
+{
+    const RaySegRes r = ray_scan_seg_v(tl, P, nx, ny, px, py, m, pos_io, neg_io);
+    pos_io = r.pos; neg_io = r.neg; tests_io += r.tests;
+    if (r.sp >= 0) segp_io = r.sp;
+    if (r.sn >= 0) segn_io = r.sn;
 }
 
 // crossings (mod 2) of the +x ray from P with the segments of one TILE of a vertex chain; the end vertex of the
 // tile's last segment is the start of the ring's next segment (next_start), shared bit for bit like every other vertex
-__device__ __noinline__ bool inside_ring_tile(const RayTile& tl_in, double2 P, float px, float py, float m, double2 next_start)
+__device__ __noinline__ bool inside_ring_tile(const RayTile tl_in, double2 P, float px, float py, float m, double2 next_start)
 {
     const RayTile tl = tile_in_smem(tl_in);
     int cnt = 0;
@@ -1450,7 +1459,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
     // built by the whole cluster and published by the cluster barrier of the halo exchange
     const long long segI0 = B.seg_off[2 * trk], segO0 = B.seg_off[2 * trk + 1], segE = B.seg_off[2 * trk + 2];
     double* gbox = nullptr;
-    if (!ev && 4ll * ((((segO0 - segI0) + 31) >> 5) + (((segE - segO0) + 31) >> 5)) + 1 <= (long long)N) {
+    if (!ev && !B.no_few_search && 4ll * ((((segO0 - segI0) + 31) >> 5) + (((segE - segO0) + 31) >> 5)) + 1 <= (long long)N) {
         gbox = B.ax + ((B.job_off[jid] + 1) & ~1ll);        // 16-byte aligned (rows start at any multiple of 8 bytes)
         few_boxes_build(cl, tid, B.seg, segI0, segO0, segE, gbox);
     }
@@ -1460,14 +1469,21 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
     for (int k = 0; k < K; ++k)
         if (k < cnt) { B.alpha_total[row0 + start + k] = 0.0; B.alpha_last[row0 + start + k] = 0.0; }
 
-    VPar q;
-    q.v_cap = C.v_cap_mps; q.a_lat_max = C.a_lat_max; q.kappa_eps = C.kappa_eps;
-    {
-        const double a_total = C.use_total_ge_lat ? fmax(C.a_total_max, C.a_lat_max) : C.a_total_max;   // main.cpp:802-804
-        q.a_tot2 = a_total * a_total;
-    }
-    q.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; q.Fr = C.mass_kg * 9.81 * C.c_rr; q.mass = C.mass_kg; q.inv_mass = 1.0 / C.mass_kg; q.P = C.P_max_W;
-    q.acc_cap = C.a_long_acc_cap; q.brk_cap = C.a_long_brake_cap; q.h = h; q.has_power = (C.P_max_W > 0);
+    // the v(s) constants are CTA-uniform: they live behind the exchange arrays of the sweeps in region B while a profile
+    // runs (thread 0 writes them before the barrier that precedes it) instead of in 25 registers for the whole job --
+    // this kernel has no static shared memory to spare (two CTAs fill the SM to 112 bytes)
+    VPar* const sq = reinterpret_cast<VPar*>(sB + 6 * (kcT + 1) + 2);
+    const VPar& q = *sq;
+    auto fill_vpar = [&]() {
+        if (tid == 0) {
+            VPar& w = *sq;
+            w.v_cap = C.v_cap_mps; w.a_lat_max = C.a_lat_max; w.kappa_eps = C.kappa_eps;
+            const double a_total = C.use_total_ge_lat ? fmax(C.a_total_max, C.a_lat_max) : C.a_total_max;   // main.cpp:802-804
+            w.a_tot2 = a_total * a_total;
+            w.kd = 0.5 * C.rho_air * C.Cd * C.A_front_m2; w.Fr = C.mass_kg * 9.81 * C.c_rr; w.mass = C.mass_kg; w.inv_mass = 1.0 / C.mass_kg; w.P = C.P_max_W;
+            w.acc_cap = C.a_long_acc_cap; w.brk_cap = C.a_long_brake_cap; w.h = h; w.has_power = (C.P_max_W > 0);
+        }
+    };
 
     const HStep H(h);
     const double inv2h = H.inv2h, invh2 = H.invh2;                       // DiffOps, main.cpp:547
@@ -1550,6 +1566,7 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             double kap[K], vv[K], axd[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) kap[k] = (k < cnt) ? N0[k] / Wd[k] : 0.0;    // kappa, main.cpp:618
+            fill_vpar();       // region B is free since the barrier that ended staged_bounds_home
             block_sync<T>();
             vprofile_c<K>(pt, cl, q, kap, vv, C.max_vpass_iters, sB, sFlag, fslot, vrounds);
             block_sync<T>();
@@ -1747,6 +1764,8 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         if (mt) {
             // final v(s) profile (main.cpp:1047)
             double vv[K], axd[K];
+            block_sync<T>();
+            fill_vpar();
             block_sync<T>();
             vprofile_c<K>(pt, cl, q, kap, vv, C.max_vpass_iters, sB, sFlag, fslot, vrounds);
             block_sync<T>();

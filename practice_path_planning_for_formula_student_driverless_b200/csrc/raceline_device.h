@@ -27,6 +27,7 @@ struct DevBatch {
     double* ax;
     rl_job_stats* stats;         // [n_jobs]
     unsigned long long* dbg;     // debug-checks build only (else null): [0] failures, [1] first failure (code | CTA << 32), [2] fault injection
+    int no_few_search;           // test hook (rl_set_option "no_few_search"): the cluster kernel rebuilds flagged samples by tile streaming only
 };
 
 // Size classes: one CTA of T threads solves one (track, config, stage) job, K samples per thread.

@@ -604,6 +604,11 @@ __device__ __forceinline__ void halo_recv(Halo& h, const Part& pt, const double*
 }
 
 struct PgdOut { double J0, Jend; int acc, bt, ev; };
+// size classes up to this thread count run one copy of the half step of the projected-gradient loop (see pgd_outer)
+#ifndef RL_SINGLE_COPY_MAX_T
+#define RL_SINGLE_COPY_MAX_T 128
+#endif
+constexpr int kSingleCopyMaxT = RL_SINGLE_COPY_MAX_T;
 
 // std::min(hi, std::max(lo, a)) of main.cpp:731 as two compare-selects (fmin/fmax cost twice as much in SASS)
 __device__ __forceinline__ double clamp_box(double a, double lo, double hi)
@@ -723,11 +728,24 @@ __device__ __forceinline__ PgdOut pgd_outer(const Part& pt, const double* sLo, c
     int it = 0, bt = 0;
     bool in_x = true;    // which array holds the current trial
     while (it < max_inner) {
-        const bool acc = in_x ? pgd_half<T, K, MODE>(pt, x, hx, y, hy, sLo, sHi, cL, cR, c)
-                              : pgd_half<T, K, MODE>(pt, y, hy, x, hx, sLo, sHi, cL, cR, c);
+        // Small CTAs: a dozen one-warp CTAs (or seven two-warp, four four-warp ones) sit on an SM, each somewhere else in the
+        // code, and the loop is bound by instruction fetch (one-warp class, ncu: no_instruction = 2/3 of the stall samples).
+        // They run ONE copy of the half step and move the new trial back (24 register moves) instead of alternating
+        // between two copies: half the loop's code (+20 % at T = 32, +9 % at T = 64, +8 % at T = 128).
+        bool acc;
+        if (T <= kSingleCopyMaxT) {
+            acc = pgd_half<T, K, MODE>(pt, x, hx, y, hy, sLo, sHi, cL, cR, c);
+            if (acc) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) x[k] = y[k];
+                hx = hy;
+            }
+        } else
+            acc = in_x ? pgd_half<T, K, MODE>(pt, x, hx, y, hy, sLo, sHi, cL, cR, c)
+                       : pgd_half<T, K, MODE>(pt, y, hy, x, hx, sLo, sHi, cL, cR, c);
         o.ev++;
         if (acc) {
-            in_x = !in_x;
+            if (T > kSingleCopyMaxT) in_x = !in_x;
             o.acc++; it++; bt = 0;
             if (fabs(Jprev - c.J) < 1e-10) break;       // main.cpp:740
             Jprev = c.J;

@@ -130,3 +130,30 @@ def test_track_longer_than_16384_on_a_16_cta_cluster(ctx):
     for st, r in zip((MC, MT), res):
         assert r.stats.status == 0 and r.stats.n == n
         _check(r, tr, st, cfg, ("16-CTA cluster", n, st))
+
+
+@pytest.mark.parametrize("cs,n", [(4, 6000), (8, 16384)])
+def test_few_sample_search_equals_tile_streaming_bit_for_bit(ctx, cs, n):
+    """The samples the update path flags are rebuilt either by the box-culled whole-CTA search (corridor_search_few_c) or by
+    streaming every ring tile again (corridor_search_c).  Both are exact: hits, point distances and therefore the corridor
+    are the same numbers, so a chained min-curv + min-time solve must agree bit for bit -- and the few-sample path must
+    actually have run (its cone certificates count as existence scans, like the tile path's)."""
+    ctx.set_option("force_cluster", cs if n <= 4096 * 2 else 0)
+    tracks = _tracks(1, n, 0xFE00 + n)
+    cfg = rl.Config()
+    jobs = [(0, 0, MC), (0, 0, MT)]
+    try:
+        a = rl.solve_batch(tracks, [cfg], jobs, ctx=ctx)
+        ctx.set_option("no_few_search", 1)
+        b = rl.solve_batch(tracks, [cfg], jobs, ctx=ctx)
+    finally:
+        ctx.set_option("no_few_search", 0)
+        ctx.set_option("force_cluster", 0)
+    for ra, rb in zip(a, b):
+        assert ra.stats.status == 0 and rb.stats.status == 0
+        assert ra.stats.accepted == rb.stats.accepted and ra.stats.backtracks == rb.stats.backtracks and ra.stats.evals == rb.stats.evals
+        for name in ("raceline", "alpha_total", "alpha_last", "heading", "curvature"):
+            assert np.array_equal(getattr(ra, name), getattr(rb, name)), (name, cs, n)
+        if ra.v is not None:
+            assert np.array_equal(ra.v, rb.v) and np.array_equal(ra.ax, rb.ax) and ra.lap_time == rb.lap_time
+        assert ra.stats.exist_scans > 0 and rb.stats.exist_scans > 0

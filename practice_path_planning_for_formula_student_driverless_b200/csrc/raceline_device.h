@@ -35,14 +35,19 @@ struct SizeClass {
     int T;
     int K;
 };
-constexpr int kNumClasses = 5;
-constexpr SizeClass kClasses[kNumClasses] = {{32, 8}, {64, 8}, {128, 8}, {256, 8}, {512, 8}};
+constexpr int kNumClasses = 6;
+// the last entry is the two-warp class of the small maps (128 <= N <= 256: four samples per thread, a projected-gradient
+// loop that fits the instruction cache next to a dozen other CTAs); class_for_n prefers it to the one-warp class
+constexpr SizeClass kClasses[kNumClasses] = {{32, 8}, {64, 8}, {128, 8}, {256, 8}, {512, 8}, {64, 4}};
+constexpr int kSmallTwoWarpClass = 5;
 constexpr int kSegBlock = 8;  // segments per bounding box in the corridor ray-cast
 constexpr int kSupBlock = 8;  // boxes per super box (fast corridor path)
 
 inline int class_for_n(int n)
 {
-    for (int c = 0; c < kNumClasses; ++c)
+    if (n >= 2 * kClasses[kSmallTwoWarpClass].T && n <= kClasses[kSmallTwoWarpClass].T * kClasses[kSmallTwoWarpClass].K)
+        return kSmallTwoWarpClass;     // every thread of a multi-warp CTA must own at least two samples
+    for (int c = 0; c < kSmallTwoWarpClass; ++c)
         if (n <= kClasses[c].T * kClasses[c].K) return c;
     return -1;
 }

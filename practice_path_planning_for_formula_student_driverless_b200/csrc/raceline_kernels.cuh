@@ -2103,6 +2103,7 @@ __host__ __device__ constexpr int class_ctas_per_sm(int T, int K)
     // ptxas grants registers in tiers: a bound of 13..16 CTAs of one warp still means 128, 12 means 168 -- and the ragged
     // one-warp kernel needs more than 128 to keep its projected-gradient loop out of local memory: 12 CTAs instead of 13
     if (T == 32 && n >= 12 && n < 16) return 12;
+    if (T == 64 && K == 4) return 8;     // two warps, four samples per thread: 8 CTAs keep 128 registers (13 would mean 72)
     return n > 16 ? 16 : (n < 1 ? 1 : n);
 }
 template <int T, int K, int MODE>
@@ -2318,8 +2319,15 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
             RL_DBG_ENTER(T, sMisc, kDbgPhVsweep);
             // the linearisation (48 registers) waits behind the exchange arrays of the sweeps (first NP doubles of region B)
             // while the v(s) profile runs: own slots only, written and read back by the same thread
+            // (the exchange arrays take 6 T doubles: with K = 4 that is more than one plane of T K, and only A1 and A2 fit behind them)
+            constexpr int kPark0 = (6 * T > NP) ? 6 * T : NP;
+            constexpr bool kParkW = (kPark0 + 3 * NP <= 4 * NP);
+            static_assert(kPark0 + 2 * NP <= 4 * NP, "region B holds the exchange arrays and two parked planes");
 #pragma unroll
-            for (int k = 0; k < K; ++k) { sB[NP + k * T + tid] = A1[k]; sB[2 * NP + k * T + tid] = A2[k]; sB[3 * NP + k * T + tid] = Wd[k]; }
+            for (int k = 0; k < K; ++k) {
+                sB[kPark0 + k * T + tid] = A1[k]; sB[kPark0 + NP + k * T + tid] = A2[k];
+                if (kParkW) sB[kPark0 + 2 * NP + k * T + tid] = Wd[k];
+            }
             vprofile_blocked<T, K>(pt, q, kap, vv, C.max_vpass_iters, sB, vrounds, closed, vkap);
             block_sync<T>();
             lap_outer = lap_and_ax<T, K>(pt, q, vv, axd, sB, sRed + ph * 32, closed);
@@ -2355,7 +2363,10 @@ solve_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __re
                 }
             }
 #pragma unroll
-            for (int k = 0; k < K; ++k) { A1[k] = sB[NP + k * T + tid]; A2[k] = sB[2 * NP + k * T + tid]; Wd[k] = sB[3 * NP + k * T + tid]; }
+            for (int k = 0; k < K; ++k) {
+                A1[k] = sB[kPark0 + k * T + tid]; A2[k] = sB[kPark0 + NP + k * T + tid];
+                if (kParkW) Wd[k] = sB[kPark0 + 2 * NP + k * T + tid];
+            }
             block_sync<T>();
         }
         RL_PH(2);   // v(s) profile + time weights

@@ -106,7 +106,7 @@ def test_config_sweep_parity(ctx, goldens):
             assert abs(r.lap_time - sw[f"j{j}_lap_time"]) <= TOL_LAP_REL * sw[f"j{j}_lap_time"]
 
 
-@pytest.mark.parametrize("n", [16, 37, 64, 100, 130, 255, 256, 257, 300, 512, 700, 1024, 1500, 2048])
+@pytest.mark.parametrize("n", [16, 37, 64, 100, 127, 128, 130, 200, 255, 256, 257, 300, 512, 700, 1024, 1500, 2048])
 def test_synthetic_tracks_vs_oracle(ctx, n):
     """ragged N across every size class (and the exact-fit kernels at N = T*K) against the pinned oracle."""
     center, seg, L, m = rl.synth_tracks(2, n, seed_base=0xB200 + 7 * n)
@@ -338,7 +338,7 @@ def test_open_track_parity_vs_reference(ctx, name):
     assert abs(res[1].lap_time - g["mt_lap_time"]) <= TOL_LAP_REL * g["mt_lap_time"]
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 33, 100, 257, 600, 2048])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 33, 100, 128, 200, 256, 257, 600, 2048])
 def test_open_tracks_vs_oracle(ctx, n):
     """open paths of every size class: an arc of a synthetic track, rings opened at the same place."""
     nn = max(n, 16)

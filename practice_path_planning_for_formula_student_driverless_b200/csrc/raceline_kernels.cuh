@@ -2103,7 +2103,10 @@ __host__ __device__ constexpr int class_ctas_per_sm(int T, int K)
     // ptxas grants registers in tiers: a bound of 13..16 CTAs of one warp still means 128, 12 means 168 -- and the ragged
     // one-warp kernel needs more than 128 to keep its projected-gradient loop out of local memory: 12 CTAs instead of 13
     if (T == 32 && n >= 12 && n < 16) return 12;
-    if (T == 64 && K == 4) return 8;     // two warps, four samples per thread: 8 CTAs keep 128 registers (13 would mean 72)
+#ifndef RL_SMALL_CLASS_CTAS
+#define RL_SMALL_CLASS_CTAS 8
+#endif
+    if (T == 64 && K == 4) return RL_SMALL_CLASS_CTAS;     // two warps, four samples per thread: 8 CTAs keep 128 registers (13 would mean 72)
     return n > 16 ? 16 : (n < 1 ? 1 : n);
 }
 template <int T, int K, int MODE>

@@ -3,9 +3,7 @@ set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-rm -f $O/c_ab.txt
-for v in "" _c10 _c12; do
-  echo "variant '$v'" >> $O/c_ab.txt
-  RL_LIB_VARIANT=$v timeout 300 python tools/sweep_probe.py 0 2>&1 | tail -1 | cut -c1-200 >> $O/c_ab.txt
-done
+timeout 2400 python -m pytest tests -m gpu -q > $O/pytest_gpu_r02d.txt 2>&1
+( time timeout 1200 python bench.py > $O/r02_bench_final.json 2> $O/r02_bench_final.err ) 2> $O/r02_bench_final.time
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:solve_cluster_kernel -c 1 -f -o $O/r02f_cluster python tools/phase_report.py --tracks 148 --n 16384 --m 7447 > $O/r02f_ncu.log 2>&1
 ls -la $O > $O/ls.txt

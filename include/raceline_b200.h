@@ -218,7 +218,8 @@ int rl_batch_download(rl_batch* b, const rl_batch_out* out);   /* async D2H     
 int rl_batch_sync(rl_batch* b);                                /* wait; returns first CUDA error */
 /* DEVICE pointers of the batch's output arrays (same layout as rl_batch_out, rows in job order), for device-side
  * consumers: the final gather of lap times and rasters over NCCL / peer copies reads them in place.  Valid until
- * the batch is destroyed; written by rl_batch_solve on the context's stream. */
+ * the batch is destroyed; written by rl_batch_solve on the context's stream.  The v / ax rows of MINCURV jobs hold
+ * no result (the kernels may use them as scratch). */
 int rl_batch_device_outputs(rl_batch* b, rl_batch_out* device_pointers);
 int rl_batch_launches_per_solve(const rl_batch* b);            /* kernels one rl_batch_solve launches */
 void rl_batch_destroy(rl_batch* b);

@@ -210,7 +210,7 @@ struct PgdCtxC {
     double lamJ, armijo_c, step2, J, decp;
     int ph;
     uint64_t* ebar;     // the two exchange mbarriers of this CTA
-    uint32_t* epar;     // their wait parities (bit b: barrier b), kept by the kernel across outer iterations and jobs
+    uint32_t epar;      // their wait parities (bit b: barrier b): a register copy, handed back to the kernel by pgd_outer_c
 };
 constexpr int kcRedStride = kMaxCS * kcNW * 2;   // doubles per phase
 constexpr int kcExStride = (kcNW + 1) * 2;
@@ -259,8 +259,8 @@ __device__ __forceinline__ bool pgd_half_c(const Part& pt, const Clu& cl, const 
             if (pt.warp == 0) mbar_arrive_expect_local(bar, (uint32_t)((int)cl.CS * kcNW + 2) * 16u);
             else mbar_arrive_local(bar);
         }
-        mbar_wait_cluster(bar, (*c.epar >> c.ph) & 1u);
-        *c.epar ^= (1u << c.ph);
+        mbar_wait_cluster(bar, (c.epar >> c.ph) & 1u);
+        c.epar ^= (1u << c.ph);
         gather_pairs(sRedPh, (int)cl.CS * kcNW, pt.lane, Jn, dec);
         halo_recv_c(hb, pt, sExF, sExL);
     }
@@ -290,7 +290,7 @@ __device__ __forceinline__ PgdOut pgd_outer_c(const Part& pt, const Clu& cl, con
     PgdCtxC<K> c;
     c.sC0 = sC0; c.sCp = sCp; c.sCm = sCm; c.sSt = sSt; c.sRed = sRed; c.sExF = sExF; c.sExL = sExL;
     c.lamJ = lamJ; c.armijo_c = armijo_c; c.ph = ph;
-    c.ebar = ebar; c.epar = &epar;
+    c.ebar = ebar; c.epar = epar;
     c.step2 = 2.0 * step_init;
     double x[K], y[K];
     Halo hx, hy;
@@ -363,6 +363,7 @@ __device__ __forceinline__ PgdOut pgd_outer_c(const Part& pt, const Clu& cl, con
         }
     }
     ph = c.ph;
+    epar = c.epar;
     o.Jend = c.J;
     return o;
 }

@@ -3,6 +3,6 @@ set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > $O/r02_bench_2gpu_final.json 2> $O/r02_bench_2gpu_final.err
-timeout 600 python -m pytest tests/test_gpu_resident.py -m gpu -q > $O/q_pytest_2gpu.txt 2>&1
+timeout 900 python -m pytest tests/test_gpu_cluster.py -m gpu -q -x > $O/q_pytest.txt 2>&1
+timeout 900 python bench.py --tracks-total 1184 --steps 2 --warmup 3 --no-cpu-baseline --long-tracks-total 2368 --extra-steps 2 > $O/q_bench.json 2> $O/q_bench.err
 ls -la $O > $O/ls.txt

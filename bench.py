@@ -56,6 +56,32 @@ TOL_ALPHA, TOL_KAPPA, TOL_V, TOL_LAP_REL = 1e-4, 1e-6, 1e-4, 1e-5
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local, world):
+    """Multi-GPU runs: keep this rank (and the pinned buffers it allocates next) on the NUMA node its GPU hangs off.
+    Returns what was done for the JSON line; a box with one node (or without the sysfs entries) is left alone."""
+    info = {"gpu_node": None, "bound_cpus": None}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        info["gpu_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2 or world < 2:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        mine = cpus & set(os.sched_getaffinity(0))
+        if mine:
+            os.sched_setaffinity(0, mine)
+            info["bound_cpus"] = len(mine)
+    except Exception:
+        pass
+    return info
+
+
 def host_cores():
     try:
         return sorted(os.sched_getaffinity(0))
@@ -444,6 +470,7 @@ def bench_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     total = args.tracks_total
@@ -582,7 +609,8 @@ def bench_ours(args):
                          "hbm_achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pb.h2d_bytes, "d2h_bytes_per_step": pb.d2h_bytes,
                     "steps": args.steps, "ms_per_step": ms_e2e / args.steps,
-                    "host_gbs_per_rank": {"h2d": pb.h2d_bytes / step_s / 1e9, "d2h": pb.d2h_bytes / step_s / 1e9}},
+                    "host_gbs_per_rank": {"h2d": pb.h2d_bytes / step_s / 1e9, "d2h": pb.d2h_bytes / step_s / 1e9},
+                    "numa": numa},
             "gpu_launches": launches,
             "clocks": clocks,
         }

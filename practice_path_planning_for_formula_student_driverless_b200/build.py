@@ -15,7 +15,7 @@ LIB = os.path.join(CSRC, "libraceline_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-SOURCES = ["raceline_inst_256.cu", "raceline_inst_cluster.cu", "raceline_geom.cu", "raceline_inst_512.cu", "raceline_inst_128.cu", "raceline_inst_64.cu", "raceline_inst_32.cu", "raceline_inst_64x4.cu",
+SOURCES = ["raceline_inst_256.cu", "raceline_inst_cluster.cu", "raceline_geom.cu", "raceline_inst_512.cu", "raceline_inst_128.cu", "raceline_inst_64.cu", "raceline_inst_32.cu", "raceline_inst_64x4.cu", "raceline_inst_128x4.cu", "raceline_inst_256x4.cu",
            "raceline_dispatch.cu", "raceline_api.cu", "synth_tracks.cpp"]
 # the geometry stage reproduces the reference's x86-64 arithmetic bit for bit: no FMA contraction in that unit
 EXTRA_FLAGS = {"raceline_geom.cu": ["-fmad=false"]}

@@ -35,19 +35,26 @@ struct SizeClass {
     int T;
     int K;
 };
-constexpr int kNumClasses = 6;
-// the last entry is the two-warp class of the small maps (128 <= N <= 256: four samples per thread, a projected-gradient
-// loop that fits the instruction cache next to a dozen other CTAs); class_for_n prefers it to the one-warp class
-constexpr SizeClass kClasses[kNumClasses] = {{32, 8}, {64, 8}, {128, 8}, {256, 8}, {512, 8}, {64, 4}};
-constexpr int kSmallTwoWarpClass = 5;
+constexpr int kNumClasses = 8;
+// the last three entries are the classes with FOUR samples per thread for tracks of up to 1024 samples (round 2): twice
+// the threads per track, half the projected-gradient loop -- a loop that fits the instruction cache, and fewer, larger CTAs
+// at different places of the code per SM.  class_for_n prefers them when every thread still owns two samples.
+constexpr SizeClass kClasses[kNumClasses] = {{32, 8}, {64, 8}, {128, 8}, {256, 8}, {512, 8}, {64, 4}, {128, 4}, {256, 4}};
 constexpr int kSegBlock = 8;  // segments per bounding box in the corridor ray-cast
 constexpr int kSupBlock = 8;  // boxes per super box (fast corridor path)
+constexpr int kFirstK4Class = 5;
+constexpr int kSmallTwoWarpClass = 5;
 
 inline int class_for_n(int n)
 {
-    if (n >= 2 * kClasses[kSmallTwoWarpClass].T && n <= kClasses[kSmallTwoWarpClass].T * kClasses[kSmallTwoWarpClass].K)
-        return kSmallTwoWarpClass;     // every thread of a multi-warp CTA must own at least two samples
-    for (int c = 0; c < kSmallTwoWarpClass; ++c)
+#ifdef RL_NO_MID_K4      // A/B builds: only the two-warp class of the small maps
+    constexpr int kEndK4 = kFirstK4Class + 1;
+#else
+    constexpr int kEndK4 = kNumClasses;
+#endif
+    for (int c = kFirstK4Class; c < kEndK4; ++c)     // every thread of a multi-warp CTA must own at least two samples
+        if (n >= 2 * kClasses[c].T && n <= kClasses[c].T * kClasses[c].K) return c;
+    for (int c = 0; c < kFirstK4Class; ++c)
         if (n <= kClasses[c].T * kClasses[c].K) return c;
     return -1;
 }

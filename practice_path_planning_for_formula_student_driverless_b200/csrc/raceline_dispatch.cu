@@ -9,7 +9,7 @@ namespace rl {
     int launch_solve_##T(const DevBatch& B, const int* job_list, const int* item_off, int n_items, int mode, void* stream); \
     int configure_solve_##T();                                                                       \
     int occupancy_solve_##T();
-RL_DECL(32) RL_DECL(64) RL_DECL(128) RL_DECL(256) RL_DECL(512) RL_DECL(64x4)
+RL_DECL(32) RL_DECL(64) RL_DECL(128) RL_DECL(256) RL_DECL(512) RL_DECL(64x4) RL_DECL(128x4) RL_DECL(256x4)
 #undef RL_DECL
 
 namespace {
@@ -27,7 +27,7 @@ __global__ void fp64_peak_kernel(double* out, int iters)
 }
 }  // namespace
 
-namespace { int g_occ[kNumClasses] = {0, 0, 0, 0, 0, 0}; }
+namespace { int g_occ[kNumClasses] = {0, 0, 0, 0, 0, 0, 0, 0}; }
 
 int configure_kernels()
 {
@@ -37,11 +37,13 @@ int configure_kernels()
     if (!e) e = configure_solve_256();
     if (!e) e = configure_solve_512();
     if (!e) e = configure_solve_64x4();
+    if (!e) e = configure_solve_128x4();
+    if (!e) e = configure_solve_256x4();
     if (!e) e = configure_solve_cluster();
     if (!e) e = configure_geom();
     if (!e) {   // what the device really holds per SM (registers, shared memory + its per-CTA reserve): the host plan's CTA slots
         g_occ[0] = occupancy_solve_32(); g_occ[1] = occupancy_solve_64(); g_occ[2] = occupancy_solve_128();
-        g_occ[3] = occupancy_solve_256(); g_occ[4] = occupancy_solve_512(); g_occ[5] = occupancy_solve_64x4();
+        g_occ[3] = occupancy_solve_256(); g_occ[4] = occupancy_solve_512(); g_occ[5] = occupancy_solve_64x4(); g_occ[6] = occupancy_solve_128x4(); g_occ[7] = occupancy_solve_256x4();
     }
     return e;
 }
@@ -57,7 +59,9 @@ int launch_solve(const DevBatch& B, const int* job_list, int n_list, const int* 
 {
     if (n_list <= 0) return 0;
     if (cls >= kClusterClassBase) return launch_solve_cluster(B, job_list, item_off, n_items, cls - kClusterClassBase, mode, stream);
-    if (cls == kSmallTwoWarpClass) return launch_solve_64x4(B, job_list, item_off, n_items, mode, stream);
+    if (cls == 5) return launch_solve_64x4(B, job_list, item_off, n_items, mode, stream);
+    if (cls == 6) return launch_solve_128x4(B, job_list, item_off, n_items, mode, stream);
+    if (cls == 7) return launch_solve_256x4(B, job_list, item_off, n_items, mode, stream);
     switch (kClasses[cls].T) {
         case 32: return launch_solve_32(B, job_list, item_off, n_items, mode, stream);
         case 64: return launch_solve_64(B, job_list, item_off, n_items, mode, stream);

@@ -2107,6 +2107,7 @@ __host__ __device__ constexpr int class_ctas_per_sm(int T, int K)
 #define RL_SMALL_CLASS_CTAS 8
 #endif
     if (T == 64 && K == 4) return RL_SMALL_CLASS_CTAS;     // two warps, four samples per thread: 8 CTAs keep 128 registers (13 would mean 72)
+    if (K == 4) { const int r = 512 / T; return r < n ? r : n; }   // the other K = 4 classes: as many CTAs as 128 registers allow
     return n > 16 ? 16 : (n < 1 ? 1 : n);
 }
 template <int T, int K, int MODE>

@@ -3,9 +3,13 @@ set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.txt 2>&1
-timeout 2400 python -m pytest tests -m gpu -q > $O/pytest_gpu_r02_final.txt 2>&1
-( time timeout 1200 python bench.py > $O/r02_bench_final.json 2> $O/r02_bench_final.err ) 2> $O/r02_bench_final.time
-( time timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/r02_bench_reference.json 2> $O/r02_bench_reference.err ) 2> $O/r02_bench_reference.time
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:solve_kernel -s 3 -c 1 -f -o $O/r02g_sweep_kernel python tools/sweep_probe.py 0 > $O/r02g_ncu.log 2>&1
+rm -f $O/k4_ab.txt
+for v in _k8 ""; do
+  for nm in "300 136" "500 227" "700 318" "1000 455"; do
+    set -- $nm
+    echo "variant '$v' N=$1" >> $O/k4_ab.txt
+    RL_LIB_VARIANT=$v timeout 300 python tools/phase_report.py --tracks 4096 --n $1 --m $2 2>&1 | head -1 >> $O/k4_ab.txt
+  done
+done
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_chains.py tests/test_gpu_fuzz.py tests/test_gpu_adversarial.py -m gpu -q > $O/q_pytest.txt 2>&1
 ls -la $O > $O/ls.txt

@@ -17,7 +17,7 @@ _LIB = None
 # every symbol include/raceline_b200.h declares
 ABI_SYMBOLS = [
     "rl_abi_version", "rl_status_string", "rl_device_count", "rl_default_params", "rl_create", "rl_destroy",
-    "rl_set_stream", "rl_set_option", "rl_last_error", "rl_host_alloc", "rl_host_free", "rl_job_sample_offsets", "rl_solve_batch",
+    "rl_set_stream", "rl_set_option", "rl_last_error", "rl_host_alloc", "rl_host_free", "rl_job_sample_offsets", "rl_plan_for_track", "rl_solve_batch",
     "rl_batch_create", "rl_batch_upload", "rl_batch_solve", "rl_batch_download", "rl_batch_sync", "rl_batch_device_outputs",
     "rl_batch_launches_per_solve", "rl_batch_destroy", "rl_compute_min_curvature_raceline",
     "rl_compute_min_time_raceline", "rl_geom_row_offsets", "rl_centerline_geom_batch", "rl_synth_tracks", "rl_last_kernel_ms", "rl_debug_check_failures",
@@ -63,6 +63,8 @@ def lib():
     L.rl_host_free.restype = None
     L.rl_job_sample_offsets.argtypes = [C.POINTER(RlBatchDesc), C.POINTER(C.c_int64)]
     L.rl_job_sample_offsets.restype = C.c_int
+    L.rl_plan_for_track.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.rl_plan_for_track.restype = C.c_int
     L.rl_solve_batch.argtypes = [vp, C.POINTER(RlBatchDesc), C.POINTER(RlBatchOut)]
     L.rl_solve_batch.restype = C.c_int
     L.rl_batch_create.argtypes = [vp, C.POINTER(RlBatchDesc), C.POINTER(C.c_int)]

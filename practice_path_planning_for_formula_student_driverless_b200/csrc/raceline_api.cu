@@ -556,6 +556,18 @@ int rl_set_option(rl_ctx* c, const char* name, int64_t value)
 
 const char* rl_last_error(rl_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
+int rl_plan_for_track(int64_t n, int32_t closed, int32_t max_cs, int32_t* threads, int32_t* spt, int32_t* cluster_ctas)
+{
+    if (n < 0 || !threads || !spt || !cluster_ctas) return RL_ERR_ARG;
+    *threads = 0; *spt = 0; *cluster_ctas = 0;
+    const int cls = (n <= (1ll << 30)) ? rl::class_for_n((int)n) : -1;     // the same calls plan_batch makes
+    if (cls >= 0) { *threads = rl::kClasses[cls].T; *spt = rl::kClasses[cls].K; return RL_OK; }
+    const int cs = closed ? rl::cluster_size_for_n(n, 0, max_cs >= 16 ? 16 : 8) : 0;
+    if (cs <= 0) return RL_ERR_UNSUPPORTED;
+    *threads = 256; *spt = 8; *cluster_ctas = cs;
+    return RL_OK;
+}
+
 int rl_job_sample_offsets(const rl_batch_desc* d, int64_t* off)
 {
     if (!d || !off || d->n_jobs < 0) return RL_ERR_ARG;

@@ -184,3 +184,27 @@ def test_pinned_pool_refuses_to_free_memory_under_live_arrays():
         pool.close()
     del a
     pool.close()
+
+
+def test_size_class_plan_boundaries():
+    """rl_plan_for_track: the host plan's choice of kernel per track length (the same class_for_n / cluster_size_for_n
+    calls plan_batch makes), at every boundary: K = 4 classes for 128 .. 1024 samples (every thread of a multi-warp CTA
+    owns at least two samples), K = 8 elsewhere, clusters of 4 / 8 / 16 CTAs for long closed tracks."""
+    L = _lib.lib()
+
+    def plan(n, closed=1, max_cs=16):
+        t, k, cs = C.c_int32(), C.c_int32(), C.c_int32()
+        st = L.rl_plan_for_track(n, closed, max_cs, C.byref(t), C.byref(k), C.byref(cs))
+        return st, t.value, k.value, cs.value
+
+    for n, want in [(0, (32, 8)), (1, (32, 8)), (127, (32, 8)), (128, (64, 4)), (216, (64, 4)), (256, (64, 4)), (257, (128, 4)),
+                    (261, (128, 4)), (512, (128, 4)), (513, (256, 4)), (1024, (256, 4)), (1025, (256, 8)), (2048, (256, 8)),
+                    (2049, (512, 8)), (4096, (512, 8))]:
+        for closed in (0, 1):
+            assert plan(n, closed) == (0, want[0], want[1], 0), (n, closed)
+    assert plan(4097) == (0, 256, 8, 4) and plan(8192) == (0, 256, 8, 4) and plan(8193) == (0, 256, 8, 8)
+    assert plan(16384) == (0, 256, 8, 8) and plan(16385) == (0, 256, 8, 16) and plan(32768) == (0, 256, 8, 16)
+    assert plan(16385, max_cs=8)[0] == rl.RL_ERR_UNSUPPORTED and plan(32769)[0] == rl.RL_ERR_UNSUPPORTED
+    assert plan(4097, closed=0)[0] == rl.RL_ERR_UNSUPPORTED          # open tracks: single-CTA kernels only
+    assert plan(-1)[0] == rl.RL_ERR_ARG
+    assert L.rl_plan_for_track(100, 1, 8, None, None, None) == rl.RL_ERR_ARG

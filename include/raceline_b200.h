@@ -204,8 +204,8 @@ void rl_host_free(void* p);
 int rl_job_sample_offsets(const rl_batch_desc* desc, int64_t* off);
 /* Which kernel a track of n samples gets (pure host logic, no device needed; for planning and tests): *threads and
  * *samples_per_thread of the size class of the single-CTA kernels (n <= 4096), or the CTAs of the thread-block cluster
- * (256 threads x 8 samples each) in *cluster_ctas for longer CLOSED tracks, else 0 there.  Returns RL_OK,
- * RL_ERR_UNSUPPORTED when no kernel covers the shape (closed > 32,768 samples, open > 4096), RL_ERR_ARG for n < 0 or
+ * (256 threads x 8 samples each) in *cluster_ctas for longer tracks (open or closed), else 0 there.  Returns RL_OK,
+ * RL_ERR_UNSUPPORTED when no kernel covers the shape (more than 32,768 samples), RL_ERR_ARG for n < 0 or
  * null pointers.  max_cluster_ctas: 8 (portable cluster size) or 16. */
 int rl_plan_for_track(int64_t n_samples, int32_t closed, int32_t max_cluster_ctas, int32_t* threads, int32_t* samples_per_thread,
                       int32_t* cluster_ctas);

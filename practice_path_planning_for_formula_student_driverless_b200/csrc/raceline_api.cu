@@ -252,7 +252,7 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
     b->vrun0[n_chunks] = (int)b->vruns.size();
     for (int c = 0; c < n_chunks; ++c) {
         std::vector<std::vector<int>> bucket(rl::kNumClasses * 3);
-        std::vector<std::vector<int>> cbucket(2 * (rl::kMaxClusterSize + 1));   // [cs][mode] cluster launches
+        std::vector<std::vector<int>> cbucket(3 * (rl::kMaxClusterSize + 1));   // [cs][mode: ragged | exact fit | open] cluster launches
         const int force_cs = b->ctx->opt_force_cluster;   // test hook: cluster kernel on shorter tracks
         for (int j = b->chunk_job0[c]; j < b->chunk_job0[c + 1]; ++j) {
             const rl_job& jb = d->jobs[j];
@@ -261,8 +261,8 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
             const long long n = d->samp_off[t + 1] - d->samp_off[t];
             if (n == 0) { b->skipped.push_back({j, RL_OK}); continue; }   // empty Result, main.cpp:689 / 912
             const int cls = rl::class_for_n((int)n);
-            const int cs = (d->track_closed[t] && (cls < 0 || force_cs > 0)) ? rl::cluster_size_for_n(n, force_cs, rl::cluster_max_size()) : 0;
-            if (cs > 0) { cbucket[2 * cs + (n == 2048ll * cs ? 1 : 0)].push_back(j); continue; }
+            const int cs = (cls < 0 || force_cs > 0) ? rl::cluster_size_for_n(n, force_cs, rl::cluster_max_size()) : 0;
+            if (cs > 0) { cbucket[3 * cs + (!d->track_closed[t] ? 2 : (n == 2048ll * cs ? 1 : 0))].push_back(j); continue; }
             if (cls < 0) { b->skipped.push_back({j, RL_ERR_UNSUPPORTED}); continue; }
             const bool exact = (n == (long long)rl::kClasses[cls].T * rl::kClasses[cls].K);
             const int mode = !d->track_closed[t] ? 2 : (exact ? 1 : 0);   // open | closed exact-fit | closed ragged
@@ -287,11 +287,11 @@ int plan_batch(rl_batch* b, const rl_batch_desc* d, int n_chunks = 1)
         }
         for (size_t k = 0; k < cbucket.size(); ++k) {
             if (cbucket[k].empty()) continue;
-            const int cs = (int)(k / 2);
+            const int cs = (int)(k / 3);
             const int slots = std::max(1, (c_sm(b) * 2) / cs);      // two CTAs per SM, cs CTAs per cluster
             int chain = pick_chain(cbucket[k].size(), slots, max_chain, longest_run(d, cbucket[k]));
             if (force_chain > 0) chain = force_chain;
-            ClassList l = {rl::kClusterClassBase + cs, (int)(k % 2), (int)b->joblist.size(), (int)cbucket[k].size(), c, (int)b->itemoff.size(), 0};
+            ClassList l = {rl::kClusterClassBase + cs, (int)(k % 3), (int)b->joblist.size(), (int)cbucket[k].size(), c, (int)b->itemoff.size(), 0};
             int run = 0, last_t = -1;
             for (size_t q = 0; q < cbucket[k].size(); ++q) {
                 const int t = d->jobs[cbucket[k][q]].track;
@@ -562,7 +562,8 @@ int rl_plan_for_track(int64_t n, int32_t closed, int32_t max_cs, int32_t* thread
     *threads = 0; *spt = 0; *cluster_ctas = 0;
     const int cls = (n <= (1ll << 30)) ? rl::class_for_n((int)n) : -1;     // the same calls plan_batch makes
     if (cls >= 0) { *threads = rl::kClasses[cls].T; *spt = rl::kClasses[cls].K; return RL_OK; }
-    const int cs = closed ? rl::cluster_size_for_n(n, 0, max_cs >= 16 ? 16 : 8) : 0;
+    (void)closed;     // open and closed tracks are covered alike
+    const int cs = rl::cluster_size_for_n(n, 0, max_cs >= 16 ? 16 : 8);
     if (cs <= 0) return RL_ERR_UNSUPPORTED;
     *threads = 256; *spt = 8; *cluster_ctas = cs;
     return RL_OK;

@@ -17,7 +17,8 @@
 // box hierarchy per tile and runs the same exact FP64 ray / distance searches as the single-CTA fast path
 // (ray_scan / dist_scan); every CTA does this for its own samples only, with no cluster traffic.
 //
-// Closed tracks only (is_closed_track = true in every BASELINE config; open long tracks -> RL_ERR_UNSUPPORTED).
+// Closed tracks (is_closed_track = true in every BASELINE config) and, MODE = open, open ones: the one-sided end stencils
+// exist in the first / last chunk only.
 #pragma once
 #include "raceline_kernels.cuh"
 
@@ -157,15 +158,30 @@ struct PathView {
     const double2* sP;
     const double2* halo;   // [0] = point before the chunk, [1] = point after the chunk
     int Nloc;
+    bool openL = false, openR = false;   // OPEN track: this chunk starts at the first / ends at the last sample (one-sided there)
     __device__ __forceinline__ double2 at(int il) const { return (il < 0) ? halo[0] : ((il >= Nloc) ? halo[1] : sP[il]); }
 };
 __device__ __forceinline__ void normal_c(const PathView& pv, int il, double& nx, double& ny)
 {
+    if (pv.openL && il == 0) { normal_from_tangent(pv.sP[1].x - pv.sP[0].x, pv.sP[1].y - pv.sP[0].y, nx, ny); return; }           // main.cpp:586
+    if (pv.openR && il == pv.Nloc - 1) { normal_from_tangent(pv.sP[il].x - pv.sP[il - 1].x, pv.sP[il].y - pv.sP[il - 1].y, nx, ny); return; }
     const double2 Pm = pv.at(il - 1), Pp = pv.at(il + 1);
     normal_from_tangent((Pp.x - Pm.x) * 0.5, (Pp.y - Pm.y) * 0.5, nx, ny);   // main.cpp:584-592
 }
 __device__ __forceinline__ void derivs_c(const PathView& pv, int il, const HStep& H, double& xp, double& yp, double& xpp, double& ypp)
 {
+    const double2* sP = pv.sP;
+    if (pv.openL && il == 0) {              // the `deriv` lambda at the ends of an open track, main.cpp:604-613 (a chunk has >= 512 samples)
+        xp = (sP[1].x - sP[0].x) * H.inv_h; yp = (sP[1].y - sP[0].y) * H.inv_h;
+        xpp = (sP[2].x - 2 * sP[1].x + sP[0].x) * H.invh2; ypp = (sP[2].y - 2 * sP[1].y + sP[0].y) * H.invh2;
+        return;
+    }
+    if (pv.openR && il == pv.Nloc - 1) {
+        const int n = pv.Nloc;
+        xp = (sP[n - 1].x - sP[n - 2].x) * H.inv_h; yp = (sP[n - 1].y - sP[n - 2].y) * H.inv_h;
+        xpp = (sP[n - 1].x - 2 * sP[n - 2].x + sP[n - 3].x) * H.invh2; ypp = (sP[n - 1].y - 2 * sP[n - 2].y + sP[n - 3].y) * H.invh2;
+        return;
+    }
     derivs_central(pv.at(il - 1), pv.at(il), pv.at(il + 1), H, xp, yp, xpp, ypp);
 }
 // publish the chunk's end points into the neighbours' halo slots (followed by a cluster barrier)
@@ -372,7 +388,7 @@ __device__ __forceinline__ PgdOut pgd_outer_c(const Part& pt, const Clu& cl, con
 // sX: 6*(T+1) doubles.  Index T of each array is the neighbour CTA's edge thread.
 template <int K>
 __device__ __forceinline__ void vprofile_c(const Part& pt, const Clu& cl, const VPar& q, const double (&kap)[K], double (&v)[K],
-                                           int max_iters, double* sX, int* sFlag, int& fslot, int& rounds)
+                                           int max_iters, double* sX, int* sFlag, int& fslot, int& rounds, bool closed = true)
 {
     constexpr int T = kcT, S = kcT + 1;
     double* sVL = sX;            // [2][S] last-slot value of each thread; [T] = last thread of the left neighbour CTA
@@ -435,7 +451,7 @@ __device__ __forceinline__ void vprofile_c(const Part& pt, const Clu& cl, const 
             if (!cluster_or(changed, sFlag, fslot, cl, tid, pt.lane)) break;
         }
         // closed-loop wrap: v[0] = min(v[0], f_acc(v[N-1])), main.cpp:834-839
-        if (gfirst) v[0] = fmin(v[0], f_acc(q, sVL[b * S + iL], kapL));
+        if (gfirst && closed) v[0] = fmin(v[0], f_acc(q, sVL[b * S + iL], kapL));
 #pragma unroll
         for (int k = 0; k < K; ++k) if (k < cnt && v[k] != v0[k]) chg_iter = true;
         // ---------------- backward sweep (main.cpp:841-845) ----------------
@@ -465,7 +481,7 @@ __device__ __forceinline__ void vprofile_c(const Part& pt, const Clu& cl, const 
             if (!cluster_or(changed, sFlag, fslot, cl, tid, pt.lane)) break;
         }
         // closed-loop wrap: v[N-1] = min(v[N-1], f_brk(v[0])), main.cpp:846-850
-        if (glast) {
+        if (glast && closed) {
             const double w = f_brk(q, sVF[b * S + iR], kapR);
 #pragma unroll
             for (int k = 0; k < K; ++k) if (k == cnt - 1) v[k] = fmin(v[k], w);
@@ -479,7 +495,7 @@ __device__ __forceinline__ void vprofile_c(const Part& pt, const Clu& cl, const 
 // ax and lap time, main.cpp:854-860 (closed track: the last sample's successor is sample 0)
 template <int K>
 __device__ __forceinline__ double lap_and_ax_c(const Part& pt, const Clu& cl, const VPar& q, const double (&v)[K], double (&ax)[K],
-                                               double* sX, double* sRedPh)
+                                               double* sX, double* sRedPh, bool closed = true)
 {
     constexpr int T = kcT;
     double* sVF = sX;   // [T+1]
@@ -493,7 +509,7 @@ __device__ __forceinline__ double lap_and_ax_c(const Part& pt, const Clu& cl, co
         ax[k] = 0.0;
         if (k < pt.cnt) {
             const double v0 = v[k];
-            double v1 = vnext_edge;
+            double v1 = (!closed && cl.rank == cl.CS - 1 && pt.tid == T - 1) ? v0 : vnext_edge;   // open: j = i at the last sample (main.cpp:856)
             if (k + 1 < K) { if (k + 1 < pt.cnt) v1 = v[k + 1]; }
             ax[k] = (v1 * v1 - v0 * v0) / (2.0 * q.h);
             t += q.h / fmax(1e-6, v0);
@@ -1238,6 +1254,7 @@ __device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const Path
 {
     constexpr int T = kcT, NP = kcT * K;
     const int Nl = pv.Nloc, tid = pt.tid;
+    const int closed_bits = (pv.openL ? 2 : 0) | (pv.openR ? 4 : 0) | ((!pv.openL && !pv.openR) ? 1 : 0);   // see corridor_update_sample<LOCAL>
     const int M[2] = {(int)(segO0 - segI0), (int)(segE - segO0)};
 #pragma unroll
     for (int j = 0; j < K; ++j) { loc[j] = 0.0; hic[j] = 0.0; }
@@ -1320,7 +1337,7 @@ __device__ __forceinline__ unsigned corridor_update_c(const Part& pt, const Path
         c.gcenter = gcenter; c.gcert = gcert; c.gapex = gapex;
         c.ox = org.x; c.oy = org.y; c.guard = guard; c.N = Nl; c.M0 = M[0]; c.M1 = M[1]; c.rf0 = sMisc[8] & 1; c.rf1 = sMisc[9] & 1;
         c.mr0 = __int_as_float(sMisc[10]); c.mr1 = __int_as_float(sMisc[11]);
-        c.parity_ok = parity_ok; c.closed = true;
+        c.parity_ok = parity_ok; c.closed = closed_bits;
         c.base0 = basev[0]; c.base1 = basev[1]; c.len0 = nseg[0]; c.len1 = nseg[1];
         c.gs0 = gseg + 4 * segI0;   // ring 1's segment records follow ring 0's (segO0 = segI0 + M0)
     }
@@ -1358,7 +1375,8 @@ __global__ void __launch_bounds__(kcT, 2)
 solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const int* __restrict__ item_off, int n_items)
 {
     constexpr int T = kcT, NP = kcT * K;
-    constexpr bool EXACT = (MODE == kModeExact);
+    constexpr bool EXACT = (MODE == kModeExact), OPEN = (MODE == kModeOpen);
+    constexpr bool closed = !OPEN;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* sP = reinterpret_cast<double2*>(smem_raw);
     double* sB = reinterpret_cast<double*>(smem_raw + (size_t)NP * 16);
@@ -1428,9 +1446,11 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
         pt.tR = (tid == T - 1) ? 0 : tid + 1;
         pt.cntL = EXACT ? K : (pt.tL < nfull ? Kc : Kc - 1);
         pt.srcL = (pt.lane + 31) & 31; pt.srcR = (pt.lane + 1) & 31;
+        pt.first_chunk = (cl.rank == 0); pt.last_chunk = (cl.rank == cl.CS - 1);
     }
     const int tid = pt.tid, cnt = pt.cnt, start = pt.start;
     PathView pv; pv.sP = sP; pv.halo = sHalo; pv.Nloc = Nl;
+    pv.openL = OPEN && pt.first_chunk; pv.openR = OPEN && pt.last_chunk;
 
     if (tid == 0) {
         if (cl.rank == 0) {
@@ -1569,9 +1589,9 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             for (int k = 0; k < K; ++k) kap[k] = (k < cnt) ? N0[k] / Wd[k] : 0.0;    // kappa, main.cpp:618
             fill_vpar();       // region B is free since the barrier that ended staged_bounds_home
             block_sync<T>();
-            vprofile_c<K>(pt, cl, q, kap, vv, C.max_vpass_iters, sB, sFlag, fslot, vrounds);
+            vprofile_c<K>(pt, cl, q, kap, vv, C.max_vpass_iters, sB, sFlag, fslot, vrounds, closed);
             block_sync<T>();
-            lap_outer = lap_and_ax_c<K>(pt, cl, q, vv, axd, sB, sRed + ph * kcRedStride);
+            lap_outer = lap_and_ax_c<K>(pt, cl, q, vv, axd, sB, sRed + ph * kcRedStride, closed);
             ph ^= 1;
             double v_avg = 0.0;
             if (C.time_weight_use_inv_v) {            // main.cpp:951
@@ -1616,6 +1636,11 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
                     c0 = gw * N0[k];
                     const double c1 = gw * A1[k] * inv2h, c2 = gw * A2[k] * invh2;
                     cp = c1 + c2; cm = c2 - c1;
+                    if (OPEN) {   // DiffOpsOpen, main.cpp:563-575: D1 one-sided with 1/h at the ends, D2 zero there
+                        const int gi = cl.n0 + start + k;
+                        if (gi == 0) { cp = 2.0 * c1; cm = 0.0; }
+                        else if (gi == N - 1) { cp = 0.0; cm = -2.0 * c1; }
+                    }
                     if (k == 0) { f0 = c0; fp = cp; fm = cm; }
                     l0 = c0; lp = cp; lm = cm;
                 }
@@ -1639,6 +1664,10 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             ld_pair<T>(pair_base_a(sB + NP, NP, pt.tR), pair_base_b(sB + NP, NP, pt.tR), 0, cR[1], cR[2]);
             if (tid == 0) { cL[0] = sCoef[0]; cL[1] = sCoef[1]; cL[2] = sCoef[2]; }
             if (tid == T - 1) { cR[0] = sCoef[4]; cR[1] = sCoef[5]; cR[2] = sCoef[6]; }
+            if (OPEN) {   // nothing beyond the two ends of an open track
+                if (tid == 0 && pt.first_chunk) { cL[0] = 0.0; cL[1] = 0.0; cL[2] = 0.0; }
+                if (tid == T - 1 && pt.last_chunk) { cR[0] = 0.0; cR[1] = 0.0; cR[2] = 0.0; }
+            }
         }
         if (!EXACT) {
             // the first unused slot mirrors the right neighbour's first sample (position cnt+1 of the window)
@@ -1768,9 +1797,9 @@ solve_cluster_kernel(const DevBatch B, const int* __restrict__ job_list, const i
             block_sync<T>();
             fill_vpar();
             block_sync<T>();
-            vprofile_c<K>(pt, cl, q, kap, vv, C.max_vpass_iters, sB, sFlag, fslot, vrounds);
+            vprofile_c<K>(pt, cl, q, kap, vv, C.max_vpass_iters, sB, sFlag, fslot, vrounds, closed);
             block_sync<T>();
-            lap = lap_and_ax_c<K>(pt, cl, q, vv, axd, sB, sRed + ph * kcRedStride);
+            lap = lap_and_ax_c<K>(pt, cl, q, vv, axd, sB, sRed + ph * kcRedStride, closed);
             ph ^= 1;
 #pragma unroll
             for (int k = 0; k < K; ++k)
@@ -1816,6 +1845,7 @@ int launch_solve_cluster(const DevBatch& B, const int* job_list, const int* item
     if (cs > cluster_max_size()) return (int)cudaErrorInvalidConfiguration;
     cudaError_t e;
     if (mode == 1) e = cudaLaunchKernelEx(&cfg, solve_cluster_kernel<K, 1>, B, job_list, item_off, n_items);
+    else if (mode == 2) e = cudaLaunchKernelEx(&cfg, solve_cluster_kernel<K, 2>, B, job_list, item_off, n_items);
     else e = cudaLaunchKernelEx(&cfg, solve_cluster_kernel<K, 0>, B, job_list, item_off, n_items);
     return (int)e;
 }
@@ -1828,10 +1858,12 @@ int configure_solve_cluster()
     const int smem = (int)smem_bytes_cluster(8);
     cudaError_t e = cudaFuncSetAttribute(solve_cluster_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_cluster_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     g_cluster_max = 8;
     if (cudaFuncSetAttribute(solve_cluster_kernel<8, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-        cudaFuncSetAttribute(solve_cluster_kernel<8, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaFuncSetAttribute(solve_cluster_kernel<8, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(solve_cluster_kernel<8, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(16); cfg.blockDim = dim3(kcT); cfg.dynamicSmemBytes = (size_t)smem;
         cudaLaunchAttribute at[1];

@@ -201,6 +201,8 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* sred, i
 // how the N samples of a job are blocked over the T threads of its CTA
 struct Part {
     int N, Tact, cnt, start, tL, tR, cntL, srcL, srcR, tid, lane, warp;
+    // open tracks on a cluster: only the first / last chunk holds an end of the track (always true in solve_kernel)
+    bool first_chunk = true, last_chunk = true;
 };
 
 // ---- per-sample geometry ---------------------------------------------------------------------------
@@ -489,7 +491,7 @@ __device__ __forceinline__ void eval_window(const double (&x)[K], const Halo& hh
     // values a[-1] := a[0], a[N] := a[N-1], zero stencil coefficients on the ghosts and end coefficients built by
     // the kernel, zhat keeps the closed form; the smoothing term gets weight 4 on the end samples
     // ((a1-a0)/h = 2 d/(2h)) and ghost terms e[-1] := -e[0], e[N] := -e[N-1], which is exactly D1^T D1.
-    const bool endL = OPEN && (pt.tid == 0), endR = OPEN && (pt.tid == pt.Tact - 1);
+    const bool endL = OPEN && (pt.tid == 0) && pt.first_chunk, endR = OPEN && (pt.tid == pt.Tact - 1) && pt.last_chunk;
     double w[K + 4];
     w[0] = hh.l0; w[1] = hh.l1;
 #pragma unroll
@@ -1850,9 +1852,14 @@ __device__ __noinline__ UpdRes corridor_update_sample(int i, double cx0, double 
     double nx, ny;
     if (LOCAL) {   // the chunk's neighbours' end points live in the halo slots (closed track)
         const double2* hl = reinterpret_cast<const double2*>(smem_raw + c.oHalo);
-        const double2 Pm = (i == 0) ? hl[0] : sP[i - 1], Pp = (i == c.N - 1) ? hl[1] : sP[i + 1];
-        normal_from_tangent((Pp.x - Pm.x) * 0.5, (Pp.y - Pm.y) * 0.5, nx, ny);
-    } else normal_at(sP, i, c.N, c.closed, nx, ny);
+        // c.closed: bit 0 closed track, bit 1 / 2: this chunk holds the first / last sample of an OPEN track (one-sided there)
+        if ((c.closed & 2) && i == 0) normal_from_tangent(sP[1].x - sP[0].x, sP[1].y - sP[0].y, nx, ny);
+        else if ((c.closed & 4) && i == c.N - 1) normal_from_tangent(sP[i].x - sP[i - 1].x, sP[i].y - sP[i - 1].y, nx, ny);
+        else {
+            const double2 Pm = (i == 0) ? hl[0] : sP[i - 1], Pp = (i == c.N - 1) ? hl[1] : sP[i + 1];
+            normal_from_tangent((Pp.x - Pm.x) * 0.5, (Pp.y - Pm.y) * 0.5, nx, ny);
+        }
+    } else normal_at(sP, i, c.N, (c.closed & 1) != 0, nx, ny);
     const unsigned hw = reinterpret_cast<const unsigned*>(smem_raw + c.oHint)[i];
     const unsigned cw = reinterpret_cast<const unsigned short*>(smem_raw + c.oClr)[i];
     // upper bound of the sample's displacement from the centre line, in FP32: the components are rounded up, the few

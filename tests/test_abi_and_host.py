@@ -205,6 +205,6 @@ def test_size_class_plan_boundaries():
     assert plan(4097) == (0, 256, 8, 4) and plan(8192) == (0, 256, 8, 4) and plan(8193) == (0, 256, 8, 8)
     assert plan(16384) == (0, 256, 8, 8) and plan(16385) == (0, 256, 8, 16) and plan(32768) == (0, 256, 8, 16)
     assert plan(16385, max_cs=8)[0] == rl.RL_ERR_UNSUPPORTED and plan(32769)[0] == rl.RL_ERR_UNSUPPORTED
-    assert plan(4097, closed=0)[0] == rl.RL_ERR_UNSUPPORTED          # open tracks: single-CTA kernels only
+    assert plan(4097, closed=0) == (0, 256, 8, 4) and plan(20000, closed=0) == (0, 256, 8, 16)   # open tracks take clusters too
     assert plan(-1)[0] == rl.RL_ERR_ARG
     assert L.rl_plan_for_track(100, 1, 8, None, None, None) == rl.RL_ERR_ARG

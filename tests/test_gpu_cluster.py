@@ -157,3 +157,36 @@ def test_few_sample_search_equals_tile_streaming_bit_for_bit(ctx, cs, n):
         if ra.v is not None:
             assert np.array_equal(ra.v, rb.v) and np.array_equal(ra.ax, rb.ax) and ra.lap_time == rb.lap_time
         assert ra.stats.exist_scans > 0 and rb.stats.exist_scans > 0
+
+
+def _open_arc(n, seed):
+    """an arc of a synthetic track as an OPEN path: the first n samples, rings cut at the same place (polylines)"""
+    center, seg, L, m = rl.synth_tracks(1, n + 8, seed_base=seed)
+    center, seg = center.reshape(n + 8, 2), seg.reshape(2, m, 4)
+    keep = max(3, int(m * n / (n + 8)))
+    return rl.Track(center[:n], rl.polyline_edges(seg[0, :keep + 2, :2]), rl.polyline_edges(seg[1, :keep + 2, :2]),
+                    L[0] * n / (n + 8), closed=False)
+
+
+@pytest.mark.parametrize("cs,n", [(2, 1100), (2, 4096), (4, 3000), (8, 4100), (0, 5000)])
+def test_open_tracks_on_the_cluster_path(ctx, cs, n):
+    """DiffOpsOpen (main.cpp:560-579) on a thread-block cluster: one-sided ends in the first / last chunk only, no wrap in
+    the v(s) sweeps, ax = 0 at the last sample.  Forced clusters on open arcs the single-CTA open kernel also solves
+    (oracle + the single-CTA result), and one open track longer than 4096 samples through the natural dispatch."""
+    tr = _open_arc(n, 0x0E00 + n)
+    cfg = rl.Config()
+    jobs = [(0, 0, MC), (0, 0, MT)]
+    ctx.set_option("force_cluster", cs)
+    try:
+        res = rl.solve_batch([tr], [cfg], jobs, ctx=ctx)
+    finally:
+        ctx.set_option("force_cluster", 0)
+    for (t, _, st), r in zip(jobs, res):
+        _check(r, tr, st, cfg, ("open cluster", cs, n, st))
+    if n <= 4096:
+        res1 = rl.solve_batch([tr], [cfg], jobs, ctx=ctx)
+        for a, b in zip(res, res1):
+            assert a.stats.accepted == b.stats.accepted and a.stats.backtracks == b.stats.backtracks
+            assert np.max(np.abs(a.alpha_total - b.alpha_total)) < 1e-9
+            if a.v is not None and a.lap_time:
+                assert abs(a.lap_time - b.lap_time) <= 1e-9 * b.lap_time

@@ -180,7 +180,7 @@ def test_errors_and_unsupported(ctx, goldens):
     with pytest.raises(rl.RacelineError) as e:
         rl.solve_batch([big], [rl.Config()], [(0, 0, MC)], ctx=ctx)
     assert e.value.status == rl.RL_ERR_UNSUPPORTED
-    big_open = rl.Track(np.zeros((5000, 2)), tr.inner_seg, tr.outer_seg, 9000.0, closed=False)   # open long tracks: not covered
+    big_open = rl.Track(np.zeros((40000, 2)), tr.inner_seg, tr.outer_seg, 72000.0, closed=False)   # open tracks have the same cap
     with pytest.raises(rl.RacelineError) as e:
         rl.solve_batch([big_open], [rl.Config()], [(0, 0, MC)], ctx=ctx)
     assert e.value.status == rl.RL_ERR_UNSUPPORTED

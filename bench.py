@@ -501,6 +501,8 @@ def bench_ours(args):
     ctx.set_stream(stream.cuda_stream)
     if args.solve_chunks:
         ctx.set_option("solve_chunks", args.solve_chunks)
+    if args.chunk_streams:
+        ctx.set_option("chunk_streams", args.chunk_streams)
     dev = rl.DeviceBatch(ctx, pb)
 
     def barrier():
@@ -714,6 +716,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--solve-chunks", type=int, default=0, help="development: rl_set_option('solve_chunks')")
+    ap.add_argument("--chunk-streams", type=int, default=0, help="development: rl_set_option('chunk_streams')")
     args = ap.parse_args()
     if args.tracks_per_gpu > 0:
         args.tracks_total = args.tracks_per_gpu * int(os.environ.get("WORLD_SIZE", "1"))

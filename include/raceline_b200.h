@@ -184,6 +184,9 @@ int rl_set_stream(rl_ctx* ctx, void* cuda_stream);
 /*
  * Tuning knobs and test hooks of the host plan (0 = automatic):
  *   "solve_chunks"  pipeline chunks of rl_solve_batch (1..16)
+ *   "chunk_streams" how those chunks are spread over the kernel streams: 1 = round robin over the device's stream
+ *                   priority levels, 2 = a stream per chunk with priorities that never rise from one chunk to the
+ *                   next, 3 = streams of one priority (order of launch only)
  *   "max_chain"     longest chain of consecutive jobs on one track that one CTA / cluster works through
  *   "force_chain"   form chains of exactly this length whatever the batch size (tests)
  *   "force_cluster" route closed tracks of any length through the cluster kernel with this many CTAs (tests)

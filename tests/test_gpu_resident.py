@@ -103,23 +103,27 @@ def test_v_and_ax_rows_of_mincurv_jobs_are_left_untouched(ctx, layout):
 
 
 def test_many_pipeline_chunks_equal_one(ctx):
-    """rl_solve_batch with 1 and with 16 pipeline chunks: bit-identical results (chunks only cut the job list)."""
+    """rl_solve_batch with 1 and with 16 pipeline chunks, the 16 spread over the kernel streams in each of the three
+    ways rl_set_option("chunk_streams") knows: bit-identical results (chunks only cut the job list)."""
     tr = _tracks(40, 128, 0xD00D)
     jobs = [(t, 0, st) for t in range(40) for st in (MC, MT)]
     outs = []
-    for chunks in (1, 16):
+    for chunks, streams in ((1, 0), (16, 0), (16, 1), (16, 2), (16, 3)):
         ctx.set_option("solve_chunks", chunks)
+        ctx.set_option("chunk_streams", streams)
         pb = rl.PackedBatch(tr, [rl.Config().to_params()], jobs)
         ctx.solve_batch(pb)
         outs.append(pb)
     ctx.set_option("solve_chunks", 0)
-    a, b = outs
-    assert np.array_equal(a.out_xy, b.out_xy) and np.array_equal(a.out_alpha_total, b.out_alpha_total)
-    for j, (_, _, st) in enumerate(jobs):
-        if st == MT:
-            assert a.out_stats[j].lap_time == b.out_stats[j].lap_time
-            lo, hi = int(a.job_off[j]), int(a.job_off[j + 1])
-            assert np.array_equal(a.out_v[lo:hi], b.out_v[lo:hi])
+    ctx.set_option("chunk_streams", 0)
+    a = outs[0]
+    for b in outs[1:]:
+        assert np.array_equal(a.out_xy, b.out_xy) and np.array_equal(a.out_alpha_total, b.out_alpha_total)
+        for j, (_, _, st) in enumerate(jobs):
+            if st == MT:
+                assert a.out_stats[j].lap_time == b.out_stats[j].lap_time
+                lo, hi = int(a.job_off[j]), int(a.job_off[j + 1])
+                assert np.array_equal(a.out_v[lo:hi], b.out_v[lo:hi])
     with pytest.raises(rl.RacelineError):
         ctx.set_option("no_such_option", 1)
 

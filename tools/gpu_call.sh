@@ -1,10 +1,11 @@
 #!/bin/bash
-# development helper: what one gpurun call runs (edit per experiment); this is the round's final validation
+# development helper: what one gpurun call runs (edit per experiment); here: how the pipeline chunks of rl_solve_batch
+# are spread over the kernel streams (rl_set_option "chunk_streams"), full 65,536 tracks
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.txt 2>&1
-timeout 2400 python -m pytest tests -m gpu -q > $O/pytest_gpu_r02_final.txt 2>&1
-timeout 900 python bench.py --tracks-total 8192 --steps 3 --warmup 3 --no-cpu-baseline --long-tracks-total 1184 --extra-steps 2 > $O/q_bench.json 2> $O/q_bench.err
+for m in 2 3 1; do
+  timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --chunk-streams $m > $O/cstreams_$m.json 2> $O/cstreams_$m.err
+done
 ls -la $O > $O/ls.txt

@@ -408,13 +408,16 @@ def run_extras(args, rl, ctx, stream, fp64_peak, world, rank, dist):
         except Exception:
             hbm_peak = None
         pg = rl.PackedGeom(mids, [N_SAMPLES] * ng, inner, outer, closed=True, cfg=cfg, pool=gpool)
+        ctx.set_option("geom_chunks", 1)    # one upload | the two kernels | one download: the kernels' own device time
+        pg.run(ctx); pg.run(ctx)
+        kms = ctx.last_kernel_ms()
+        ctx.set_option("geom_chunks", 0)    # the call as a user gets it: a pipeline of track ranges
         walls = []
         for it in range(4):
             t0 = time.perf_counter()
             pg.run(ctx)                     # one rl_centerline_geom_batch call: pinned H2D + two kernels + pinned D2H
             walls.append(time.perf_counter() - t0)
         wall = min(walls[1:])
-        kms = ctx.last_kernel_ms()
         rows = ng * N_SAMPLES
         # algorithmic HBM bytes per track: mid points and both rings in (16 B + 2 x 32 B per cone), 9 doubles per row out
         alg_bytes = ng * (16.0 * M_PER_RING + 64.0 * M_PER_RING + 72.0 * N_SAMPLES)
@@ -424,7 +427,8 @@ def run_extras(args, rl, ctx, stream, fp64_peak, world, rank, dist):
                        "rows_per_s": rows / (kms * 1e-3),
                        "e2e": {"value": ng / wall, "unit": "tracks/s", "ms_wall": wall * 1e3, "h2d_bytes_per_step": pg.h2d_bytes,
                                "d2h_bytes_per_step": pg.d2h_bytes,
-                               "note": "one rl_centerline_geom_batch call: pinned H2D + kernels + pinned D2H of 9 output columns"},
+                               "note": "one rl_centerline_geom_batch call: pinned H2D + kernels + pinned D2H of 9 output columns, "
+                                       "pipelined over 8 track ranges"},
                        "roofline": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": (alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                                     "note": "two kernels (centerline_kernel, ring_distance_kernel); FP64 ray tests and a sequential "

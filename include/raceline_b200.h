@@ -187,6 +187,8 @@ int rl_set_stream(rl_ctx* ctx, void* cuda_stream);
  *   "chunk_streams" how those chunks are spread over the kernel streams: 1 = round robin over the device's stream
  *                   priority levels, 2 = a stream per chunk with priorities that never rise from one chunk to the
  *                   next, 3 = streams of one priority (order of launch only)
+ *   "geom_chunks"   track ranges rl_centerline_geom_batch pipelines (upload | kernels | download); automatic: one per
+ *                   1024 tracks, at most 8; 1 = one upload, the kernels, one download
  *   "max_chain"     longest chain of consecutive jobs on one track that one CTA / cluster works through
  *   "force_chain"   form chains of exactly this length whatever the batch size (tests)
  *   "force_cluster" route closed tracks of any length through the cluster kernel with this many CTAs (tests)
@@ -321,7 +323,8 @@ int rl_synth_tracks(uint64_t seed_base, int64_t first_id, int n_tracks, int n_sa
  */
 int rl_debug_check_failures(rl_ctx* ctx, uint64_t* out2);
 /* device time (CUDA events on the context's stream) of the kernels of the last rl_centerline_geom_batch call on this
- * context, in milliseconds, copies excluded; -1 before the first call */
+ * context, in milliseconds, copies excluded; -1 before the first call and after a call that ran as a pipeline of track
+ * ranges (kernels and copies overlap there; option "geom_chunks" = 1 gives the unpipelined call) */
 double rl_last_kernel_ms(rl_ctx* ctx);
 /* measured DFMA throughput of this device in TFLOP/s (2 flop per FMA); the FP64 roofline denominator */
 int rl_measure_fp64_peak(rl_ctx* ctx, double* tflops);

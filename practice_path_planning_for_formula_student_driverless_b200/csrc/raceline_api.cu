@@ -31,7 +31,7 @@ struct rl_ctx {
     // may be shared by host threads (calls are serialised); use one context per thread for concurrency
     std::recursive_mutex mu;
     // tuning knobs and test hooks (rl_set_option); 0 = automatic
-    int opt_solve_chunks = 0, opt_chunk_streams = 0, opt_max_chain = 0, opt_force_chain = 0, opt_force_cluster = 0, opt_no_few_search = 0;
+    int opt_solve_chunks = 0, opt_chunk_streams = 0, opt_geom_chunks = 0, opt_max_chain = 0, opt_force_chain = 0, opt_force_cluster = 0, opt_no_few_search = 0;
     bool pipeline_ready = false;
     struct GeomBufs* geom = nullptr;   // device buffers of rl_centerline_geom_batch, kept between calls (grow only)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // timing events around the kernels of the last geometry call
@@ -545,6 +545,7 @@ int rl_set_option(rl_ctx* c, const char* name, int64_t value)
     const int v = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     if (!std::strcmp(name, "solve_chunks")) c->opt_solve_chunks = std::min(v, kMaxChunks);
     else if (!std::strcmp(name, "chunk_streams")) c->opt_chunk_streams = std::min(v, 3);
+    else if (!std::strcmp(name, "geom_chunks")) c->opt_geom_chunks = std::min(v, kMaxChunks);
     else if (!std::strcmp(name, "max_chain")) c->opt_max_chain = v;
     else if (!std::strcmp(name, "force_chain")) c->opt_force_chain = v;
     else if (!std::strcmp(name, "force_cluster")) c->opt_force_cluster = v;
@@ -923,6 +924,64 @@ int rl_geom_row_offsets(const rl_geom_desc* d, int64_t* off)
     return RL_OK;
 }
 
+// rl_centerline_geom_batch on a large batch: the tracks are cut into n_chunks ranges; range k's mid points and rings go up
+// while range k-1's two kernels run and range k-2's rows come down (the streams and events of rl_solve_batch's pipeline;
+// a kernel stream per range, so the ranges finish in order).  The per-track arrays are already on the device; the
+// kernels index them by track, everything else by the absolute offsets they hold, so a range is the same GeomBatch
+// with the per-track pointers moved up.
+static int geom_pipeline(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out* o, const rl::GeomBatch& G,
+                         const std::vector<long long>& row_off, int n_chunks, int max_pts)
+{
+    cudaStream_t s = c->stream;
+    const int nt = d->n_tracks;
+    RL_CUDA(c, cudaEventRecord(c->ev_start, s));
+    RL_CUDA(c, cudaStreamWaitEvent(c->s_in, c->ev_start, 0));
+    RL_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_start, 0));
+    for (int k = 0; k < n_chunks; ++k) RL_CUDA(c, cudaStreamWaitEvent(c->s_k[k], c->ev_start, 0));
+    for (int k = 0; k < n_chunks; ++k) {
+        const int t0 = (int)(((long long)nt * k) / n_chunks), t1 = (int)(((long long)nt * (k + 1)) / n_chunks);
+        if (t1 <= t0) continue;
+        const long long m0 = d->mid_off[t0], m1 = d->mid_off[t1], g0 = d->seg_off[2 * t0], g1 = d->seg_off[2 * t1];
+        RL_CUDA(c, cudaMemcpyAsync(const_cast<double*>(G.mids_xy) + 2 * m0, d->mids_xy + 2 * m0, sizeof(double) * 2 * (size_t)(m1 - m0), cudaMemcpyHostToDevice, c->s_in));
+        if (g1 > g0)
+            RL_CUDA(c, cudaMemcpyAsync(const_cast<double*>(G.seg) + 4 * g0, d->seg + 4 * g0, sizeof(double) * 4 * (size_t)(g1 - g0), cudaMemcpyHostToDevice, c->s_in));
+        RL_CUDA(c, cudaEventRecord(c->ev_in[k], c->s_in));
+        cudaStream_t sk = c->s_k[k];
+        RL_CUDA(c, cudaStreamWaitEvent(sk, c->ev_in[k], 0));
+        rl::GeomBatch Gk = G;
+        Gk.mid_off += t0; Gk.samples += t0; Gk.closed += t0; Gk.seg_off += 2 * t0; Gk.row_off += t0;
+        Gk.track_L += t0; Gk.track_s0 += t0;
+        const int e = rl::launch_geom(Gk, t1 - t0, max_pts, sk);
+        if (e != 0) return cuda_fail(c, (cudaError_t)e, "geometry kernels");
+        RL_CUDA(c, cudaEventRecord(c->ev_k[k], sk));
+        RL_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
+        const size_t r0 = (size_t)row_off[t0], nr = (size_t)(row_off[t1] - row_off[t0]);
+        if (nr) {
+            if (o->xy) RL_CUDA(c, cudaMemcpyAsync(o->xy + 2 * r0, G.xy + 2 * r0, 16 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->s_rel) RL_CUDA(c, cudaMemcpyAsync(o->s_rel + r0, G.s_rel + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->heading) RL_CUDA(c, cudaMemcpyAsync(o->heading + r0, G.heading + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->curvature) RL_CUDA(c, cudaMemcpyAsync(o->curvature + r0, G.curvature + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->dist_inner) RL_CUDA(c, cudaMemcpyAsync(o->dist_inner + r0, G.dist_inner + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->dist_outer) RL_CUDA(c, cudaMemcpyAsync(o->dist_outer + r0, G.dist_outer + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->width) RL_CUDA(c, cudaMemcpyAsync(o->width + r0, G.width + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+            if (o->v_kappa) RL_CUDA(c, cudaMemcpyAsync(o->v_kappa + r0, G.v_kappa + r0, 8 * nr, cudaMemcpyDeviceToHost, c->s_out));
+        }
+    }
+    for (int i = 0; i < kMaxChunks + 2; ++i) {
+        cudaStream_t tail = (i < kMaxChunks) ? c->s_k[i] : (i == kMaxChunks ? c->s_in : c->s_out);
+        RL_CUDA(c, cudaEventRecord(c->ev_end[i], tail));
+        RL_CUDA(c, cudaStreamWaitEvent(s, c->ev_end[i], 0));
+    }
+    // the two per-track columns come down once, at the end: callers tend to hold them in pageable memory, and a copy
+    // into pageable memory inside the loop would block the host until that range's kernels are done (no pipeline left)
+    if (o->track_L) RL_CUDA(c, cudaMemcpyAsync(o->track_L, G.track_L, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, s));
+    if (o->track_s0) RL_CUDA(c, cudaMemcpyAsync(o->track_s0, G.track_s0, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, s));
+    RL_CUDA(c, cudaStreamSynchronize(s));
+    RL_CUDA(c, cudaGetLastError());
+    c->last_kernel_ms = -1.f;   // copies and kernels overlap: no separate kernel time (geom_chunks = 1 measures it)
+    return RL_OK;
+}
+
 // pipeline::make_centerline + the per-sample body of pipeline::compute_geom_and_save (main.cpp:1270-1335), batched
 int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out* o)
 {
@@ -979,8 +1038,12 @@ int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out
     RL_CUDA(c, cudaMemcpyAsync(d_mid_off, d->mid_off, sizeof(long long) * ((size_t)nt + 1), cudaMemcpyHostToDevice, s));
     RL_CUDA(c, cudaMemcpyAsync(d_seg_off, d->seg_off, sizeof(long long) * ((size_t)2 * nt + 1), cudaMemcpyHostToDevice, s));
     RL_CUDA(c, cudaMemcpyAsync(d_row_off, row_off.data(), sizeof(long long) * ((size_t)nt + 1), cudaMemcpyHostToDevice, s));
-    RL_CUDA(c, cudaMemcpyAsync(d_mids, d->mids_xy, sizeof(double) * 2 * n_mid, cudaMemcpyHostToDevice, s));
-    if (n_seg) RL_CUDA(c, cudaMemcpyAsync(d_seg, d->seg, sizeof(double) * 4 * n_seg, cudaMemcpyHostToDevice, s));
+    // large batches run as a pipeline of track ranges (geom_pipeline below); rl_set_option("geom_chunks"): 0 = automatic
+    const int n_chunks = std::min(nt, c->opt_geom_chunks > 0 ? c->opt_geom_chunks : std::max(1, std::min(8, nt / 1024)));
+    if (n_chunks <= 1) {
+        RL_CUDA(c, cudaMemcpyAsync(d_mids, d->mids_xy, sizeof(double) * 2 * n_mid, cudaMemcpyHostToDevice, s));
+        if (n_seg) RL_CUDA(c, cudaMemcpyAsync(d_seg, d->seg, sizeof(double) * 4 * n_seg, cudaMemcpyHostToDevice, s));
+    }
     RL_CUDA(c, cudaMemcpyAsync(d_samples, d->samples, sizeof(int) * (size_t)nt, cudaMemcpyHostToDevice, s));
     RL_CUDA(c, cudaMemcpyAsync(d_closed, d->track_closed, sizeof(int) * (size_t)nt, cudaMemcpyHostToDevice, s));
     rl::GeomBatch G;
@@ -990,6 +1053,20 @@ int rl_centerline_geom_batch(rl_ctx* c, const rl_geom_desc* d, const rl_geom_out
     G.xy = d_out; G.s_rel = d_out + 2 * rows; G.heading = G.s_rel + rows; G.curvature = G.heading + rows;
     G.dist_inner = G.curvature + rows; G.dist_outer = G.dist_inner + rows; G.width = G.dist_outer + rows; G.v_kappa = G.width + rows;
     G.track_L = d_L; G.track_s0 = d_s0;
+    if (n_chunks > 1) {
+        int st = ensure_pipeline(c);
+        if (st == RL_OK) st = geom_pipeline(c, d, o, G, row_off, n_chunks, max_pts);
+        if (st != RL_OK) {   // nothing queued by this call may outlive it (the caller's buffers)
+            const std::string keep = c->err;
+            if (c->s_in) cudaStreamSynchronize(c->s_in);
+            if (c->s_out) cudaStreamSynchronize(c->s_out);
+            for (int i = 0; i < kMaxChunks; ++i) if (c->s_k[i]) cudaStreamSynchronize(c->s_k[i]);
+            cudaStreamSynchronize(s);
+            cudaGetLastError();
+            c->err = keep;
+        }
+        return st;
+    }
     RL_CUDA(c, cudaEventRecord(c->ev_t0, s));
     const int e = rl::launch_geom(G, nt, max_pts, s);
     if (e != 0) return cuda_fail(c, (cudaError_t)e, "geometry kernels");

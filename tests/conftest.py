@@ -61,7 +61,7 @@ def _plan_options_back_to_automatic():
     """Tests steer the host plan through rl_set_option on the shared context; none of that may leak into the next test."""
     yield
     for c in _CTX:
-        for name in ("solve_chunks", "chunk_streams", "max_chain", "force_chain", "force_cluster"):
+        for name in ("solve_chunks", "chunk_streams", "geom_chunks", "max_chain", "force_chain", "force_cluster"):
             c.set_option(name, 0)
 
 

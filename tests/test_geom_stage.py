@@ -138,3 +138,23 @@ def test_packed_geom_pinned_reuse_and_kernel_time(ctx):
     assert pg.d2h_bytes == pg.rows * 72 + 16 * len(gs)
     del pg, b
     pool.close(force=True)
+
+
+@pytest.mark.gpu
+def test_geom_batch_pipelined_ranges_equal_one_call(ctx):
+    """rl_centerline_geom_batch as a pipeline of track ranges (what large batches get automatically) against the
+    single upload | kernels | download call on the same batch: every output column and L, s0 bit for bit."""
+    gs = [load_golden(n) for n in GEOM_CASES[:3]] * 4 + [load_golden(GEOM_CASES[0])]          # 13 tracks, ragged shapes
+    args = ([g["mids_xy"] for g in gs], [int(g["samples"]) for g in gs], [g["inner_seg"] for g in gs], [g["outer_seg"] for g in gs])
+    ctx.set_option("geom_chunks", 1)
+    one = rl.centerline_geom_batch(*args, closed=True, ctx=ctx)
+    assert ctx.last_kernel_ms() > 0.0
+    for chunks in (2, 5, 13, 16):
+        ctx.set_option("geom_chunks", chunks)
+        many = rl.centerline_geom_batch(*args, closed=True, ctx=ctx)
+        assert ctx.last_kernel_ms() < 0.0          # kernels and copies overlap: no separate kernel time
+        for a, b in zip(one, many):
+            for col in ("xy", "s", "heading", "curvature", "dist_inner", "dist_outer", "width", "v_kappa"):
+                assert np.array_equal(getattr(a, col), getattr(b, col)), (chunks, col)
+            assert a.L == b.L and a.s0 == b.s0
+    ctx.set_option("geom_chunks", 0)

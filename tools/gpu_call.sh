@@ -1,8 +1,8 @@
 #!/bin/bash
-# development helper: what one gpurun call runs (edit per experiment); here: the bench on all GPUs of the box
+# development helper: what one gpurun call runs (edit per experiment); here: the pipelined geometry batch
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-N=$(nvidia-smi -L | wc -l)
-( time timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 --no-extras > $O/r02_bench_${N}gpu_final.json 2> $O/r02_bench_${N}gpu_final.err ) 2> $O/r02_bench_${N}gpu_final.time
+timeout 300 python -m pytest tests/test_geom_stage.py tests/test_abi_and_host.py -m gpu -q > $O/pytest_geom_pipe.txt 2>&1
+timeout 300 python bench.py --tracks-total 8192 --long-tracks-total 0 --no-cpu-baseline --steps 2 --warmup 3 > $O/geom_pipe_bench.json 2> $O/geom_pipe_bench.err

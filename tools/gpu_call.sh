@@ -1,8 +1,10 @@
 #!/bin/bash
-# development helper: what one gpurun call runs (edit per experiment); here: the pipelined geometry batch
+# development helper: what one gpurun call runs (edit per experiment); this is the round's final validation
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-timeout 300 python -m pytest tests/test_geom_stage.py tests/test_abi_and_host.py -m gpu -q > $O/pytest_geom_pipe.txt 2>&1
-timeout 300 python bench.py --tracks-total 8192 --long-tracks-total 0 --no-cpu-baseline --steps 2 --warmup 3 > $O/geom_pipe_bench.json 2> $O/geom_pipe_bench.err
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.txt 2>&1
+timeout 1200 python -m pytest tests -m gpu -q > $O/pytest_gpu_r02_final.txt 2>&1
+( time timeout 600 python bench.py > $O/r02_bench_final.json 2> $O/r02_bench_final.err ) 2> $O/r02_bench_final.time
+ls -la $O > $O/ls.txt

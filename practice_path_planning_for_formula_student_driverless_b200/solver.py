@@ -295,8 +295,9 @@ class Context:
         lib().rl_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None)
 
     def set_option(self, name: str, value: int):
-        """rl_set_option: tuning knobs / test hooks of the host plan ("solve_chunks", "max_chain", "force_chain",
-        "force_cluster"; 0 = automatic)."""
+        """rl_set_option: tuning knobs / test hooks of the host plan ("solve_chunks", "chunk_streams", "geom_chunks",
+        "max_chain", "force_chain", "force_cluster", "no_few_search", "debug_inject"; 0 = automatic; see
+        include/raceline_b200.h)."""
         self._check(lib().rl_set_option(self._h, name.encode(), int(value)), "rl_set_option")
 
     def _check(self, st, what=""):

@@ -208,3 +208,19 @@ def test_size_class_plan_boundaries():
     assert plan(4097, closed=0) == (0, 256, 8, 4) and plan(20000, closed=0) == (0, 256, 8, 16)   # open tracks take clusters too
     assert plan(-1)[0] == rl.RL_ERR_ARG
     assert L.rl_plan_for_track(100, 1, 8, None, None, None) == rl.RL_ERR_ARG
+
+
+def test_every_option_of_rl_set_option_is_documented_and_reset_between_tests():
+    """The option names rl_set_option accepts (csrc/raceline_api.cu) are exactly the ones the header documents, the
+    Python wrapper's docstring lists them, and the GPU test fixture puts every plan option back to automatic."""
+    src = open(os.path.join(ROOT, "practice_path_planning_for_formula_student_driverless_b200", "csrc", "raceline_api.cu")).read()
+    body = src[src.index("int rl_set_option("):src.index("const char* rl_last_error")]
+    accepted = set(re.findall(r'strcmp\(name, "([a-z_]+)"\)', body))
+    hdr = open(os.path.join(ROOT, "include", "raceline_b200.h")).read()
+    doc = hdr[hdr.index("Tuning knobs and test hooks"):hdr.index("int rl_set_option(")]
+    documented = set(re.findall(r'^ \*   "([a-z_]+)"', doc, flags=re.M))
+    assert accepted == documented, accepted ^ documented
+    assert {"solve_chunks", "chunk_streams", "geom_chunks"} <= accepted
+    conf = open(os.path.join(ROOT, "tests", "conftest.py")).read()
+    reset = set(re.findall(r'"([a-z_]+)"', conf[conf.index("def _plan_options_back_to_automatic"):conf.index("def angle_diff")]))
+    assert accepted - {"no_few_search", "debug_inject"} <= reset, accepted - reset

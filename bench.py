@@ -428,7 +428,7 @@ def run_extras(args, rl, ctx, stream, fp64_peak, world, rank, dist):
                        "e2e": {"value": ng / wall, "unit": "tracks/s", "ms_wall": wall * 1e3, "h2d_bytes_per_step": pg.h2d_bytes,
                                "d2h_bytes_per_step": pg.d2h_bytes,
                                "note": "one rl_centerline_geom_batch call: pinned H2D + kernels + pinned D2H of 9 output columns, "
-                                       "pipelined over 8 track ranges"},
+                                       f"pipelined over {max(1, min(8, ng // 1024))} track range(s)"},
                        "roofline": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": (alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                                     "note": "two kernels (centerline_kernel, ring_distance_kernel); FP64 ray tests and a sequential "
